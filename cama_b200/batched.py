@@ -1,0 +1,207 @@
+"""Batched reprojection of a whole clip: every (frame x camera x vertex) in a handful of launches.
+
+``Reproject(configs, clip_path)(dataset)`` returns what the reference's loop
+
+    for image_idx, instance_map in cm.yield_frame(dataset):
+        maps_2d = cm.project_all_camera(instance_map)
+        frames  = [cam.render_maps(background, maps_2d[cam.camera_name]) for cam in cm.cm_list]
+
+(/root/reference/main.py:57-59 over cama/dataset.py:78-126) produces, as one
+``uint8 [F', C, 540, 960, 3]`` array.  Host side: the F' world->chassis float32 matrices are
+computed exactly like the reference does (pose lookup, float32 cast, ``np.linalg.inv``).  Device
+side: one ``cama_clip_render`` call (csrc/clip.cu).  Static inputs — dense vertices, instance
+colours, camera matrices — are uploaded once per dataset and stay resident.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+from .dataset import ClipManager
+from .reproject import render_bgr_of_class
+from .runtime import CROP_KEYS, get_runtime
+
+_MODES = {"auto": N.CLIP_AUTO, "plane": N.CLIP_PLANE, "binned": N.CLIP_BINNED}
+
+
+def pack_vertices(instances):
+    """instances -> (layout, vertex array, per-vertex ordinal or None, instance BGR [I,3]).
+
+    float32 instances (the normal case) become float4 {x, y, z, bit-cast ordinal}: one aligned
+    16-byte load per vertex.  Anything else is passed as float64 [N,3] + int32 ordinals.
+    """
+    pts = [np.asarray(inst["points"]) for inst in instances]
+    counts = np.array([p.shape[0] for p in pts], dtype=np.int64)
+    ordinal = np.repeat(np.arange(len(pts), dtype=np.int32), counts)
+    bgr = np.array([render_bgr_of_class(inst["class"]) for inst in instances], dtype=np.uint8).reshape(-1, 3)
+    if not pts:
+        return N.VERTEX_F32X4, np.zeros((0, 4), np.float32), None, bgr
+    if all(p.dtype == np.float32 for p in pts):
+        packed = np.empty((int(counts.sum()), 4), dtype=np.float32)
+        packed[:, :3] = np.concatenate(pts, axis=0)
+        packed[:, 3] = ordinal.view(np.float32)
+        return N.VERTEX_F32X4, packed, None, bgr
+    flat = np.concatenate([p.astype(np.float64) for p in pts], axis=0)
+    return N.VERTEX_F64X3, np.ascontiguousarray(flat), ordinal, bgr
+
+
+class _Resident:
+    """Device copies of what does not change from frame to frame."""
+
+    def __init__(self, rt, instances):
+        self.layout, verts, ordinal, bgr = pack_vertices(instances)
+        self.n_vertices = int(verts.shape[0])
+        self.n_instances = len(instances)
+        self.vertices = rt.to_device(verts)
+        self.ordinal = rt.to_device(ordinal) if ordinal is not None else None
+        self.bgr = rt.to_device(bgr)
+
+
+class ClipRenderer:
+    """Thin object around ``cama_clip_render`` for fixed cameras and a fixed output size."""
+
+    def __init__(self, chassis2cam, intrinsics, height, width, crop_box, device=None):
+        self.rt = get_runtime(device)
+        self.chassis2cam = np.ascontiguousarray(chassis2cam, dtype=np.float64).reshape(-1, 16)
+        self.intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float64).reshape(-1, 9)
+        assert self.chassis2cam.shape[0] == self.intrinsics.shape[0]
+        self.n_cams = self.chassis2cam.shape[0]
+        self.height, self.width = int(height), int(width)
+        self.crop_box = [float(v) for v in crop_box]
+        self.capacity = {}            # (resident id, n_frames) -> records per frame that were enough
+        self.last_stats = None
+
+    def resident(self, instances):
+        return _Resident(self.rt, instances)
+
+    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug):
+        d = N.ClipDesc()
+        d.struct_bytes = ctypes.sizeof(N.ClipDesc)
+        d.mode = _MODES[mode] if isinstance(mode, str) else int(mode)
+        d.n_frames, d.n_cams, d.n_instances = n_frames, self.n_cams, res.n_instances
+        d.height, d.width = self.height, self.width
+        d.vertex_layout = res.layout
+        d.n_vertices = res.n_vertices
+        d.vertices = res.vertices.data_ptr() if res.n_vertices else None
+        d.vertex_instance = res.ordinal.data_ptr() if res.ordinal is not None and res.n_vertices else None
+        d.world2chassis = w2c_dev.data_ptr() if n_frames else None
+        d.chassis2cam = N.dptr(self.chassis2cam)
+        d.intrinsics = N.dptr(self.intrinsics)
+        d.crop_box = (ctypes.c_double * 6)(*self.crop_box)
+        d.instance_bgr = res.bgr.data_ptr() if res.n_instances else None
+        d.background = background.data_ptr() if background is not None else None
+        d.frames = frames.data_ptr() if n_frames else None
+        d.crop_counts = debug["crop_counts"].data_ptr() if debug else None
+        d.visible_counts = debug["visible_counts"].data_ptr() if debug else None
+        d.vu_dense = debug["vu_dense"].data_ptr() if debug and debug.get("vu_dense") is not None else None
+        d.record_capacity = int(capacity)
+        return d
+
+    def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False):
+        """Enqueue one clip on the current stream.
+
+        res         _Resident from :meth:`resident`
+        w2c_dev     torch float32 [F,16] (or [F,4,4]) on this device
+        out         optional torch uint8 [F,C,H,W,3] to write into
+        background  optional torch uint8 [F,C,H,W,3] composited under the overlay (may be ``out``)
+        check       read the record counters back (synchronises) and rerun with a larger pool if a
+                    frame overflowed; with ``check=False`` the call is fully asynchronous
+        debug       also return per-instance crop / visibility counts (and dense (v,u) if want_vu)
+        """
+        import torch
+        rt = self.rt
+        n_frames = int(w2c_dev.shape[0])
+        shape = (n_frames, self.n_cams, self.height, self.width, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=rt.device)
+        assert tuple(out.shape) == shape and out.dtype == torch.uint8 and out.is_contiguous()
+        dbg = None
+        if debug:
+            dbg = {"crop_counts": torch.zeros((n_frames, res.n_instances), dtype=torch.int32, device=rt.device),
+                   "visible_counts": torch.zeros((n_frames, self.n_cams, res.n_instances), dtype=torch.int32, device=rt.device),
+                   "vu_dense": torch.empty((n_frames, self.n_cams, res.n_vertices, 2), dtype=torch.float64, device=rt.device)
+                   if want_vu else None}
+        key = (id(res), n_frames)
+        capacity = self.capacity.get(key, 0)
+        for attempt in range(3):
+            desc = self._desc(res, w2c_dev, n_frames, out, background, mode, capacity, dbg)
+            need = ctypes.c_size_t()
+            N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+            ws = rt.scratch("clip", need.value)
+            N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
+            if not check:
+                break
+            stats = N.ClipStats()
+            code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
+            self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
+            if code == N.CAMA_E_CAPACITY and attempt < 2:
+                capacity = int(stats.records_max_per_frame * 1.1) + 1024
+                self.capacity[key] = capacity
+                if dbg:
+                    dbg["crop_counts"].zero_()
+                    dbg["visible_counts"].zero_()
+                continue
+            N.check(code)
+            break
+        return (out, dbg) if debug else out
+
+
+class Reproject:
+    """Batched drop-in for the frame loop: ``Reproject(configs, clip_path)(dataset)``."""
+
+    def __init__(self, configs, clip_path=None, device=None, clip_manager=None):
+        self.cm = clip_manager if clip_manager is not None else ClipManager(configs, clip_path, device=device, progress=False)
+        self.configs = configs
+        cams = self.cm.cm_list
+        assert len({(c.height, c.width) for c in cams}) == 1, "all cameras must share one output size"
+        self.camera_names = [c.camera_name for c in cams]
+        self.renderer = ClipRenderer(
+            np.stack([np.asarray(c.get_chassis2camera(), dtype=np.float64) for c in cams]),
+            np.stack([np.asarray(c.K, dtype=np.float64) for c in cams]),
+            cams[0].height, cams[0].width, [self.cm.mm.crop_dict[k] for k in CROP_KEYS], device=device)
+        self.rt = self.renderer.rt
+        self._resident = {}
+        self._pinned = {}
+
+    def resident(self, dataset):
+        if dataset not in self._resident:
+            self._resident[dataset] = self.renderer.resident(self.cm.instance_maps[dataset])
+        return self._resident[dataset]
+
+    def frame_poses(self, dataset):
+        """-> (image_idx list, float32 [F',16] world->chassis), host side."""
+        poses = self.cm.frame_poses(dataset)
+        idx = [i for i, _ in poses]
+        w2c = np.stack([m for _, m in poses]).reshape(-1, 16) if poses else np.zeros((0, 16), np.float32)
+        return idx, np.ascontiguousarray(w2c, dtype=np.float32)
+
+    def render_device(self, dataset, w2c=None, out=None, background=None, mode="auto", check=True):
+        """Frames as a torch uint8 [F',C,H,W,3] tensor on the GPU (w2c: host float32 [F',16])."""
+        import torch
+        if w2c is None:
+            _, w2c = self.frame_poses(dataset)
+        w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(self.rt.device)
+        return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check)
+
+    def __call__(self, dataset, backgrounds=None, mode="auto"):
+        """-> (image_idx list, uint8 numpy [F',C,H,W,3]); ``backgrounds`` (same shape, host) are
+        composited under the overlay exactly like drawing in place on the camera images."""
+        import torch
+        idx, w2c = self.frame_poses(dataset)
+        bg_dev = None
+        if backgrounds is not None:
+            bg_dev = torch.from_numpy(np.ascontiguousarray(backgrounds, dtype=np.uint8)).to(self.rt.device)
+        frames = self.render_device(dataset, w2c=w2c, background=bg_dev, out=bg_dev, mode=mode)
+        host = self._pinned.get(tuple(frames.shape))
+        if host is None:
+            host = torch.empty(tuple(frames.shape), dtype=torch.uint8, pin_memory=True)
+            self._pinned = {tuple(frames.shape): host}
+        host.copy_(frames, non_blocking=True)
+        self.rt.synchronize()
+        return idx, host.numpy()
+
+    def as_image_dicts(self, frames):
+        """[F',C,H,W,3] -> list of {camera_name: HxWx3}: the shape main.py hands to VideoGenerator."""
+        return [{name: frames[f, c] for c, name in enumerate(self.camera_names)} for f in range(frames.shape[0])]

@@ -1,0 +1,698 @@
+// libcama_b200: the batched clip path — the whole frame x camera x vertex loop of
+// /root/reference/cama/dataset.py:78-126 (yield_frame -> project_all_camera -> render_maps)
+// for every frame of a clip in a fixed handful of launches.
+//
+// Pipeline (BINNED mode, the throughput path):
+//   prep      w2c float32 -> float64 (exact), instance colours -> packed LUT
+//   geometry  FP64: world->chassis, crop box, 6 x (chassis->camera, K, /z, mask); every visible
+//             centre becomes a 4-byte record {ordinal+1 : 16 | pixel-in-band-plane : 16} tagged
+//             with its (frame, camera, row-band) bucket and its rank inside that bucket
+//   scan      exclusive scan of the bucket histogram
+//   scatter   records -> bucket order
+//   raster    one CTA per (frame, camera, band): uint16 centre plane in shared memory
+//             (atomic max of ordinals), L1-radius-2 max-dilation with packed u16x2 max,
+//             colour LUT, optional composite over a background, rows staged in shared memory
+//             and written with bulk async copies (cp.async.bulk shared -> global).
+// PLANE mode keeps the centre ids in a global uint32 plane and dilates per pixel: slower, no
+// shape restrictions, and an independent implementation the tests cross-check BINNED against.
+#include <algorithm>
+#include <climits>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace cama {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct CamBlock {                      // by-value kernel parameter (constant bank)
+    double E[CAMA_MAX_CAMERAS][12];    // chassis -> camera, rows 0..2 of the 4x4
+    double K[CAMA_MAX_CAMERAS][9];
+    double box[6];
+    int k_row2_is_001[CAMA_MAX_CAMERAS];
+};
+
+struct ClipArgs {
+    int n_frames, n_cams, n_instances, height, width;
+    long long n_vertices;
+    const void *vertices;
+    const int *vertex_instance;
+    const double *w2c64;               // [F,12]
+    int *crop_counts;
+    int *visible_counts;
+    double *vu_dense;
+    // PLANE
+    unsigned *plane;                   // [F,C,H,W]
+    // BINNED
+    int band_rows, n_bands;
+    long long cap;                     // records per frame
+    unsigned *fcount;                  // [F]
+    unsigned *hist;                    // [F*C*NB]
+    uint4 *unsorted;                   // [F*cap] {bucket, rank, payload, -}
+};
+
+// ------------------------------------------------------------------------------------------------ prep
+__global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
+                            const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
+    if (i <= n_inst) lut[i] = i == 0 ? 0u
+                                      : (unsigned)inst_bgr[3 * (i - 1)] | ((unsigned)inst_bgr[3 * (i - 1) + 1] << 8) |
+                                            ((unsigned)inst_bgr[3 * (i - 1) + 2] << 16);
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+template <int LAYOUT>
+__device__ __forceinline__ bool load_vertex(const ClipArgs &a, long long n, double &x, double &y, double &z, int &ord) {
+    if (n >= a.n_vertices) return false;
+    if (LAYOUT == CAMA_VERTEX_F32X4) {
+        const float4 v = __ldg(static_cast<const float4 *>(a.vertices) + n);
+        x = (double)v.x; y = (double)v.y; z = (double)v.z;
+        ord = __float_as_int(v.w);
+    } else {
+        const double *p = static_cast<const double *>(a.vertices) + 3 * n;
+        x = p[0]; y = p[1]; z = p[2];
+        ord = a.vertex_instance[n];
+    }
+    return true;
+}
+
+// One chassis-frame point against one camera (reference cama/dataset.py:110-115 + reproject.py:187-205).
+// The early exits only skip work whose result the visibility mask would discard anyway:
+//  * K row 2 == (0,0,1) makes q_z == p_z bit-for-bit, so p_z <= 0 rejects before x,y are formed;
+//  * q_x < -q_z or q_x > (W+1) q_z (same for y) puts u (v) outside [0,W) by a whole pixel, far
+//    beyond what the rounding of the division could undo.
+__device__ __forceinline__ bool camera_visible(const CamBlock &cams, int c, double cx, double cy, double cz, int width, int height,
+                                               double &v, double &u) {
+    const double *E = cams.E[c];
+    const double *K = cams.K[c];
+    const double pz = affine_row(E + 8, cx, cy, cz);
+    if (cams.k_row2_is_001[c] && !(pz > 0.0)) return false;
+    const double px = affine_row(E, cx, cy, cz);
+    const double py = affine_row(E + 4, cx, cy, cz);
+    const double qz = linear_row(K + 6, px, py, pz);
+    if (!((qz > 0.0) & (qz <= DBL_MAX))) return false;
+    const double qx = linear_row(K, px, py, pz);
+    const double qy = linear_row(K + 3, px, py, pz);
+    if ((qx < -qz) | (qx > (double)(width + 1) * qz) | (qy < -qz) | (qy > (double)(height + 1) * qz)) return false;
+    u = __ddiv_rn(qx, qz);
+    v = __ddiv_rn(qy, qz);
+    return (u >= 0.0) & (u < (double)width) & (v >= 0.0) & (v < (double)height);
+}
+
+// Warp-collective append of one record per predicated lane: slot in the frame's record pool
+// (one atomic per warp) and rank inside the record's bucket (one atomic per distinct bucket).
+__device__ __forceinline__ void warp_append(const ClipArgs &a, int f, bool pred, unsigned bucket, unsigned payload) {
+    const unsigned mask = __ballot_sync(kFull, pred);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&a.fcount[f], (unsigned)__popc(mask));
+    base = __shfl_sync(kFull, base, leader);
+    if (pred) {
+        const unsigned peers = __match_any_sync(mask, bucket);
+        const int head = __ffs(peers) - 1;
+        unsigned first = 0;
+        if (lane == head) first = atomicAdd(&a.hist[bucket], (unsigned)__popc(peers));
+        first = __shfl_sync(peers, first, head);
+        const unsigned rank = first + __popc(peers & ((1u << lane) - 1u));
+        const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
+        if ((long long)slot < a.cap) a.unsorted[(size_t)f * a.cap + slot] = make_uint4(bucket, rank, payload, 0u);
+    }
+}
+
+template <bool BINNED>
+__device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, bool vis, double v, double u, int ord, long long n) {
+    const int vi = vis ? __double2int_rz(v) : 0;   // reference cama/reproject.py:249 (values are >= 0: trunc == floor)
+    const int ui = vis ? __double2int_rz(u) : 0;
+    if (vis) {
+        if (a.visible_counts) atomicAdd(&a.visible_counts[((size_t)f * a.n_cams + c) * a.n_instances + ord], 1);
+        if (a.vu_dense) {
+            double *o = a.vu_dense + (((size_t)f * a.n_cams + c) * a.n_vertices + n) * 2;
+            o[0] = v; o[1] = u;
+        }
+    }
+    if (!BINNED) {
+        if (vis) atomicMax(&a.plane[(((size_t)f * a.n_cams + c) * a.height + vi) * a.width + ui], (unsigned)(ord + 1));
+    } else {
+        const int rb = a.band_rows;
+        const int b0 = vi / rb;
+        const int r = vi - b0 * rb;
+        const unsigned bucket = (unsigned)((f * a.n_cams + c) * a.n_bands + b0);
+        const unsigned key = (unsigned)(ord + 1) << 16;
+        warp_append(a, f, vis, bucket, key | (unsigned)((r + 2) * a.width + ui));
+        // the two rows next to a band edge also matter to the neighbouring band (dilation radius 2)
+        const bool up = vis && r < 2 && b0 > 0;
+        const bool down = vis && r >= rb - 2 && b0 + 1 < a.n_bands;
+        const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
+        const int r2 = up ? r + rb : r - rb;
+        warp_append(a, f, up || down, bucket2, key | (unsigned)((r2 + 2) * a.width + ui));
+    }
+}
+
+constexpr int kGeoThreads = 256;
+constexpr int kGeoV = 4;                   // vertices held in registers per thread
+constexpr int kGeoTile = kGeoThreads * kGeoV;
+constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads amortised over them)
+
+// Work unit = (tile of 1024 vertices, chunk of 8 frames).  A thread keeps its 4 vertices in
+// registers and walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).
+// Lanes hold consecutive vertices, so crop survival — and with it the expensive 6-camera tail —
+// is almost warp-uniform (polylines are spatially coherent).
+template <int LAYOUT, bool BINNED>
+__global__ void __launch_bounds__(kGeoThreads) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
+    __shared__ double sT[kGeoFrames][12];
+    const int tid = threadIdx.x;
+    const long long n_tiles = (a.n_vertices + kGeoTile - 1) / kGeoTile;
+    const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
+    const long long units = n_tiles * n_chunks;
+    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const long long tile = unit / n_chunks;
+        const int f0 = (int)(unit % n_chunks) * kGeoFrames;
+        const int nf = min(kGeoFrames, a.n_frames - f0);
+        __syncthreads();
+        if (tid < nf * 12) sT[tid / 12][tid % 12] = a.w2c64[(size_t)f0 * 12 + tid];
+        __syncthreads();
+        double vx[kGeoV], vy[kGeoV], vz[kGeoV];
+        int vord[kGeoV];
+        bool valid[kGeoV];
+#pragma unroll
+        for (int k = 0; k < kGeoV; ++k)
+            valid[k] = load_vertex<LAYOUT>(a, tile * kGeoTile + k * kGeoThreads + tid, vx[k], vy[k], vz[k], vord[k]);
+        for (int fi = 0; fi < nf; ++fi) {
+            const int f = f0 + fi;
+            const double *T = sT[fi];
+#pragma unroll
+            for (int k = 0; k < kGeoV; ++k) {
+                // reference cama/dataset.py:99-105: world -> chassis, then the crop box
+                const double cx = affine_row(T, vx[k], vy[k], vz[k]);
+                const double cy = affine_row(T + 4, vx[k], vy[k], vz[k]);
+                const double cz = affine_row(T + 8, vx[k], vy[k], vz[k]);
+                const bool alive = valid[k] && in_box(cams.box, cx, cy, cz);
+                if (!__any_sync(kFull, alive)) continue;
+                if (alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + vord[k]], 1);
+                const long long n = tile * kGeoTile + k * kGeoThreads + tid;
+                for (int c = 0; c < a.n_cams; ++c) {
+                    double v = 0.0, u = 0.0;
+                    const bool vis = alive && camera_visible(cams, c, cx, cy, cz, a.width, a.height, v, u);
+                    if (!BINNED || __any_sync(kFull, vis)) emit_centre<BINNED>(a, f, c, vis, v, u, vord[k], n);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PLANE raster
+__global__ void __launch_bounds__(256) plane_raster_kernel(const unsigned *__restrict__ plane, const unsigned *__restrict__ lut,
+                                                          const uint8_t *bg, uint8_t *frames, int height, int width, long long n_images) {
+    const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long per = (long long)height * width;
+    if (p >= n_images * per) return;
+    const long long img = p / per;
+    const int y = (int)((p % per) / width), x = (int)(p % width);
+    const unsigned *pl = plane + img * per;
+    unsigned m = 0;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= height) continue;
+        const int span = 2 - (dy < 0 ? -dy : dy);
+        for (int dx = -span; dx <= span; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= width) continue;
+            m = max(m, pl[(size_t)yy * width + xx]);
+        }
+    }
+    uint8_t *o = frames + 3 * p;
+    if (m) {
+        const unsigned c = lut[m];
+        o[0] = (uint8_t)c; o[1] = (uint8_t)(c >> 8); o[2] = (uint8_t)(c >> 16);
+    } else if (bg) {
+        const uint8_t *b = bg + 3 * p;
+        const uint8_t b0 = b[0], b1 = b[1], b2 = b[2];
+        o[0] = b0; o[1] = b1; o[2] = b2;
+    } else {
+        o[0] = 0; o[1] = 0; o[2] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ BINNED: scan + scatter
+struct ClipStatsDev {
+    unsigned long long records_total;
+    unsigned long long records_max_per_frame;
+    unsigned overflow;
+    unsigned pad;
+};
+
+// single CTA: start[b] = exclusive scan of hist, start[nb] = total; per-frame overflow check
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, int nb,
+                                                           const unsigned *__restrict__ fcount, int n_frames, long long cap,
+                                                           ClipStatsDev *__restrict__ stats) {
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    __shared__ unsigned long long s_total, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = 0; s_total = 0; s_max = 0; }
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int idx = base + tid;
+        const unsigned v = idx < nb ? hist[idx] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(kFull, w, d);
+                if (lane >= d) w += t;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const unsigned before = carry + (warp > 0 ? warp_sum[warp - 1] : 0u) + inc - v;
+        if (idx < nb) start[idx] = before;
+        __syncthreads();
+        if (tid == 1023) carry = before + v;
+        __syncthreads();
+    }
+    unsigned long long tot = 0, mx = 0;
+    for (int f = tid; f < n_frames; f += 1024) {
+        const unsigned long long c = fcount[f];
+        tot += c;
+        mx = c > mx ? c : mx;
+    }
+    atomicAdd(&s_total, tot);
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    if (tid == 0) {
+        start[nb] = carry;
+        stats->records_total = s_total;
+        stats->records_max_per_frame = s_max;
+        stats->overflow = s_max > (unsigned long long)cap ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) record_scatter_kernel(const uint4 *__restrict__ unsorted, const unsigned *__restrict__ fcount,
+                                                            const unsigned *__restrict__ start, long long cap, long long sorted_cap,
+                                                            unsigned *__restrict__ sorted) {
+    const int f = blockIdx.y;
+    const long long n = min((long long)fcount[f], cap);
+    const uint4 *src = unsorted + (size_t)f * cap;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const uint4 r = src[i];
+        const long long pos = (long long)start[r.x] + r.y;
+        if (pos < sorted_cap) sorted[pos] = r.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ BINNED raster
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_shared_to_global(void *gptr, const void *sptr, unsigned bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(sptr);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ unsigned max3_u16x2(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+
+// max of a 16-bit lane inside shared memory (ordinals of different instances race for a pixel)
+__device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix, unsigned val) {
+    unsigned *word = reinterpret_cast<unsigned *>(plane) + (pix >> 1);
+    const unsigned sh = (pix & 1u) * 16u;
+    unsigned old = *reinterpret_cast<volatile unsigned *>(word);
+    while (((old >> sh) & 0xffffu) < val) {
+        const unsigned want = (old & ~(0xffffu << sh)) | (val << sh);
+        const unsigned prev = atomicCAS(word, old, want);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+constexpr int kRasterThreads = 256;
+constexpr int kStageRows = 3;              // rows per bulk store
+
+struct RasterArgs {
+    int n_items;                           // F*C*NB
+    int n_bands, band_rows, height, width, n_instances;
+    long long sorted_cap;
+    const unsigned *start;                 // [n_items+1]
+    const unsigned *sorted;
+    const unsigned *lut;
+    const uint8_t *bg;
+    uint8_t *frames;
+    unsigned *work_counter;
+};
+
+// One work item = one (frame, camera, band).  Shared memory: uint16 plane [(band_rows+4)][W] |
+// two staging buffers [kStageRows][W*3].  Thread t owns columns 4t..4t+3 and walks down the band
+// keeping the 5-row dilation window in registers.
+__global__ void __launch_bounds__(kRasterThreads, 2) binned_raster_kernel(const RasterArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+    const int W = a.width;
+    const int plane_rows = a.band_rows + 4;
+    const unsigned plane_elems = (unsigned)(plane_rows * W);
+    unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
+    const unsigned row_bytes = (unsigned)W * 3u;
+    unsigned char *stage0 = smem + (size_t)plane_elems * 2;
+    const unsigned stage_bytes = kStageRows * row_bytes;
+    const int strips = W >> 2;
+    const bool owner = tid < strips;
+    const int x0 = tid * 4;
+    int pending_slot = 0;                  // staging buffer the next chunk will use
+
+    for (;;) {
+        __syncthreads();                   // everyone is done with s_item / plane of the previous item
+        if (tid == 0) s_item = (int)atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.n_items) break;
+        const int band = item % a.n_bands;
+        const long long image = item / a.n_bands;
+        const int y_first = band * a.band_rows;
+        const int rows_out = min(a.band_rows, a.height - y_first);
+
+        // 1. clear the plane
+        {
+            uint4 *p4 = reinterpret_cast<uint4 *>(plane);
+            const int n16 = (int)(plane_elems >> 3);
+            for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        // 2. centres of this bucket
+        {
+            // (the bounds only matter after a capacity overflow, when the pool holds stale records)
+            const long long lo = a.start[item], hi = min((long long)a.start[item + 1], a.sorted_cap);
+            for (long long i = lo + tid; i < hi; i += kRasterThreads) {
+                const unsigned rec = __ldg(a.sorted + i);
+                const unsigned pix = rec & 0xffffu, ord1 = rec >> 16;
+                if (pix < plane_elems && ord1 <= (unsigned)a.n_instances) smem_max_u16(plane, pix, ord1);
+            }
+        }
+        __syncthreads();
+        // 3. dilation + colour, kStageRows rows at a time
+        uint8_t *out_base = a.frames + ((size_t)image * a.height + y_first) * row_bytes;
+        const uint8_t *bg_base = a.bg ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
+        // window registers: raw rows j-4..j-1, h3 rows j-3..j-1, h5 rows j-2..j-1 (as packed u16x2 pairs)
+        unsigned raw[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        unsigned h3[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+        unsigned h5[2][2] = {{0, 0}, {0, 0}};
+        for (int j = 0; j < rows_out + 4; ++j) {
+            unsigned A0 = 0, A1 = 0, L = 0, R = 0;
+            if (owner) {
+                const unsigned short *row = plane + (size_t)j * W + x0;
+                const uint2 own = *reinterpret_cast<const uint2 *>(row);
+                A0 = own.x; A1 = own.y;
+                if (x0 > 0) L = *reinterpret_cast<const unsigned *>(row - 2);
+                if (x0 + 4 < W) R = *reinterpret_cast<const unsigned *>(row + 4);
+            }
+            const unsigned S0 = __byte_perm(L, A0, 0x5432);    // (p[-1], p[0])
+            const unsigned S1 = __byte_perm(A0, A1, 0x5432);   // (p[1],  p[2])
+            const unsigned S2 = __byte_perm(A1, R, 0x5432);    // (p[3],  p[4])
+            const unsigned t0 = max3_u16x2(S0, A0, S1);        // 3-wide max for p0,p1
+            const unsigned t1 = max3_u16x2(S1, A1, S2);        //                 p2,p3
+            const unsigned f0 = max3_u16x2(t0, L, A1);         // 5-wide max
+            const unsigned f1 = max3_u16x2(t1, A0, R);
+            // window before the shift: raw[k] = row j-4+k, h3[k] = row j-3+k, h5[k] = row j-2+k
+            if (j >= 4) {
+                // band output row yb = j-4, centred on plane row j-2:
+                //   out = max(raw[j-4], h3[j-3], h5[j-2], h3[j-1], raw[j])      (the 13-px L1 ball)
+                const int yb = j - 4;
+                const unsigned m0 = max3_u16x2(max3_u16x2(raw[0][0], h3[0][0], h5[0][0]), h3[2][0], A0);
+                const unsigned m1 = max3_u16x2(max3_u16x2(raw[0][1], h3[0][1], h5[0][1]), h3[2][1], A1);
+                const int slot_row = yb % kStageRows;
+                if (slot_row == 0) {
+                    // about to overwrite staging buffer `pending_slot`: the store issued two chunks ago must have read it
+                    if (tid == 0) bulk_wait_group_read<1>();
+                    __syncthreads();
+                }
+                if (owner) {
+                    unsigned w0 = 0, w1 = 0, w2 = 0;
+                    if (bg_base) {
+                        const unsigned *b = reinterpret_cast<const unsigned *>(bg_base + (size_t)yb * row_bytes + (size_t)x0 * 3);
+                        w0 = b[0]; w1 = b[1]; w2 = b[2];
+                    }
+                    if (m0 | m1) {
+                        unsigned c0 = w0 & 0xffffffu;
+                        unsigned c1 = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+                        unsigned c2 = (w1 >> 16) | ((w2 & 0xffu) << 16);
+                        unsigned c3 = w2 >> 8;
+                        if (m0 & 0xffffu) c0 = __ldg(a.lut + (m0 & 0xffffu));
+                        if (m0 >> 16) c1 = __ldg(a.lut + (m0 >> 16));
+                        if (m1 & 0xffffu) c2 = __ldg(a.lut + (m1 & 0xffffu));
+                        if (m1 >> 16) c3 = __ldg(a.lut + (m1 >> 16));
+                        w0 = c0 | (c1 << 24);
+                        w1 = (c1 >> 8) | (c2 << 16);
+                        w2 = (c2 >> 16) | (c3 << 8);
+                    }
+                    unsigned *dst = reinterpret_cast<unsigned *>(stage0 + (size_t)pending_slot * stage_bytes + (size_t)slot_row * row_bytes + (size_t)x0 * 3);
+                    dst[0] = w0; dst[1] = w1; dst[2] = w2;
+                }
+                if (slot_row == kStageRows - 1 || yb == rows_out - 1) {
+                    const int chunk_rows = slot_row + 1;
+                    fence_proxy_async_shared();
+                    __syncthreads();
+                    if (tid == 0) {
+                        bulk_store_shared_to_global(out_base + (size_t)(yb - slot_row) * row_bytes,
+                                                    stage0 + (size_t)pending_slot * stage_bytes, (unsigned)chunk_rows * row_bytes);
+                        bulk_commit_group();
+                    }
+                    pending_slot ^= 1;
+                }
+            }
+            // slide the window down one row
+            raw[0][0] = raw[1][0]; raw[0][1] = raw[1][1];
+            raw[1][0] = raw[2][0]; raw[1][1] = raw[2][1];
+            raw[2][0] = raw[3][0]; raw[2][1] = raw[3][1];
+            raw[3][0] = A0;        raw[3][1] = A1;
+            h3[0][0] = h3[1][0]; h3[0][1] = h3[1][1];
+            h3[1][0] = h3[2][0]; h3[1][1] = h3[2][1];
+            h3[2][0] = t0;       h3[2][1] = t1;
+            h5[0][0] = h5[1][0]; h5[0][1] = h5[1][1];
+            h5[1][0] = f0;       h5[1][1] = f1;
+        }
+    }
+    // staging memory must stay valid until the last bulk stores have read it
+    if (tid == 0) bulk_wait_group_read<0>();
+}
+
+}  // namespace cama
+
+using namespace cama;
+
+namespace {
+
+struct ClipPlan {
+    int mode;
+    int band_rows, n_bands;
+    long long cap;          // records per frame
+    int n_buckets;
+    size_t raster_smem;
+    // workspace offsets
+    size_t off_zero, zero_bytes;     // region memset to 0 each call: work counter | fcount | hist
+    size_t off_counter, off_fcount, off_hist, off_start, off_stats, off_w2c64, off_lut, off_unsorted, off_sorted, off_plane;
+    size_t total;
+};
+
+constexpr size_t kRasterSmemBudget = 110 * 1024;     // two CTAs per SM
+
+int make_plan(const cama_clip_desc *d, ClipPlan &p) {
+    CAMA_REQUIRE(d, "desc is NULL");
+    CAMA_REQUIRE(d->struct_bytes == sizeof(cama_clip_desc), "cama_clip_desc size mismatch: caller %u, library %zu", d->struct_bytes, sizeof(cama_clip_desc));
+    CAMA_REQUIRE(d->n_frames >= 0 && d->n_cams > 0 && d->n_instances >= 0 && d->n_vertices >= 0, "negative size");
+    CAMA_REQUIRE(d->height > 0 && d->width > 0, "bad image size");
+    if (d->n_cams > CAMA_MAX_CAMERAS) return fail(CAMA_E_UNSUPPORTED, "at most %d cameras per call", CAMA_MAX_CAMERAS);
+    CAMA_REQUIRE(d->vertex_layout == CAMA_VERTEX_F32X4 || d->vertex_layout == CAMA_VERTEX_F64X3, "bad vertex_layout");
+    CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width < (1ll << 40), "clip too large");
+    const int W = d->width, H = d->height;
+    // BINNED needs: 16-byte rows for the bulk stores, one 4-px strip per thread, 16-bit pixel index and ordinal
+    int band_rows = 0;
+    bool binned_ok = (W % 16 == 0) && (W / 4 <= kRasterThreads) && d->n_instances <= 65534;
+    if (binned_ok) {
+        const long long stage = 2ll * kStageRows * W * 3;
+        long long rows = ((long long)kRasterSmemBudget - stage) / (2ll * W) - 4;
+        rows = std::min<long long>(rows, 65536 / W - 4);
+        rows = std::min<long long>(rows, H);
+        if (rows < 4 && rows < H) binned_ok = false;
+        band_rows = (int)rows;
+    }
+    int mode = d->mode;
+    if (mode == CAMA_CLIP_AUTO) mode = binned_ok ? CAMA_CLIP_BINNED : CAMA_CLIP_PLANE;
+    CAMA_REQUIRE(mode == CAMA_CLIP_PLANE || mode == CAMA_CLIP_BINNED, "bad mode");
+    if (mode == CAMA_CLIP_BINNED && !binned_ok)
+        return fail(CAMA_E_UNSUPPORTED, "BINNED mode needs width %% 16 == 0, width <= %d, <= 65534 instances", 4 * kRasterThreads);
+    p = ClipPlan();
+    p.mode = mode;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p.off_w2c64 = take(sizeof(double) * 12 * (size_t)std::max(d->n_frames, 1));
+    p.off_lut = take(sizeof(unsigned) * ((size_t)d->n_instances + 1));
+    p.off_stats = take(sizeof(ClipStatsDev));
+    if (mode == CAMA_CLIP_PLANE) {
+        p.off_plane = take(sizeof(unsigned) * (size_t)d->n_frames * d->n_cams * H * W);
+    } else {
+        p.band_rows = band_rows;
+        p.n_bands = (H + band_rows - 1) / band_rows;
+        const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
+        CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
+        p.n_buckets = (int)nb;
+        long long cap = d->record_capacity;
+        if (cap <= 0) cap = std::max<long long>(d->n_vertices, 4096);      // one visible camera per vertex and frame
+        CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
+        p.cap = cap;
+        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + 2 * (size_t)kStageRows * W * 3;
+        p.off_zero = off;
+        p.off_counter = take(256);
+        p.off_fcount = take(sizeof(unsigned) * (size_t)std::max(d->n_frames, 1));
+        p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));
+        p.zero_bytes = off - p.off_zero;
+        p.off_start = take(sizeof(unsigned) * ((size_t)nb + 1));
+        p.off_unsorted = take(sizeof(uint4) * (size_t)d->n_frames * cap);
+        p.off_sorted = take(sizeof(unsigned) * (size_t)d->n_frames * cap);
+    }
+    p.total = std::max<size_t>(off, 256);
+    return CAMA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cama_clip_workspace_bytes(const cama_clip_desc *desc, size_t *bytes) {
+    CAMA_REQUIRE(bytes, "bytes is NULL");
+    ClipPlan p;
+    const int rc = make_plan(desc, p);
+    if (rc != CAMA_OK) return rc;
+    *bytes = p.total;
+    return CAMA_OK;
+}
+
+int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, size_t workspace_bytes, void *stream) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    ClipPlan p;
+    int rc = make_plan(d, p);
+    if (rc != CAMA_OK) return rc;
+    if (!workspace || workspace_bytes < p.total) return fail(CAMA_E_WORKSPACE, "clip workspace: need %zu bytes, got %zu", p.total, workspace_bytes);
+    CAMA_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (d->n_frames == 0) return CAMA_OK;
+    CAMA_REQUIRE(d->frames && d->world2chassis && d->chassis2cam && d->intrinsics, "NULL buffer in desc");
+    CAMA_REQUIRE(d->n_vertices == 0 || d->vertices, "vertices is NULL");
+    CAMA_REQUIRE(d->n_instances == 0 || d->instance_bgr, "instance_bgr is NULL");
+    CAMA_REQUIRE(d->vertex_layout != CAMA_VERTEX_F64X3 || d->n_vertices == 0 || d->vertex_instance, "vertex_instance is NULL");
+    CAMA_REQUIRE(((uintptr_t)d->frames & 15) == 0 && ((uintptr_t)d->background & 15) == 0 && ((uintptr_t)d->vertices & 15) == 0,
+                 "frames/background/vertices must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+
+    CamBlock cams;
+    for (int c = 0; c < CAMA_MAX_CAMERAS; ++c) {
+        const bool live = c < d->n_cams;
+        for (int i = 0; i < 12; ++i) cams.E[c][i] = live ? d->chassis2cam[16 * c + i] : 0.0;
+        for (int i = 0; i < 9; ++i) cams.K[c][i] = live ? d->intrinsics[9 * c + i] : 0.0;
+        cams.k_row2_is_001[c] = live && cams.K[c][6] == 0.0 && cams.K[c][7] == 0.0 && cams.K[c][8] == 1.0;
+    }
+    for (int i = 0; i < 6; ++i) cams.box[i] = d->crop_box[i];
+
+    ClipArgs a{};
+    a.n_frames = d->n_frames; a.n_cams = d->n_cams; a.n_instances = d->n_instances;
+    a.height = d->height; a.width = d->width; a.n_vertices = d->n_vertices;
+    a.vertices = d->vertices; a.vertex_instance = d->vertex_instance;
+    a.w2c64 = reinterpret_cast<const double *>(ws + p.off_w2c64);
+    a.crop_counts = d->crop_counts; a.visible_counts = d->visible_counts; a.vu_dense = d->vu_dense;
+    unsigned *lut = reinterpret_cast<unsigned *>(ws + p.off_lut);
+    ClipStatsDev *stats = reinterpret_cast<ClipStatsDev *>(ws + p.off_stats);
+
+    if (d->vu_dense)
+        CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
+    CAMA_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(ClipStatsDev), s));
+    {
+        const int n = std::max(d->n_frames * 12, d->n_instances + 1);
+        prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
+                                                    d->instance_bgr, d->n_instances, lut);
+        CAMA_LAUNCHED(ctx);
+    }
+    const long long n_tiles = (d->n_vertices + kGeoTile - 1) / kGeoTile;
+    const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
+    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 8));
+    const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
+
+    if (p.mode == CAMA_CLIP_PLANE) {
+        a.plane = reinterpret_cast<unsigned *>(ws + p.off_plane);
+        const size_t px = (size_t)d->n_frames * d->n_cams * d->height * d->width;
+        CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
+        if (units > 0) {
+            if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+            else clip_geometry_kernel<CAMA_VERTEX_F64X3, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+            CAMA_LAUNCHED(ctx);
+        }
+        plane_raster_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(a.plane, lut, d->background, d->frames, d->height, d->width,
+                                                                        (long long)d->n_frames * d->n_cams);
+        CAMA_LAUNCHED(ctx);
+        return CAMA_OK;
+    }
+
+    // BINNED
+    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.cap = p.cap;
+    a.fcount = reinterpret_cast<unsigned *>(ws + p.off_fcount);
+    a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
+    a.unsorted = reinterpret_cast<uint4 *>(ws + p.off_unsorted);
+    unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
+    unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
+    unsigned *counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
+    CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
+    if (units > 0) {
+        if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+        else clip_geometry_kernel<CAMA_VERTEX_F64X3, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+        CAMA_LAUNCHED(ctx);
+    }
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.fcount, d->n_frames, p.cap, stats);
+    CAMA_LAUNCHED(ctx);
+    {
+        const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((p.cap + 255) / 256, 64));
+        record_scatter_kernel<<<dim3(gx, (unsigned)d->n_frames), 256, 0, s>>>(a.unsorted, a.fcount, start, p.cap, (long long)d->n_frames * p.cap, sorted);
+        CAMA_LAUNCHED(ctx);
+    }
+    RasterArgs r{};
+    r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
+    r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
+    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames; r.work_counter = counter;
+    CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+    const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * 2);
+    binned_raster_kernel<<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *workspace, void *stream, cama_clip_stats *out) {
+    CAMA_REQUIRE(ctx && out && workspace, "NULL argument");
+    ClipPlan p;
+    const int rc = make_plan(d, p);
+    if (rc != CAMA_OK) return rc;
+    DeviceGuard guard(ctx->device);
+    ClipStatsDev h{};
+    CAMA_CUDA_TRY(cudaMemcpyAsync(&h, static_cast<const unsigned char *>(workspace) + p.off_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    out->records_total = (int64_t)h.records_total;
+    out->records_max_per_frame = (int64_t)h.records_max_per_frame;
+    out->record_capacity = p.cap;
+    out->overflow = (int32_t)h.overflow;
+    out->mode = p.mode;
+    out->band_rows = p.band_rows;
+    out->n_bands = p.n_bands;
+    if (h.overflow)
+        return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", h.records_max_per_frame, p.cap);
+    return CAMA_OK;
+}
+
+}  // extern "C"

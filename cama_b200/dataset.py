@@ -1,0 +1,134 @@
+"""Clip orchestration: the frame x camera loop that *is* the reprojection hot path.
+
+Call-compatible with /root/reference/cama/dataset.py (``ClipManager``): same constructor, same
+``configs`` keys (config.yaml ``cama_configs``), same generator/dict protocol, so the reference's
+main.py runs against this class unchanged::
+
+    for image_idx, instance_map in cm.yield_frame(dataset):          # main.py:57
+        maps_2d_dict = cm.project_all_camera(instance_map)            # main.py:58
+        image_dict = cm.render_vectors(maps_2d_dict, image_idx)       # main.py:59
+
+Those three methods run one device operator per call (fused transform+crop, fused
+transform+project, disc raster).  ``render_clip`` / ``cama_b200.batched.Reproject`` do the same
+work for every frame of the clip in a handful of launches and are what the benchmark measures.
+"""
+from __future__ import annotations
+
+from os.path import exists, join
+
+import numpy as np
+
+from .dataset_reader import DatasetReader
+from .pose_transformer import PoseTransformer
+from .reproject import CameraManager, MapManager
+from .tools import load_json
+
+try:                                    # progress bar is cosmetic; the reference shows one per clip
+    from tqdm import tqdm as _progress
+except Exception:                       # pragma: no cover
+    def _progress(it, **_):
+        return it
+
+
+class ClipManager:
+    def __init__(self, configs, clip_path=None, device=None, progress=True):
+        self.configs = configs
+        self._device = device
+        self._progress = progress
+        self.mm = MapManager(device=device)
+        self.instance_maps = dict()
+        if clip_path is not None:
+            self.clip_path = clip_path
+            self.cm_list = self.prepare_camera_manager(clip_path)
+            for name, loader in (("cama", self.load_clip_cama), ("nuscenes", self.load_clip_nuscenes)):
+                instances = loader(clip_path)
+                if instances is not None:
+                    self.instance_maps[name] = instances
+
+    # ------------------------------------------------------------------ load time
+    def _label_path(self, clip_path, key):
+        return join(clip_path, self.configs["result_dir"], self.configs[key])
+
+    def load_clip_cama(self, clip_path):
+        """CAMA labels (BEV pixels) + MLP height map -> dense world instances, or None if absent."""
+        label_json = self._label_path(clip_path, "cama_map_file")
+        if not exists(label_json):
+            return None
+        bev_height = np.load(self._label_path(clip_path, "height_mlp"))
+        return self.mm.calculate_3d_instance_maps(bev_height, load_json(label_json))
+
+    def load_clip_nuscenes(self, clip_path):
+        """nuScenes HD-map labels (metres, z = 0) -> dense instances, or None if absent."""
+        label_json = self._label_path(clip_path, "nuscenes_map_file")
+        if not exists(label_json):
+            return None
+        return self.mm.load_3d_instance_maps(load_json(label_json))
+
+    def prepare_camera_manager(self, clip_path):
+        return [CameraManager(clip_path, name, device=self._device) for name in self.configs["camera_list"]]
+
+    # ------------------------------------------------------------------ trajectories (chassis -> world)
+    def get_pt_cama(self, dr):
+        """SfM poses of the main camera, right-multiplied by chassis->camera."""
+        main = self.configs["camera_main"]
+        pt = PoseTransformer()
+        pt.loadarray(dr.get_odometry(f"{self.configs['pose_prefix']}_{main}.txt"))
+        pt.right_rotate(dr.get_extrinsic("chassis", main))
+        return pt
+
+    def get_pt_nuscenes(self, dr):
+        """Ego poses, re-expressed relative to the middle pose of the clip."""
+        pt = PoseTransformer()
+        pt.loadarray(dr.get_odometry("wigo_offset_clip.txt"))
+        pt.normalize2center()
+        return pt
+
+    def frame_poses(self, dataset):
+        """[(image_idx, world2chassis float32 4x4)] for every renderable frame.
+
+        Reference cama/dataset.py:78-99: index 0 is skipped; the pose is sought with
+        interpolation and ``t_max_diff=0.5``; a ``RuntimeError`` from the lookup skips the frame;
+        the pose is cast to float32 *before* ``np.linalg.inv``.
+        """
+        dr = DatasetReader(self.clip_path)
+        if dataset == "nuscenes":
+            pt = self.get_pt_nuscenes(dr)
+        elif dataset == "cama":
+            pt = self.get_pt_cama(dr)
+        else:
+            raise UnboundLocalError(f"unknown dataset {dataset!r}")     # the reference fails the same way
+        stamps = dr.get_sensor_timestamp(self.configs["camera_main"], sync=True)
+        out = []
+        for image_idx in range(1, len(stamps)):
+            try:
+                chassis2world = pt.seek_by_timestamp(stamps[image_idx], t_max_diff=0.5, interpolate=True).astype(np.float32)
+            except RuntimeError:
+                continue
+            out.append((image_idx, np.linalg.inv(chassis2world)))
+        return out
+
+    # ------------------------------------------------------------------ the per-frame protocol of main.py
+    def yield_frame(self, dataset):
+        """Generator of ``(image_idx, chassis-frame instances inside the crop box)``."""
+        poses = self.frame_poses(dataset)
+        instances = self.instance_maps[dataset]
+        for image_idx, world2chassis in (_progress(poses) if self._progress else poses):
+            yield image_idx, self.mm.transform_crop_3d_instance_maps(instances, world2chassis)
+
+    def project_all_camera(self, maps_3d):
+        """{camera_name: visible (v,u) instances}, cameras in ``camera_list`` order."""
+        return {cm.camera_name: cm.transform_project_to_image(maps_3d) for cm in self.cm_list}
+
+    def render_vectors(self, maps_2d_dict, image_idx):
+        """{camera_name: undistort-resized camera image with the map points stamped in}."""
+        out = {}
+        for cm in self.cm_list:
+            image = cm.read_resized_image_by_index(image_idx)
+            out[cm.camera_name] = cm.render_maps(image, maps_2d_dict[cm.camera_name])
+        return out
+
+    # ------------------------------------------------------------------ batched path
+    def render_clip(self, dataset, backgrounds=None, mode="auto"):
+        """All frames of the clip at once -> (image_idx list, uint8 [F,C,H,W,3] numpy)."""
+        from .batched import Reproject
+        return Reproject(self.configs, clip_manager=self, device=self._device)(dataset, backgrounds=backgrounds, mode=mode)

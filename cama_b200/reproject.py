@@ -1,0 +1,263 @@
+"""Geometry + raster managers of the reprojection path, backed by the sm_100a kernels.
+
+Call-compatible with /root/reference/cama/reproject.py: ``BaseManager``, ``MapManager``,
+``CameraManager`` keep their constructor signatures, attributes, method names, argument meaning
+and the "instance map" convention (list of ``{"class": str, "points": ndarray}``; empty instances
+are dropped; 2-D points are (v,u); images are uint8 HxWx3 BGR mutated in place).
+
+Where the work runs:
+* per-frame methods — ``transform_3d_instance_maps`` (reference :108-116), ``crop_3d_instance_maps``
+  (:118-131), ``project_to_image`` (:187-205), ``render_maps`` (:246-257) — each call one operator of
+  libcama_b200 through the C ABI (cama_transform_points / cama_crop_points / cama_project_points /
+  cama_render_points).  They exist for drop-in compatibility and operator-level parity tests; the
+  throughput path is the batched one in cama_b200.batched.
+* load-time methods — ``load_3d_instance_maps`` (:42-70), ``calculate_3d_instance_maps`` (:72-106) —
+  vectorised float32 NumPy here on the host (bit-identical to the reference's scalar loops, NEP-50
+  float32 semantics included).
+There is no CPU fallback for the device methods.
+"""
+from __future__ import annotations
+
+from os.path import join
+
+import numpy as np
+
+from .dataset_reader import DatasetReader
+from .runtime import CROP_KEYS, get_runtime
+
+LANE_CLASS = "lane_marking"
+OTHER_CLASS = "Crosswalk_Line"
+
+
+class BaseManager:
+    def __init__(self):
+        pass
+
+    @staticmethod
+    def get_color_maps():
+        """class -> RGB (reference :11-17)."""
+        return {"Road_teeth": np.array([235, 73, 127]),
+                "lane_marking": np.array([211, 211, 211]),
+                "Stop_Line": np.array([211, 211, 211]),
+                "Crosswalk_Line": np.array([255, 215, 0])}
+
+
+def render_bgr_of_class(class_name):
+    """BGR triple render_maps paints an instance with: every class except lane_marking is drawn as
+    Crosswalk_Line (reference :251-254)."""
+    key = class_name if class_name == LANE_CLASS else OTHER_CLASS
+    return BaseManager.get_color_maps()[key][::-1]
+
+
+def pack_instances(instances):
+    """list of instances -> (flat points, int64 offsets[I+1], classes)."""
+    pts = [np.asarray(inst["points"]) for inst in instances]
+    offsets = np.zeros(len(pts) + 1, dtype=np.int64)
+    if pts:
+        offsets[1:] = np.cumsum([p.shape[0] for p in pts])
+        dtype = np.result_type(*[p.dtype for p in pts])
+        width = pts[0].shape[1] if pts[0].ndim == 2 else 3
+        flat = np.concatenate([p.reshape(-1, width) for p in pts], axis=0).astype(dtype, copy=False)
+    else:
+        flat = np.zeros((0, 3), dtype=np.float64)
+    return flat, offsets, [inst["class"] for inst in instances]
+
+
+def unpack_instances(flat, offsets, classes, drop_empty=True):
+    out = []
+    for i, cls in enumerate(classes):
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        if hi > lo or not drop_empty:
+            out.append({"class": cls, "points": flat[lo:hi]})
+    return out
+
+
+def densify_polyline(points, resolution):
+    """Dense float32 points of one polyline (reference :49-63 / :79-93), vectorised.
+
+    Per segment ``num = int(len / resolution)`` in float32; the segment contributes
+    ``start + (end - start) / num * j`` for j = 0..num-1 (end point excluded, zero-``num`` segments
+    dropped).  Every intermediate is rounded to float32 exactly as the reference's scalar code.
+    """
+    pts = np.array(points).astype(np.float32)
+    delta = pts[1:] - pts[:-1]
+    length = np.linalg.norm(delta, axis=-1)
+    num = (length / resolution).astype(np.int64)
+    total = int(num.sum())
+    if total == 0:
+        # the reference indexes an empty 1-D array here and raises the same exception type
+        raise IndexError("polyline has no segment of at least one resolution step")
+    seg = np.repeat(np.arange(len(num)), num)
+    first = np.cumsum(num) - num
+    j = (np.arange(total) - np.repeat(first, num)).astype(np.float32)
+    step = delta[seg] / num[seg].astype(np.float32)[:, None]
+    return pts[:-1][seg] + step * j[:, None]
+
+
+class MapManager(BaseManager):
+    def __init__(self, device=None):
+        super(MapManager, self).__init__()
+        self.solution = 0.1      # metre per BEV pixel, also the densify step
+        self.center_x = 0
+        self.center_y = 0
+        self.map_width = 600
+        self.map_height = 600
+        self.crop_dict = {"x_min": -50, "x_max": 50, "y_min": -100, "y_max": 100, "z_min": -200, "z_max": 200}
+        self._device = device
+
+    # ------------------------------------------------------------------ load time (host)
+    def pixel2world_xy(self, pixel_xy):
+        worlds_xy = np.zeros_like(pixel_xy)
+        worlds_xy[:, 0] = pixel_xy[:, 1] * self.solution - self.map_width / 2 + self.center_x
+        worlds_xy[:, 1] = pixel_xy[:, 0] * self.solution - self.map_height / 2 + self.center_y
+        return worlds_xy
+
+    def load_3d_instance_maps(self, maps_2d):
+        """Metric (nuScenes-style) labels -> dense instances on the z = 0 plane."""
+        instance_list = []
+        for item in maps_2d:
+            if len(item["data"]) <= 1:
+                continue
+            dense = densify_polyline(item["data"], self.solution)
+            xyz = np.concatenate((dense, np.zeros_like(dense[:, 0])[:, None]), axis=-1).reshape(-1, 3)
+            instance_list.append({"class": item["attrs"]["type"], "points": xyz})
+        return instance_list
+
+    def calculate_3d_instance_maps(self, bev_height, maps_2d):
+        """BEV-pixel (CAMA) labels + height map -> dense world instances."""
+        instance_list = []
+        for item in maps_2d:
+            if len(item["data"]) <= 1:
+                continue
+            dense = densify_polyline(item["data"], self.solution)
+            cell = dense.round().astype(np.uint16)[:, ::-1].clip(0, bev_height.shape[0] - 1)
+            height = bev_height[cell[:, 0], cell[:, 1]]
+            xyz = np.concatenate((self.pixel2world_xy(dense), height[:, None]), axis=-1).reshape(-1, 3)
+            instance_list.append({"class": item["attrs"]["type"], "points": xyz})
+        return instance_list
+
+    # ------------------------------------------------------------------ per frame (device)
+    def transform_3d_instance_maps(self, maps, transform):
+        """(T @ [p;1])[:3] for every point of every instance; float64 out."""
+        if len(maps) == 0:
+            return []
+        flat, offsets, classes = pack_instances(maps)
+        out = get_runtime(self._device).transform_points(flat, np.asarray(transform))
+        return unpack_instances(out, offsets, classes, drop_empty=False)
+
+    def crop_3d_instance_maps(self, maps, crop_dict=None):
+        """Keep the points inside the (inclusive) box; drop instances left empty."""
+        crop_dict = crop_dict if crop_dict is not None else self.crop_dict
+        if len(maps) == 0:
+            return []
+        flat, offsets, classes = pack_instances(maps)
+        box = [crop_dict[k] for k in CROP_KEYS]
+        out, out_offsets = get_runtime(self._device).crop_points(flat, offsets, box)
+        if flat.dtype == np.float32:
+            out = out.astype(np.float32)       # survivors keep the caller's dtype, as boolean indexing does
+        return unpack_instances(out, out_offsets, classes)
+
+    def transform_crop_3d_instance_maps(self, maps, transform, crop_dict=None):
+        """Fused transform + crop (one pass, one round trip); same result as calling the two
+        methods above in sequence, which is what the frame loop does (cama/dataset.py:99-105)."""
+        crop_dict = crop_dict if crop_dict is not None else self.crop_dict
+        if len(maps) == 0:
+            return []
+        flat, offsets, classes = pack_instances(maps)
+        box = [crop_dict[k] for k in CROP_KEYS]
+        out, out_offsets = get_runtime(self._device).crop_points(flat, offsets, box, T=np.asarray(transform))
+        return unpack_instances(out, out_offsets, classes)
+
+    # ------------------------------------------------------------------ debugging dumps (host)
+    def save_pcd(self, maps, pcd_path):
+        import open3d as o3d
+        cloud = o3d.geometry.PointCloud()
+        pts = np.concatenate([inst["points"] for inst in maps], axis=0)
+        cols = np.concatenate([np.tile(self.get_color_maps()[inst["class"]], (inst["points"].shape[0], 1)) for inst in maps], axis=0)
+        cloud.points = o3d.utility.Vector3dVector(pts)
+        cloud.colors = o3d.utility.Vector3dVector(cols / 255.)
+        o3d.io.write_point_cloud(pcd_path, cloud)
+
+    def save_xyz(self, maps, xyz_path):
+        np.savetxt(xyz_path, np.concatenate([inst["points"] for inst in maps], axis=0), fmt="%.3f")
+
+
+class CameraManager(BaseManager):
+    def __init__(self, clip_path, camera_name, output_size=(540, 960), undisort=True, device=None):
+        super(CameraManager, self).__init__()
+        dr = DatasetReader(clip_path)
+        self.dr = dr
+        self.clip_path = clip_path
+        self.camera_name = camera_name
+        self.chassis2camera = dr.get_extrinsic("chassis", camera_name)
+        intrinsics = dr.get_intrinsics(camera_name)
+        self.K_origin = intrinsics["K"]
+        self.d_origin = intrinsics["d"]
+        self.width_origin = intrinsics["width"]
+        self.height_origin = intrinsics["height"]
+        self.width = output_size[1]
+        self.height = output_size[0]
+        if undisort:
+            self.d = []
+        # intrinsics of the resized output: rows 0 / 1 scaled by the width / height ratio
+        self.K = self.K_origin.copy()
+        self.K[0, :] = self.K[0, :] * self.width / self.width_origin
+        self.K[1, :] = self.K[1, :] * self.height / self.height_origin
+        self._device = device
+
+    def get_chassis2camera(self):
+        return self.chassis2camera
+
+    def project_to_image(self, maps):
+        """Camera-frame instances -> visible (v,u) float64 per instance; empty instances dropped."""
+        if len(maps) == 0:
+            return []
+        flat, offsets, classes = pack_instances(maps)
+        vu, out_offsets = get_runtime(self._device).project_points(flat, offsets, self.K, self.width, self.height)
+        return unpack_instances(vu, out_offsets, classes)
+
+    def transform_project_to_image(self, maps_chassis):
+        """Fused chassis->camera transform + projection (cama/dataset.py:110-115 in one pass)."""
+        if len(maps_chassis) == 0:
+            return []
+        flat, offsets, classes = pack_instances(maps_chassis)
+        vu, out_offsets = get_runtime(self._device).project_points(flat, offsets, self.K, self.width, self.height,
+                                                                    T=np.asarray(self.chassis2camera, dtype=np.float64))
+        return unpack_instances(vu, out_offsets, classes)
+
+    def render_maps(self, image, maps_2d):
+        """Stamp every point as a radius-2 filled disc, instance after instance, in place."""
+        if len(maps_2d) == 0:
+            return image
+        flat, offsets, classes = pack_instances(maps_2d)
+        bgr = np.array([render_bgr_of_class(c) for c in classes], dtype=np.uint8).reshape(-1, 3)
+        return get_runtime(self._device).render_points(image, flat, offsets, bgr)
+
+    # ------------------------------------------------------------------ image files (host I/O)
+    def index2timestamp(self, index, sync):
+        return self.dr.attribute["sync" if sync else "unsync"][self.camera_name][index]
+
+    def get_image_path(self, index, sync):
+        return join(self.clip_path, self.camera_name, f"{self.index2timestamp(index, sync)}.jpg")
+
+    def get_instance_path(self, index, sync=True):
+        return join(self.clip_path, f"lane_ins_{self.camera_name}", f"{self.index2timestamp(index, sync)}.png")
+
+    def read_resized_instance_by_index(self, index, sync=True):
+        import cv2
+        raw = cv2.imread(self.get_instance_path(index, sync=sync), cv2.IMREAD_ANYDEPTH)
+        return self.resize_image(raw, interpolation=cv2.INTER_NEAREST)
+
+    def read_resized_image_by_index(self, index, sync=True):
+        return self.read_resized_image(self.get_image_path(index, sync))
+
+    def resize_image(self, image, interpolation=1):
+        """Undistort + resize to the output size (reference :232-240; interpolation 1 = cv2.INTER_LINEAR)."""
+        import cv2
+        distortion = self.d_origin if self.d == [] else self.d
+        mapx, mapy = cv2.initUndistortRectifyMap(self.K_origin, distortion, None, self.K, (self.width, self.height), cv2.CV_32FC1)
+        return cv2.remap(image, mapx, mapy, interpolation=interpolation)
+
+    def read_resized_image(self, image_path):
+        import cv2
+        return self.resize_image(cv2.imread(image_path))

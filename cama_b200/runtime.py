@@ -1,0 +1,178 @@
+"""Device runtime: one libcama_b200 context per GPU, torch tensors as the device-memory container.
+
+Everything that touches the GPU goes through here.  There is no CPU fallback anywhere in the
+package: without a CUDA device (or without the built library) these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _native as N
+
+_RUNTIMES = {}
+_LOCK = threading.Lock()
+
+CROP_KEYS = ("x_min", "x_max", "y_min", "y_max", "z_min", "z_max")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Runtime:
+    """Context + scratch memory for one CUDA device."""
+
+    def __init__(self, index):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cama_b200 needs a CUDA device (B200, sm_100a); it has no CPU path")
+        self.index = index
+        self.device = torch.device("cuda", index)
+        handle = ctypes.c_void_p()
+        N.check(N.lib().cama_ctx_create(index, ctypes.byref(handle)))
+        self.ctx = handle
+        self._scratch = {}
+
+    # -------------------------------------------------------------- plumbing
+    def stream(self):
+        """The torch current stream of this device as the void* the C ABI takes."""
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    def launches(self):
+        n = ctypes.c_uint64()
+        N.check(N.lib().cama_ctx_launch_count(self.ctx, ctypes.byref(n)))
+        return int(n.value)
+
+    def sm_count(self):
+        n = ctypes.c_int()
+        N.check(N.lib().cama_ctx_sm_count(self.ctx, ctypes.byref(n)))
+        return int(n.value)
+
+    def scratch(self, name, nbytes):
+        """A cached uint8 device buffer of at least nbytes (grown geometrically, 512-B aligned by torch)."""
+        torch = _torch()
+        buf = self._scratch.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._scratch[name] = buf
+        return buf
+
+    def to_device(self, array, dtype=None):
+        torch = _torch()
+        arr = np.ascontiguousarray(array, dtype=dtype)
+        if arr.size == 0:
+            return torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)), device=self.device)
+        return torch.from_numpy(arr).to(self.device, non_blocking=False)
+
+    @staticmethod
+    def ptr(tensor):
+        return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None and tensor.numel() > 0 else ctypes.c_void_p(0)
+
+    # -------------------------------------------------------------- per-call operators (numpy in / numpy out)
+    def transform_points(self, points, T):
+        """cama_transform_points: (n,3) float32/float64 -> (n,3) float64 = (T @ [p;1])[:3]."""
+        torch = _torch()
+        pts = np.ascontiguousarray(points)
+        if pts.dtype != np.float32:
+            pts = pts.astype(np.float64, copy=False)
+        n = pts.shape[0]
+        T64 = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        d_in = self.to_device(pts)
+        d_out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        N.check(N.lib().cama_transform_points(self.ctx, self.ptr(d_in), int(pts.dtype == np.float32), n, N.dptr(T64),
+                                              self.ptr(d_out), self.stream()))
+        return d_out.cpu().numpy()
+
+    def _compact_scratch(self, n):
+        need = ctypes.c_size_t()
+        N.check(N.lib().cama_compact_workspace_bytes(n, ctypes.byref(need)))
+        return self.scratch("compact", need.value), need.value
+
+    def crop_points(self, flat, offsets, box6, T=None):
+        """cama_crop_points on a flat instance list -> (survivors (m,3) f64, new offsets)."""
+        torch = _torch()
+        pts = np.ascontiguousarray(flat)
+        is_f32 = pts.dtype == np.float32
+        if not is_f32:
+            pts = pts.astype(np.float64, copy=False)
+        if is_f32 and T is None:
+            pts, is_f32 = pts.astype(np.float64), False
+        n, n_inst = pts.shape[0], len(offsets) - 1
+        d_in = self.to_device(pts)
+        d_off = self.to_device(offsets, np.int64)
+        d_out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        d_out_off = torch.empty(n_inst + 1, dtype=torch.int64, device=self.device)
+        ws, ws_bytes = self._compact_scratch(n)
+        T64 = None if T is None else np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        box = np.ascontiguousarray(box6, dtype=np.float64)
+        N.check(N.lib().cama_crop_points(self.ctx, self.ptr(d_in), int(is_f32), n, N.dptr(T64), N.dptr(box), self.ptr(d_off), n_inst,
+                                         self.ptr(d_out), self.ptr(d_out_off), self.ptr(ws), ws_bytes, self.stream()))
+        out_off = d_out_off.cpu().numpy()
+        return d_out[:int(out_off[-1])].cpu().numpy(), out_off
+
+    def project_points(self, flat, offsets, K, width, height, T=None):
+        """cama_project_points -> ((k,2) f64 (v,u), new offsets)."""
+        torch = _torch()
+        pts = np.ascontiguousarray(flat, dtype=np.float64)
+        n, n_inst = pts.shape[0], len(offsets) - 1
+        d_in = self.to_device(pts)
+        d_off = self.to_device(offsets, np.int64)
+        d_out = torch.empty((n, 2), dtype=torch.float64, device=self.device)
+        d_out_off = torch.empty(n_inst + 1, dtype=torch.int64, device=self.device)
+        ws, ws_bytes = self._compact_scratch(n)
+        T64 = None if T is None else np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        K64 = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        N.check(N.lib().cama_project_points(self.ctx, self.ptr(d_in), n, N.dptr(T64), N.dptr(K64), int(width), int(height),
+                                            self.ptr(d_off), n_inst, self.ptr(d_out), self.ptr(d_out_off), self.ptr(ws), ws_bytes,
+                                            self.stream()))
+        out_off = d_out_off.cpu().numpy()
+        return d_out[:int(out_off[-1])].cpu().numpy(), out_off
+
+    def render_points(self, image, vu_flat, offsets, inst_bgr):
+        """cama_render_points: stamps into ``image`` (uint8 HxWx3 numpy) in place and returns it."""
+        torch = _torch()
+        assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3, "image must be uint8 [H,W,3]"
+        vu = np.ascontiguousarray(vu_flat, dtype=np.float64)
+        n, n_inst = vu.shape[0], len(offsets) - 1
+        if n == 0:
+            return image
+        height, width = image.shape[:2]
+        d_img = self.to_device(image)
+        d_vu = self.to_device(vu)
+        d_off = self.to_device(offsets, np.int64)
+        d_bgr = self.to_device(inst_bgr, np.uint8)
+        need = ctypes.c_size_t()
+        N.check(N.lib().cama_render_workspace_bytes(height, width, ctypes.byref(need)))
+        ws = self.scratch("render", need.value)
+        N.check(N.lib().cama_render_points(self.ctx, self.ptr(d_vu), n, self.ptr(d_off), n_inst, self.ptr(d_bgr), self.ptr(d_img),
+                                           height, width, self.ptr(ws), need.value, self.stream()))
+        result = d_img.cpu().numpy()
+        if image.flags.writeable:
+            image[...] = result            # the reference draws in place (cv2.circle mutates its argument)
+            return image
+        return result
+
+
+def get_runtime(device=None) -> Runtime:
+    """Runtime of ``device`` (int, torch.device or None = current CUDA device)."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("cama_b200 needs a CUDA device (B200, sm_100a); it has no CPU path")
+    if device is None:
+        index = torch.cuda.current_device()
+    elif isinstance(device, int):
+        index = device
+    else:
+        dev = torch.device(device)
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _LOCK:
+        if index not in _RUNTIMES:
+            _RUNTIMES[index] = Runtime(index)
+        return _RUNTIMES[index]

@@ -1,0 +1,168 @@
+/*
+ * cama_b200 — C ABI of the B200-native reprojection hot path of manymuch/CAMA.
+ *
+ * The reference (pure Python, no FFI of its own) implements this path in
+ * cama/reproject.py + cama/pose_transformer.py, driven by cama/dataset.py
+ * (file:line below are relative to the reference tree).  This header is what a
+ * binding in any host language loads from libcama_b200.so; cama_b200/_native.py
+ * is the ctypes binding shipped with the package, INTEGRATION.md shows the stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every entry point returns a cama_status (0 = ok, < 0 = error); the text of the
+ *     last error of the calling thread is cama_last_error().  Nothing throws.
+ *   - the library never allocates caller-visible memory: all buffers (inputs,
+ *     outputs, scratch workspace) are owned by the caller.  "device" pointers are
+ *     CUDA device pointers of the context's device (e.g. torch.Tensor.data_ptr());
+ *     "host" pointers are ordinary host memory, read synchronously during the call.
+ *   - every device call takes the cudaStream_t to enqueue on as a void* (0 = legacy
+ *     default stream) and returns after enqueueing; no call synchronises unless its
+ *     comment says so.  The context holds no mutable state besides a launch counter,
+ *     so calls on different streams are independent.
+ *   - images are uint8 [H,W,3] BGR, row-major, as in the reference (cv2 convention).
+ *   - point arrays are row-major [n,3] (x,y,z) or [n,2] (v,u) = (row,col), like the
+ *     reference's "points" arrays; ragged instance lists are flat arrays plus
+ *     int64 offsets[I+1] (instance i owns rows offsets[i]..offsets[i+1]).
+ *   - arithmetic contract (bit-exactness with the reference's NumPy/BLAS path): every
+ *     matrix-vector product accumulates in index order with fused multiply-adds,
+ *     a0*b0 first; divisions are IEEE double.  See DESIGN.md "Numerics".
+ */
+#ifndef CAMA_B200_H_
+#define CAMA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAMA_ABI_VERSION 1
+#define CAMA_MAX_CAMERAS 8
+
+typedef enum cama_status {
+    CAMA_OK = 0,
+    CAMA_E_INVALID = -1,    /* bad argument (null pointer, negative size, misaligned buffer ...) */
+    CAMA_E_CUDA = -2,       /* a CUDA runtime call failed; text in cama_last_error() */
+    CAMA_E_WORKSPACE = -3,  /* caller's workspace is smaller than cama_*_workspace_bytes() */
+    CAMA_E_CAPACITY = -4,   /* clip path: record pool overflowed; rerun with the capacity in cama_clip_stats */
+    CAMA_E_NODEVICE = -5,   /* no CUDA device / not an sm_100 device */
+    CAMA_E_UNSUPPORTED = -6 /* shape outside what the requested mode supports */
+} cama_status;
+
+typedef struct cama_ctx cama_ctx;
+
+/* ---- library / context -------------------------------------------------------------------- */
+int cama_abi_version(void);
+const char *cama_last_error(void);
+int cama_device_count(int *count);
+/* Binds a context to a device (does not change the caller's current device permanently). */
+int cama_ctx_create(int device, cama_ctx **out);
+int cama_ctx_destroy(cama_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
+int cama_ctx_launch_count(const cama_ctx *ctx, uint64_t *count);
+int cama_ctx_sm_count(const cama_ctx *ctx, int *count);
+
+/* ---- per-call operators: one per reference method ------------------------------------------ */
+
+/* MapManager.transform_3d_instance_maps (cama/reproject.py:108-116): out = (T @ [p;1])[:3].
+ *   pts      device, [n,3] float32 (pts_is_f32 != 0) or float64
+ *   T        host,   16 doubles row-major (a float32 matrix is widened by the caller, exactly)
+ *   out      device, [n,3] float64 */
+int cama_transform_points(cama_ctx *ctx, const void *pts, int pts_is_f32, int64_t n, const double *T,
+                          double *out, void *stream);
+
+/* Scratch needed by the three compacting operators below for n points. */
+int cama_compact_workspace_bytes(int64_t n, size_t *bytes);
+
+/* MapManager.crop_3d_instance_maps (cama/reproject.py:118-131), optionally fused with the
+ * transform that always precedes it (cama/dataset.py:99-105).  Order-preserving compaction.
+ *   pts          device [n,3] (float32 or float64, see pts_is_f32)
+ *   T            host 16 doubles or NULL (no transform; pts must then be float64)
+ *   box          host 6 doubles {x_min,x_max,y_min,y_max,z_min,z_max}, inclusive
+ *   in_offsets   device int64 [n_inst+1]
+ *   out_pts      device [n,3] float64 (first out_offsets[n_inst] rows valid)
+ *   out_offsets  device int64 [n_inst+1]; an instance with no survivor has equal neighbours */
+int cama_crop_points(cama_ctx *ctx, const void *pts, int pts_is_f32, int64_t n, const double *T,
+                     const double *box, const int64_t *in_offsets, int64_t n_inst, double *out_pts,
+                     int64_t *out_offsets, void *workspace, size_t workspace_bytes, void *stream);
+
+/* CameraManager.project_to_image (cama/reproject.py:187-205), optionally fused with the
+ * chassis->camera transform that precedes it (cama/dataset.py:110-115).
+ *   pts          device [n,3] float64
+ *   T            host 16 doubles or NULL
+ *   K            host 9 doubles row-major (already rescaled to the output size)
+ *   out_vu       device [n,2] float64, (v,u) per visible point, order preserved
+ *   out_offsets  device int64 [n_inst+1] */
+int cama_project_points(cama_ctx *ctx, const double *pts, int64_t n, const double *T, const double *K,
+                        int width, int height, const int64_t *in_offsets, int64_t n_inst,
+                        double *out_vu, int64_t *out_offsets, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* CameraManager.render_maps (cama/reproject.py:246-257): stamps the radius-2 filled disc
+ * (13 px, |dx|+|dy|<=2, border-clipped) of every point, instance after instance (painter's
+ * order), into the image IN PLACE.
+ *   vu           device [n,2] float64 (v,u); centres are truncated like astype(np.int32)
+ *   in_offsets   device int64 [n_inst+1]
+ *   inst_bgr     device uint8 [n_inst,3]
+ *   image        device uint8 [height,width,3], in/out
+ *   workspace    cama_render_workspace_bytes(height,width) bytes */
+int cama_render_workspace_bytes(int height, int width, size_t *bytes);
+int cama_render_points(cama_ctx *ctx, const double *vu, int64_t n, const int64_t *in_offsets,
+                       int64_t n_inst, const uint8_t *inst_bgr, uint8_t *image, int height, int width,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- the batched clip path: the loop of cama/dataset.py:78-126 in one call ------------------- */
+
+enum { CAMA_VERTEX_F32X4 = 0,   /* float4 {x,y,z, bit-cast int32 instance ordinal} */
+       CAMA_VERTEX_F64X3 = 1 }; /* double[n,3] + int32 vertex_instance[n] */
+enum { CAMA_CLIP_AUTO = 0,      /* BINNED when the shape allows it, else PLANE */
+       CAMA_CLIP_PLANE = 1,     /* global uint32 centre-id plane + per-pixel dilation (simple, any shape) */
+       CAMA_CLIP_BINNED = 2 };  /* band-binned centre records + shared-memory plane + bulk-store raster */
+
+typedef struct cama_clip_desc {
+    uint32_t struct_bytes;          /* sizeof(cama_clip_desc), ABI guard */
+    int32_t mode;                   /* CAMA_CLIP_* */
+    int32_t n_frames, n_cams, n_instances;
+    int32_t height, width;
+    int32_t vertex_layout;          /* CAMA_VERTEX_* */
+    int64_t n_vertices;
+    const void *vertices;           /* device */
+    const int32_t *vertex_instance; /* device, only for CAMA_VERTEX_F64X3 */
+    const float *world2chassis;     /* device float32 [n_frames,16]: np.linalg.inv(chassis2world.astype(f32)) (cama/dataset.py:92,99) */
+    const double *chassis2cam;      /* host   float64 [n_cams,16]  (cama/reproject.py:170) */
+    const double *intrinsics;       /* host   float64 [n_cams,9]   rescaled K (cama/reproject.py:180-182) */
+    double crop_box[6];             /* x_min,x_max,y_min,y_max,z_min,z_max (cama/reproject.py:28-34) */
+    const uint8_t *instance_bgr;    /* device uint8 [n_instances,3]: colour of each instance (cama/reproject.py:251-254) */
+    const uint8_t *background;      /* device uint8 [n_frames,n_cams,H,W,3] or NULL (= black); may alias frames */
+    uint8_t *frames;                /* device uint8 [n_frames,n_cams,H,W,3] out */
+    int32_t *crop_counts;           /* device int32 [n_frames,n_instances] or NULL; caller zero-fills */
+    int32_t *visible_counts;        /* device int32 [n_frames,n_cams,n_instances] or NULL; caller zero-fills */
+    double *vu_dense;               /* device float64 [n_frames,n_cams,n_vertices,2] or NULL; NaN where not visible */
+    int64_t record_capacity;        /* BINNED: centre records per frame the workspace is sized for; 0 = default */
+} cama_clip_desc;
+
+typedef struct cama_clip_stats {
+    int64_t records_total;          /* centre records emitted (incl. band-halo duplicates) */
+    int64_t records_max_per_frame;  /* largest per-frame count: the capacity a rerun needs */
+    int64_t record_capacity;        /* per-frame capacity this run used */
+    int32_t overflow;               /* != 0: some frame exceeded the capacity, frames are incomplete */
+    int32_t mode;                   /* mode actually used (CAMA_CLIP_PLANE / CAMA_CLIP_BINNED) */
+    int32_t band_rows;              /* BINNED: output rows per band */
+    int32_t n_bands;
+} cama_clip_stats;
+
+/* Workspace (device bytes) a cama_clip_render call with this descriptor needs. */
+int cama_clip_workspace_bytes(const cama_clip_desc *desc, size_t *bytes);
+/* Enqueues the whole clip.  workspace: device, 256-byte aligned. */
+int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *desc, void *workspace, size_t workspace_bytes,
+                     void *stream);
+/* Synchronises `stream` and reads back the counters of the last cama_clip_render that used this
+ * workspace.  Returns CAMA_E_CAPACITY when the record pool overflowed. */
+int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *desc, const void *workspace, void *stream,
+                         cama_clip_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAMA_B200_H_ */
