@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the reprojection hot path (BASELINE.json metric: reprojected camera-frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config2]
+
+A step = one pass of the hot path over one clip: every frame x camera x dense map vertex
+transformed, cropped, projected, masked and stamped into the uint8 [F,C,540,960,3] frames
+(reference loop: cama/dataset.py:78-126).  Workload at N=1 = BASELINE.json configs[1]
+(40 frames x 6 cameras, 200 polylines, 0.1 m densify => ~96 k vertices); at N>1 every rank renders
+its own such clip (the scenes of a site, seeds 0..N-1), i.e. weak scaling, no data-path collective;
+`allgather` additionally reports the NCCL all-gather of the rendered frames north_star asks for.
+
+One JSON line on rank 0:
+  value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM
+  e2e          same metric through Reproject.__call__: host pose lookup + float32 inverse, H2D of
+               the poses from pinned memory, render, D2H of every frame into pinned host memory
+  roofline     the raster kernel (writes every frame byte once) against the measured HBM peak
+  cpu_baseline the NumPy/OpenCV oracle (= the reference's loop) on this box's host cores
+`--impl reference` times that CPU path alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+METRIC = "reprojected camera-frames/sec"
+UNIT = "cam-frames/s"
+H, W = 540, 960
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config2_cama", "config3"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--ramp-seconds", type=float, default=0.4, help="untimed clock-ramp loop before the warm-up (0 under ncu)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded cpu_baseline sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_clip(workload, root, seed):
+    from cama_b200 import synth
+    if workload == "config3":
+        spec = synth.config3_spec(seed=1 + seed, name=f"config3_s{seed}")
+        spec.write_cama = False
+        dataset = "nuscenes"
+    elif workload == "config2_cama":
+        spec = synth.config2_spec(seed=seed, name=f"config2cama_s{seed}")
+        spec.write_nuscenes = False
+        dataset = "cama"
+    else:
+        spec = synth.config2_spec(seed=seed, name=f"config2_s{seed}")
+        spec.write_cama = False
+        dataset = "nuscenes"
+    return synth.write_clip(spec, root), dataset
+
+
+def workload_name(workload):
+    return {"config2": "BASELINE.json configs[1]: one clip, 40 frames x 6 cams, 200 polylines, 0.1 m densify (nuScenes-style labels)",
+            "config2_cama": "configs[1] with CAMA labels: 40 frames x 6 cams, 200 polylines, 0.1 px densify (~1.0 M vertices)",
+            "config3": "BASELINE.json configs[2]: site, 320 frames x 6 cams, 1600 polylines, 0.1 m densify"}[workload]
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while a region runs."""
+
+    def __init__(self, index, period_s=0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._loaded = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                if self._loaded.is_set():
+                    self.samples.append(mhz)
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for name, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def load(self, on):
+        (self._loaded.set if on else self._loaded.clear)()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline(clip, dataset, budget_s):
+    """Bounded sample of the workload on the host cores -> the cpu_baseline object."""
+    from cama_b200 import synth
+    from oracle.cpu_bench import CpuRunner, usable_cores
+    runner = CpuRunner(synth.CAMA_CONFIGS, clip, dataset)
+    try:
+        n_frames = runner.n_frames
+        probe_frames = max(1, min(2, n_frames))
+        dt1, cf1 = runner.step("numpy", parallel=False, frames=probe_frames)      # as shipped: one process
+        per_frame = dt1 / probe_frames
+        # whole clip over all cores if it fits the budget, else as many frames as do
+        est = per_frame * n_frames / max(runner.workers, 1) * 1.5
+        frames = n_frames if est <= budget_s else max(runner.workers, int(budget_s / est * n_frames))
+        runner.step("numpy", parallel=True, frames=min(frames, runner.workers))   # warm the pool
+        dt, cf = runner.step("numpy", parallel=True, frames=frames)
+        dtc, cfc = runner.step("c", parallel=True, frames=n_frames)
+        dtc1, cfc1 = runner.step("c", parallel=False, frames=min(n_frames, 8))
+        return {"value": cf / dt, "unit": UNIT, "cores": runner.workers, "kind": "port",
+                "sample": f"{frames} of {n_frames} frames x {runner.n_cams} cams of the same clip, NumPy/OpenCV oracle "
+                          f"(reference loop structure), frames sharded over {runner.workers} processes; blank backgrounds",
+                "single_process": {"value": cf1 / dt1, "unit": UNIT, "cores": 1, "sample": f"{probe_frames} frames"},
+                "c_port": {"value": cfc / dtc, "unit": UNIT, "cores": runner.workers, "single_core": cfc1 / dtc1,
+                           "note": "scalar C restatement (oracle/oracle.c), not what the reference runs"},
+                "host": {"cpu": cpu_model(), "usable_cores": usable_cores(), "os_cpu_count": os.cpu_count()}}
+    finally:
+        runner.close()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (NumPy/OpenCV port; the reference is pure Python
+    and /root/reference does not exist on the GPU box) on all host cores."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from cama_b200 import synth
+    from oracle.cpu_bench import CpuRunner
+    with tempfile.TemporaryDirectory() as root:
+        clip, dataset = make_clip(args.workload, root, 0)
+        runner = CpuRunner(synth.CAMA_CONFIGS, clip, dataset)
+        try:
+            # bounded sample per step: the whole clip when it is small, else ~4 s worth of frames
+            dt_probe, _ = runner.step("numpy", parallel=True, frames=runner.workers)
+            per_step_frames = runner.n_frames
+            est = dt_probe * runner.n_frames / runner.workers
+            budget = 240.0 / max(args.steps + args.warmup, 1)
+            if est > budget:
+                per_step_frames = max(runner.workers, int(runner.n_frames * budget / est))
+            for _ in range(args.warmup):
+                runner.step("numpy", parallel=True, frames=per_step_frames)
+            total_t, total_cf = 0.0, 0
+            for _ in range(args.steps):
+                dt, cf = runner.step("numpy", parallel=True, frames=per_step_frames)
+                total_t += dt
+                total_cf += cf
+            value = total_cf / total_t
+            sample = (f"{per_step_frames} of {runner.n_frames} frames x {runner.n_cams} cams per step, NumPy/OpenCV oracle "
+                      f"(reference loop structure), frames sharded over {runner.workers} processes; blank backgrounds")
+            line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": workload_name(args.workload), "frames": runner.n_frames, "cams": runner.n_cams,
+                               "cam_frames_per_step": per_step_frames * runner.n_cams},
+                    "cpu_baseline": {"value": value, "unit": UNIT, "cores": runner.workers, "kind": "port", "sample": sample,
+                                     "host": {"cpu": cpu_model(), "os_cpu_count": os.cpu_count()}},
+                    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0}
+            print(json.dumps(line), flush=True)
+        finally:
+            runner.close()
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    tmp = tempfile.TemporaryDirectory()
+    clip, dataset = make_clip(args.workload, tmp.name, rank)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(clip, dataset, args.cpu_seconds)        # before CUDA is initialised (forks workers)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from cama_b200 import synth
+    from cama_b200 import _native as N
+    from cama_b200.batched import Reproject
+
+    rp = Reproject(synth.CAMA_CONFIGS, clip, device=local_rank)
+    rt = rp.rt
+    res = rp.resident(dataset)
+    idx, w2c_host = rp.frame_poses(dataset)
+    F, C = len(idx), rp.renderer.n_cams
+    cam_frames = F * C
+    w2c_dev = torch.from_numpy(w2c_host).to(rt.device)
+    frames = torch.empty((F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=False)
+
+    # sizing pass: settles the record-pool capacity (checked, synchronous) and verifies no overflow
+    rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=True)
+    stats = dict(rp.renderer.last_stats)
+    assert not stats["overflow"]
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # untimed clock ramp (a 100-us step does not lift an idle GPU to its boost clock), then W warm-up steps
+    t_end = time.perf_counter() + args.ramp_seconds
+    while time.perf_counter() < t_end:
+        step()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    # ---- device-resident throughput: exactly K steps between two events
+    rt.profile_enable(args.steps)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = rt.launches()
+    barrier()
+    sampler.load(True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sampler.load(False)
+    launches = rt.launches() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    phases = rt.profile_read()                      # [K, 4] ms
+    rt.profile_enable(0)
+
+    # ---- end to end through the public call: host poses -> frames in pinned host memory
+    rp(dataset, mode=args.mode)                     # allocates the pinned result buffer, untimed
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    sampler.load(True)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, host_frames = rp(dataset, mode=args.mode)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.load(False)
+    checksum = int(host_frames[:, :, ::9, ::9].sum())
+
+    # ---- optional: the all-gather of rendered frames north_star names (N > 1)
+    gather = None
+    if world > 1 and not args.no_allgather:
+        full = torch.empty((world * F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+        for _ in range(2):
+            dist.all_gather_into_tensor(full, frames)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record(stream)
+        for _ in range(args.steps):
+            step()
+            dist.all_gather_into_tensor(full, frames)
+        g1.record(stream)
+        barrier()
+        gather = g0.elapsed_time(g1)
+
+    clocks = sampler.stop()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=rt.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total = max_over_ranks(ms_total)
+    e2e_s = max_over_ranks(e2e_s)
+    if gather is not None:
+        gather = max_over_ranks(gather)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        raster_ms = float(np.mean(phases[:, 3]))
+        frame_bytes = cam_frames * H * W * 3
+        vertex_bytes = F * 12 * res.n_vertices
+        achieved = frame_bytes / (raster_ms * 1e-3) / 1e9
+        ms_per_step = ms_total / args.steps
+        line = {
+            "metric": METRIC, "value": world * cam_frames / (ms_per_step * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload) + (f"; one such clip per GPU (seeds 0..{world - 1})" if world > 1 else ""),
+                       "frames": F, "cams": C, "cam_frames_per_step_per_gpu": cam_frames, "vertices": res.n_vertices,
+                       "instances": res.n_instances, "raster_mode": {1: "plane", 2: "binned"}[stats["mode"]],
+                       "l2": f"no flush needed: every step writes {frame_bytes / 1e6:.0f} MB of frames (> 126 MB L2); "
+                             f"the {res.n_vertices * 16 / 1e6:.1f} MB vertex array is L2-resident by nature (re-read for each of the {F} frames)",
+                       "background": "blank (black) frames, as in the reference CPU timing"},
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "e2e": {"value": world * cam_frames * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(w2c_host.nbytes), "d2h_bytes_per_step": int(frame_bytes),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "call": "cama_b200.batched.Reproject.__call__(dataset): host pose seek + float32 inverse, pinned H2D, "
+                            "cama_clip_render, D2H of all frames into pinned host memory",
+                    "d2h_gbs": frame_bytes * e2e_steps / e2e_s / 1e9, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "binned_raster_kernel" if stats["mode"] == 2 else "plane_raster_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "traffic": None, "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": raster_ms,
+                         "whole_step": {"algorithmic_bytes": int(frame_bytes + vertex_bytes),
+                                        "achieved": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9,
+                                        "frac": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
+                         "phase_ms": {name: float(np.mean(phases[:, i])) for i, name in enumerate(N.PHASE_NAMES)}},
+            "records": {k: int(stats[k]) for k in ("records_total", "records_max_per_frame", "record_capacity")},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if gather is not None:
+            ms_g = gather / args.steps
+            line["allgather"] = {"value": world * cam_frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                                 "bytes_received_per_gpu": int((world - 1) * frame_bytes),
+                                 "note": "render + NCCL all_gather_into_tensor of the uint8 frames of all ranks"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    tmp.cleanup()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,8 @@ CAMA_E_INVALID, CAMA_E_CUDA, CAMA_E_WORKSPACE, CAMA_E_CAPACITY, CAMA_E_NODEVICE,
 VERTEX_F32X4, VERTEX_F64X3 = 0, 1
 CLIP_AUTO, CLIP_PLANE, CLIP_BINNED = 0, 1, 2
 MAX_CAMERAS = 8
+CLIP_PHASES = 4
+PHASE_NAMES = ("prep", "geometry", "sort", "raster")
 ABI_VERSION = 1
 
 
@@ -59,6 +61,9 @@ SIGNATURES = {
     "cama_ctx_destroy": (c_int, [c_void_p]),
     "cama_ctx_launch_count": (c_int, [c_void_p, POINTER(c_uint64)]),
     "cama_ctx_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "cama_ctx_profile_enable": (c_int, [c_void_p, c_int]),
+    "cama_ctx_profile_calls": (c_int, [c_void_p, POINTER(c_int)]),
+    "cama_ctx_profile_read": (c_int, [c_void_p, c_int, POINTER(ctypes.c_float)]),
     "cama_transform_points": (c_int, [c_void_p, c_void_p, c_int, c_int64, POINTER(c_double), c_void_p, c_void_p]),
     "cama_compact_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
     "cama_crop_points": (c_int, [c_void_p, c_void_p, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_void_p, c_int64,

@@ -594,6 +594,11 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
+    // phase events of this call, when profiling is on (cama_ctx_profile_enable)
+    cudaEvent_t *prof = nullptr;
+    if (ctx->prof_calls < ctx->prof_capacity) prof = ctx->prof_events.data() + (size_t)(ctx->prof_calls++) * (CAMA_CLIP_PHASES + 1);
+    auto mark = [&](int i) { return prof ? cudaEventRecord(prof[i], s) : cudaSuccess; };
+    CAMA_CUDA_TRY(mark(0));
 
     CamBlock cams;
     for (int c = 0; c < CAMA_MAX_CAMERAS; ++c) {
@@ -631,14 +636,18 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         a.plane = reinterpret_cast<unsigned *>(ws + p.off_plane);
         const size_t px = (size_t)d->n_frames * d->n_cams * d->height * d->width;
         CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
+        CAMA_CUDA_TRY(mark(1));
         if (units > 0) {
             if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
             else clip_geometry_kernel<CAMA_VERTEX_F64X3, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
             CAMA_LAUNCHED(ctx);
         }
+        CAMA_CUDA_TRY(mark(2));
+        CAMA_CUDA_TRY(mark(3));
         plane_raster_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(a.plane, lut, d->background, d->frames, d->height, d->width,
                                                                         (long long)d->n_frames * d->n_cams);
         CAMA_LAUNCHED(ctx);
+        CAMA_CUDA_TRY(mark(4));
         return CAMA_OK;
     }
 
@@ -651,11 +660,13 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
     unsigned *counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
+    CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
         if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
         else clip_geometry_kernel<CAMA_VERTEX_F64X3, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
         CAMA_LAUNCHED(ctx);
     }
+    CAMA_CUDA_TRY(mark(2));
     bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.fcount, d->n_frames, p.cap, stats);
     CAMA_LAUNCHED(ctx);
     {
@@ -663,6 +674,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         record_scatter_kernel<<<dim3(gx, (unsigned)d->n_frames), 256, 0, s>>>(a.unsorted, a.fcount, start, p.cap, (long long)d->n_frames * p.cap, sorted);
         CAMA_LAUNCHED(ctx);
     }
+    CAMA_CUDA_TRY(mark(3));
     RasterArgs r{};
     r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
     r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
@@ -671,6 +683,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * 2);
     binned_raster_kernel<<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
     CAMA_LAUNCHED(ctx);
+    CAMA_CUDA_TRY(mark(4));
     return CAMA_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <vector>
 
 #include "../../include/cama_b200.h"
 
@@ -68,4 +69,8 @@ struct cama_ctx {
     int cc_major = 0, cc_minor = 0;
     size_t smem_optin = 0;
     std::atomic<uint64_t> launches{0};
+    // phase profiling (cama_ctx_profile_*): (CAMA_CLIP_PHASES + 1) events per recorded call
+    std::vector<cudaEvent_t> prof_events;
+    int prof_capacity = 0;
+    int prof_calls = 0;
 };

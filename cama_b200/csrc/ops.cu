@@ -260,7 +260,41 @@ int cama_ctx_create(int device, cama_ctx **out) {
 }
 
 int cama_ctx_destroy(cama_ctx *ctx) {
+    if (ctx) cama_ctx_profile_enable(ctx, 0);
     delete ctx;
+    return CAMA_OK;
+}
+
+int cama_ctx_profile_enable(cama_ctx *ctx, int max_calls) {
+    CAMA_REQUIRE(ctx && max_calls >= 0 && max_calls <= (1 << 20), "bad argument");
+    DeviceGuard guard(ctx->device);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    ctx->prof_capacity = 0;
+    ctx->prof_calls = 0;
+    ctx->prof_events.reserve((size_t)max_calls * (CAMA_CLIP_PHASES + 1));
+    for (int i = 0; i < max_calls * (CAMA_CLIP_PHASES + 1); ++i) {
+        cudaEvent_t e;
+        CAMA_CUDA_TRY(cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+    }
+    ctx->prof_capacity = max_calls;
+    return CAMA_OK;
+}
+
+int cama_ctx_profile_calls(const cama_ctx *ctx, int *calls) {
+    CAMA_REQUIRE(ctx && calls, "NULL argument");
+    *calls = ctx->prof_calls;
+    return CAMA_OK;
+}
+
+int cama_ctx_profile_read(cama_ctx *ctx, int call, float *phase_ms) {
+    CAMA_REQUIRE(ctx && phase_ms, "NULL argument");
+    CAMA_REQUIRE(call >= 0 && call < ctx->prof_calls, "call %d was not recorded (%d recorded)", call, ctx->prof_calls);
+    DeviceGuard guard(ctx->device);
+    cudaEvent_t *e = ctx->prof_events.data() + (size_t)call * (CAMA_CLIP_PHASES + 1);
+    CAMA_CUDA_TRY(cudaEventSynchronize(e[CAMA_CLIP_PHASES]));
+    for (int p = 0; p < CAMA_CLIP_PHASES; ++p) CAMA_CUDA_TRY(cudaEventElapsedTime(&phase_ms[p], e[p], e[p + 1]));
     return CAMA_OK;
 }
 

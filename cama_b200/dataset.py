@@ -83,6 +83,21 @@ class ClipManager:
         pt.normalize2center()
         return pt
 
+    def _trajectory(self, dataset):
+        """(chassis->world PoseTransformer, frame stamps) of a label set; parsed once per clip
+        (the reference re-reads attribute.json and the odometry file on every yield_frame call)."""
+        cache = self.__dict__.setdefault("_trajectory_cache", {})
+        if dataset not in cache:
+            dr = DatasetReader(self.clip_path)
+            if dataset == "nuscenes":
+                pt = self.get_pt_nuscenes(dr)
+            elif dataset == "cama":
+                pt = self.get_pt_cama(dr)
+            else:
+                raise UnboundLocalError(f"unknown dataset {dataset!r}")     # the reference fails the same way
+            cache[dataset] = (pt, dr.get_sensor_timestamp(self.configs["camera_main"], sync=True))
+        return cache[dataset]
+
     def frame_poses(self, dataset):
         """[(image_idx, world2chassis float32 4x4)] for every renderable frame.
 
@@ -90,14 +105,7 @@ class ClipManager:
         interpolation and ``t_max_diff=0.5``; a ``RuntimeError`` from the lookup skips the frame;
         the pose is cast to float32 *before* ``np.linalg.inv``.
         """
-        dr = DatasetReader(self.clip_path)
-        if dataset == "nuscenes":
-            pt = self.get_pt_nuscenes(dr)
-        elif dataset == "cama":
-            pt = self.get_pt_cama(dr)
-        else:
-            raise UnboundLocalError(f"unknown dataset {dataset!r}")     # the reference fails the same way
-        stamps = dr.get_sensor_timestamp(self.configs["camera_main"], sync=True)
+        pt, stamps = self._trajectory(dataset)
         out = []
         for image_idx in range(1, len(stamps)):
             try:

@@ -55,6 +55,19 @@ class Runtime:
         N.check(N.lib().cama_ctx_sm_count(self.ctx, ctypes.byref(n)))
         return int(n.value)
 
+    def profile_enable(self, max_calls):
+        """Record per-phase CUDA events for the next ``max_calls`` clip renders (0 = off)."""
+        N.check(N.lib().cama_ctx_profile_enable(self.ctx, int(max_calls)))
+
+    def profile_read(self):
+        """-> float array [calls, CLIP_PHASES] of milliseconds (waits for the recorded calls)."""
+        calls = ctypes.c_int()
+        N.check(N.lib().cama_ctx_profile_calls(self.ctx, ctypes.byref(calls)))
+        out = np.zeros((calls.value, N.CLIP_PHASES), dtype=np.float32)
+        for i in range(calls.value):
+            N.check(N.lib().cama_ctx_profile_read(self.ctx, i, out[i].ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        return out
+
     def scratch(self, name, nbytes):
         """A cached uint8 device buffer of at least nbytes (grown geometrically, 512-B aligned by torch)."""
         torch = _torch()

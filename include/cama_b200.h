@@ -63,6 +63,16 @@ int cama_ctx_destroy(cama_ctx *ctx);
 int cama_ctx_launch_count(const cama_ctx *ctx, uint64_t *count);
 int cama_ctx_sm_count(const cama_ctx *ctx, int *count);
 
+/* Per-phase device timing of cama_clip_render (bench.py's roofline figure).  After
+ * cama_ctx_profile_enable(ctx, max_calls) every cama_clip_render records CUDA events on ITS OWN
+ * stream around its phases (no synchronisation, a few hundred ns each) until max_calls calls have
+ * been recorded; max_calls = 0 disables and frees the events.  cama_ctx_profile_read waits for
+ * call `call` (0-based since enable) to finish and returns the milliseconds of each phase. */
+#define CAMA_CLIP_PHASES 4 /* 0 prep + clears, 1 geometry, 2 bucket scan + scatter (BINNED), 3 raster */
+int cama_ctx_profile_enable(cama_ctx *ctx, int max_calls);
+int cama_ctx_profile_calls(const cama_ctx *ctx, int *calls);
+int cama_ctx_profile_read(cama_ctx *ctx, int call, float *phase_ms /* [CAMA_CLIP_PHASES] */);
+
 /* ---- per-call operators: one per reference method ------------------------------------------ */
 
 /* MapManager.transform_3d_instance_maps (cama/reproject.py:108-116): out = (T @ [p;1])[:3].
