@@ -17,6 +17,7 @@
 // shape restrictions, and an independent implementation the tests cross-check BINNED against.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -44,7 +45,7 @@ struct ClipArgs {
     // PLANE
     unsigned *plane;                   // [F,C,H,W]
     // BINNED
-    int band_rows, n_bands;
+    int band_rows, n_bands, x_bits;
     long long cap;                     // records per frame
     unsigned *fcount;                  // [F]
     unsigned *hist;                    // [F*C*NB]
@@ -141,13 +142,13 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, boo
         const int r = vi - b0 * rb;
         const unsigned bucket = (unsigned)((f * a.n_cams + c) * a.n_bands + b0);
         const unsigned key = (unsigned)(ord + 1) << 16;
-        warp_append(a, f, vis, bucket, key | (unsigned)((r + 2) * a.width + ui));
+        warp_append(a, f, vis, bucket, key | (unsigned)(((r + 2) << a.x_bits) | ui));
         // the two rows next to a band edge also matter to the neighbouring band (dilation radius 2)
         const bool up = vis && r < 2 && b0 > 0;
         const bool down = vis && r >= rb - 2 && b0 + 1 < a.n_bands;
         const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
         const int r2 = up ? r + rb : r - rb;
-        warp_append(a, f, up || down, bucket2, key | (unsigned)((r2 + 2) * a.width + ui));
+        warp_append(a, f, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
     }
 }
 
@@ -338,11 +339,17 @@ __device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix
 }
 
 constexpr int kRasterThreads = 256;
-constexpr int kStageRows = 3;              // rows per bulk store
+constexpr int kRasterWarps = kRasterThreads / 32;
+constexpr int kStripPx = 256;                  // pixels of one warp strip: 8 per lane
+constexpr int kStripBytes = kStripPx * 3;
+constexpr int kSlots = 4;                      // staging rows per warp (ring)
+constexpr int kOccBytes = 512;                 // per-plane-row occupancy words, padded
 
 struct RasterArgs {
     int n_items;                           // F*C*NB
     int n_bands, band_rows, height, width, n_instances;
+    int x_bits;                            // record = ord1 : 16 | plane row : 16 - x_bits | x : x_bits
+    int n_strips, n_groups, rows_per_group;
     long long sorted_cap;
     const unsigned *start;                 // [n_items+1]
     const unsigned *sorted;
@@ -352,27 +359,157 @@ struct RasterArgs {
     unsigned *work_counter;
 };
 
-// One work item = one (frame, camera, band).  Shared memory: uint16 plane [(band_rows+4)][W] |
-// two staging buffers [kStageRows][W*3].  Thread t owns columns 4t..4t+3 and walks down the band
-// keeping the 5-row dilation window in registers.
+// 24-bit colours of the 8 pixels of a lane (ids packed as u16x2 in m[4]) -> 24 output bytes.
+// MODE 0: unlit pixels are black.  MODE 1: unlit pixels keep the background bytes already in w[].
+template <int MODE>
+__device__ __forceinline__ void colour8(const unsigned *__restrict__ lut, const unsigned (&m)[4], unsigned (&w)[6]) {
+    unsigned c[8];
+    if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = 0u;
+    } else {
+        c[0] = w[0] & 0xffffffu;                   c[1] = (w[0] >> 24) | ((w[1] & 0xffffu) << 8);
+        c[2] = (w[1] >> 16) | ((w[2] & 0xffu) << 16); c[3] = w[2] >> 8;
+        c[4] = w[3] & 0xffffffu;                   c[5] = (w[3] >> 24) | ((w[4] & 0xffffu) << 8);
+        c[6] = (w[4] >> 16) | ((w[5] & 0xffu) << 16); c[7] = w[5] >> 8;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (m[k]) {
+            const unsigned lo = m[k] & 0xffffu, hi = m[k] >> 16;
+            if (lo) c[2 * k] = __ldg(lut + lo);
+            if (hi) c[2 * k + 1] = __ldg(lut + hi);
+        }
+    }
+    w[0] = c[0] | (c[1] << 24); w[1] = (c[1] >> 8) | (c[2] << 16); w[2] = (c[2] >> 16) | (c[3] << 8);
+    w[3] = c[4] | (c[5] << 24); w[4] = (c[5] >> 8) | (c[6] << 16); w[5] = (c[6] >> 16) | (c[7] << 8);
+}
+
+// One warp renders output rows [y_lo, y_hi) of one 256-pixel column strip of the band: it walks
+// down the plane rows keeping the dilation window in registers (lane = 8 pixels = 4 u16x2 words);
+// plane rows without a centre near the strip (occupancy word) are neither loaded nor computed,
+// output rows whose 5-row window is empty are stored straight from a shared row of zeros.
+//   out(y) = max(raw[y-2], h3[y-1], h5[y], h3[y+1], raw[y+2])     (the 13-px L1 ball; h3/h5 = 3/5-wide row max)
+template <int MODE>
+__device__ __forceinline__ void raster_strip(const RasterArgs &a, const unsigned short *plane, const unsigned *occ,
+                                             const unsigned char *zero_row, unsigned char *stage, unsigned &seq, int s,
+                                             int y_lo, int y_hi, uint8_t *out_base, const uint8_t *bg_base, bool inplace, int lane) {
+    const int W = a.width;
+    const unsigned row_bytes = (unsigned)W * 3u;
+    const int xs = s * kStripPx;
+    const int x0 = xs + lane * 8;
+    const bool lane_on = x0 < W;
+    const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
+    // 64-px occupancy segments that can reach this strip (+-2 px)
+    const int seg_lo = max(4 * s - 1, 0), seg_hi = min(4 * s + 4, 31);
+    const unsigned seg_mask = (seg_hi == 31 ? 0xffffffffu : ((2u << seg_hi) - 1u)) & ~((1u << seg_lo) - 1u);
+    uint4 raw[4], h3[3], h5[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) raw[k] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) h3[k] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) h5[k] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned nz = 0;                         // bit i: plane row j-i has a centre near the strip
+    const int j_end = y_hi + 4;              // plane rows y_lo .. y_hi+3 (plane row = band row + 2, window +-2)
+    for (int jb = y_lo; jb < j_end; jb += 12) {
+#pragma unroll
+        for (int jj = 0; jj < 12; ++jj) {    // 12 = lcm of the ring sizes: every ring index below is a compile-time constant
+            const int j = jb + jj;
+            if (j >= j_end) break;
+            const bool hit = (occ[j] & seg_mask) != 0u;
+            uint4 A = make_uint4(0u, 0u, 0u, 0u), t = A, f = A;
+            if (hit && lane_on) {
+                const unsigned short *row = plane + (size_t)j * W + x0;
+                A = *reinterpret_cast<const uint4 *>(row);
+                const unsigned L = x0 > 0 ? *reinterpret_cast<const unsigned *>(row - 2) : 0u;
+                const unsigned R = x0 + 8 < W ? *reinterpret_cast<const unsigned *>(row + 8) : 0u;
+                const unsigned S0 = __byte_perm(L, A.x, 0x5432);     // (p-1, p0)
+                const unsigned S1 = __byte_perm(A.x, A.y, 0x5432);   // (p1, p2)
+                const unsigned S2 = __byte_perm(A.y, A.z, 0x5432);   // (p3, p4)
+                const unsigned S3 = __byte_perm(A.z, A.w, 0x5432);   // (p5, p6)
+                const unsigned S4 = __byte_perm(A.w, R, 0x5432);     // (p7, p8)
+                t.x = max3_u16x2(S0, A.x, S1); t.y = max3_u16x2(S1, A.y, S2);
+                t.z = max3_u16x2(S2, A.z, S3); t.w = max3_u16x2(S3, A.w, S4);
+                f.x = max3_u16x2(t.x, L, A.y);   f.y = max3_u16x2(t.y, A.x, A.z);
+                f.z = max3_u16x2(t.z, A.y, A.w); f.w = max3_u16x2(t.w, A.z, R);
+            }
+            nz = ((nz << 1) | (hit ? 1u : 0u)) & 0x1fu;
+            if (j >= y_lo + 4) {
+                const int y = j - 4;         // band output row, centred on plane row j-2
+                uint8_t *gdst = out_base + (size_t)y * row_bytes + (size_t)xs * 3;
+                if (MODE == 0 && nz == 0u) {
+                    if (lane == 0) {
+                        bulk_store_shared_to_global(gdst, zero_row, strip_bytes);
+                        bulk_commit_group();
+                    }
+                } else if (!(MODE == 1 && nz == 0u && inplace)) {
+                    unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+                    if (MODE == 1 && lane_on) {
+                        const uint2 *b = reinterpret_cast<const uint2 *>(bg_base + (size_t)y * row_bytes + (size_t)x0 * 3);
+                        const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
+                        w[0] = b0.x; w[1] = b0.y; w[2] = b1.x; w[3] = b1.y; w[4] = b2.x; w[5] = b2.y;
+                    }
+                    if (nz != 0u) {
+                        const uint4 &r0 = raw[jj % 4], &a3 = h3[jj % 3], &a5 = h5[jj % 2], &b3 = h3[(jj + 2) % 3];
+                        unsigned m[4];
+                        m[0] = max3_u16x2(max3_u16x2(r0.x, a3.x, a5.x), b3.x, A.x);
+                        m[1] = max3_u16x2(max3_u16x2(r0.y, a3.y, a5.y), b3.y, A.y);
+                        m[2] = max3_u16x2(max3_u16x2(r0.z, a3.z, a5.z), b3.z, A.z);
+                        m[3] = max3_u16x2(max3_u16x2(r0.w, a3.w, a5.w), b3.w, A.w);
+                        if (m[0] | m[1] | m[2] | m[3]) colour8<MODE>(a.lut, m, w);
+                    }
+                    unsigned char *sptr = stage + (seq % kSlots) * kStripBytes;
+                    if (lane == 0) bulk_wait_group_read<kSlots - 1>();      // the store that last read this slot is done with it
+                    __syncwarp();
+                    if (lane_on) {
+                        uint2 *d = reinterpret_cast<uint2 *>(sptr + lane * 24);
+                        d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+                    }
+                    fence_proxy_async_shared();
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_store_shared_to_global(gdst, sptr, strip_bytes);
+                        bulk_commit_group();
+                    }
+                    ++seq;
+                }
+            }
+            if (nz != 0u) {                  // (nz == 0 implies the whole window already holds zeros)
+                raw[jj % 4] = A; h3[jj % 3] = t; h5[jj % 2] = f;
+            }
+        }
+    }
+}
+
+// One work item = one (frame, camera, band).  Shared memory: uint16 centre plane [(band_rows+4)][W] |
+// occupancy words | a strip row of zeros | per-warp staging rows.
+template <int MODE>
 __global__ void __launch_bounds__(kRasterThreads, 2) binned_raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_item;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.width;
     const int plane_rows = a.band_rows + 4;
-    const unsigned plane_elems = (unsigned)(plane_rows * W);
+    const unsigned plane_bytes = (unsigned)(plane_rows * W) * 2u;
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
+    unsigned *occ = reinterpret_cast<unsigned *>(smem + plane_bytes);
+    unsigned char *zero_row = smem + plane_bytes + kOccBytes;
+    unsigned char *stage = zero_row + kStripBytes + (size_t)warp * (kSlots * kStripBytes);
     const unsigned row_bytes = (unsigned)W * 3u;
-    unsigned char *stage0 = smem + (size_t)plane_elems * 2;
-    const unsigned stage_bytes = kStageRows * row_bytes;
-    const int strips = W >> 2;
-    const bool owner = tid < strips;
-    const int x0 = tid * 4;
-    int pending_slot = 0;                  // staging buffer the next chunk will use
+    const bool inplace = MODE == 1 && a.bg == a.frames;
+    const unsigned x_mask = (1u << a.x_bits) - 1u;
+    {   // plane, occupancy and the zero row start out (and are kept) all-zero between items
+        uint4 *p4 = reinterpret_cast<uint4 *>(smem);
+        const int n16 = (int)((plane_bytes + kOccBytes + kStripBytes) >> 4);
+        for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
+    unsigned seq = 0;                      // staging rows this warp has used
+    bool plane_busy = false;               // a bulk store may still be reading the (all-zero) plane
 
     for (;;) {
-        __syncthreads();                   // everyone is done with s_item / plane of the previous item
+        __syncthreads();                   // previous item: clean-up finished, s_item consumed
         if (tid == 0) s_item = (int)atomicAdd(a.work_counter, 1u);
         __syncthreads();
         const int item = s_item;
@@ -381,109 +518,60 @@ __global__ void __launch_bounds__(kRasterThreads, 2) binned_raster_kernel(const 
         const long long image = item / a.n_bands;
         const int y_first = band * a.band_rows;
         const int rows_out = min(a.band_rows, a.height - y_first);
-
-        // 1. clear the plane
-        {
-            uint4 *p4 = reinterpret_cast<uint4 *>(plane);
-            const int n16 = (int)(plane_elems >> 3);
-            for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        // 2. centres of this bucket
-        {
-            // (the bounds only matter after a capacity overflow, when the pool holds stale records)
-            const long long lo = a.start[item], hi = min((long long)a.start[item + 1], a.sorted_cap);
-            for (long long i = lo + tid; i < hi; i += kRasterThreads) {
-                const unsigned rec = __ldg(a.sorted + i);
-                const unsigned pix = rec & 0xffffu, ord1 = rec >> 16;
-                if (pix < plane_elems && ord1 <= (unsigned)a.n_instances) smem_max_u16(plane, pix, ord1);
-            }
-        }
-        __syncthreads();
-        // 3. dilation + colour, kStageRows rows at a time
+        // (the bounds only matter after a capacity overflow, when the pool holds stale records)
+        const long long lo = a.start[item], hi = min((long long)a.start[item + 1], a.sorted_cap);
         uint8_t *out_base = a.frames + ((size_t)image * a.height + y_first) * row_bytes;
-        const uint8_t *bg_base = a.bg ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
-        // window registers: raw rows j-4..j-1, h3 rows j-3..j-1, h5 rows j-2..j-1 (as packed u16x2 pairs)
-        unsigned raw[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        unsigned h3[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-        unsigned h5[2][2] = {{0, 0}, {0, 0}};
-        for (int j = 0; j < rows_out + 4; ++j) {
-            unsigned A0 = 0, A1 = 0, L = 0, R = 0;
-            if (owner) {
-                const unsigned short *row = plane + (size_t)j * W + x0;
-                const uint2 own = *reinterpret_cast<const uint2 *>(row);
-                A0 = own.x; A1 = own.y;
-                if (x0 > 0) L = *reinterpret_cast<const unsigned *>(row - 2);
-                if (x0 + 4 < W) R = *reinterpret_cast<const unsigned *>(row + 4);
+        const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
+
+        if (hi <= lo) {                    // nothing lands in this band
+            if (MODE == 0) {
+                if (tid == 0) {            // the clean plane is the source of zeros
+                    unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+                    while (left) {
+                        const unsigned n = min(left, plane_bytes);
+                        bulk_store_shared_to_global(out_base + off, plane, n);
+                        off += n; left -= n;
+                    }
+                    bulk_commit_group();
+                }
+                plane_busy = true;
+                continue;
             }
-            const unsigned S0 = __byte_perm(L, A0, 0x5432);    // (p[-1], p[0])
-            const unsigned S1 = __byte_perm(A0, A1, 0x5432);   // (p[1],  p[2])
-            const unsigned S2 = __byte_perm(A1, R, 0x5432);    // (p[3],  p[4])
-            const unsigned t0 = max3_u16x2(S0, A0, S1);        // 3-wide max for p0,p1
-            const unsigned t1 = max3_u16x2(S1, A1, S2);        //                 p2,p3
-            const unsigned f0 = max3_u16x2(t0, L, A1);         // 5-wide max
-            const unsigned f1 = max3_u16x2(t1, A0, R);
-            // window before the shift: raw[k] = row j-4+k, h3[k] = row j-3+k, h5[k] = row j-2+k
-            if (j >= 4) {
-                // band output row yb = j-4, centred on plane row j-2:
-                //   out = max(raw[j-4], h3[j-3], h5[j-2], h3[j-1], raw[j])      (the 13-px L1 ball)
-                const int yb = j - 4;
-                const unsigned m0 = max3_u16x2(max3_u16x2(raw[0][0], h3[0][0], h5[0][0]), h3[2][0], A0);
-                const unsigned m1 = max3_u16x2(max3_u16x2(raw[0][1], h3[0][1], h5[0][1]), h3[2][1], A1);
-                const int slot_row = yb % kStageRows;
-                if (slot_row == 0) {
-                    // about to overwrite staging buffer `pending_slot`: the store issued two chunks ago must have read it
-                    if (tid == 0) bulk_wait_group_read<1>();
-                    __syncthreads();
-                }
-                if (owner) {
-                    unsigned w0 = 0, w1 = 0, w2 = 0;
-                    if (bg_base) {
-                        const unsigned *b = reinterpret_cast<const unsigned *>(bg_base + (size_t)yb * row_bytes + (size_t)x0 * 3);
-                        w0 = b[0]; w1 = b[1]; w2 = b[2];
-                    }
-                    if (m0 | m1) {
-                        unsigned c0 = w0 & 0xffffffu;
-                        unsigned c1 = (w0 >> 24) | ((w1 & 0xffffu) << 8);
-                        unsigned c2 = (w1 >> 16) | ((w2 & 0xffu) << 16);
-                        unsigned c3 = w2 >> 8;
-                        if (m0 & 0xffffu) c0 = __ldg(a.lut + (m0 & 0xffffu));
-                        if (m0 >> 16) c1 = __ldg(a.lut + (m0 >> 16));
-                        if (m1 & 0xffffu) c2 = __ldg(a.lut + (m1 & 0xffffu));
-                        if (m1 >> 16) c3 = __ldg(a.lut + (m1 >> 16));
-                        w0 = c0 | (c1 << 24);
-                        w1 = (c1 >> 8) | (c2 << 16);
-                        w2 = (c2 >> 16) | (c3 << 8);
-                    }
-                    unsigned *dst = reinterpret_cast<unsigned *>(stage0 + (size_t)pending_slot * stage_bytes + (size_t)slot_row * row_bytes + (size_t)x0 * 3);
-                    dst[0] = w0; dst[1] = w1; dst[2] = w2;
-                }
-                if (slot_row == kStageRows - 1 || yb == rows_out - 1) {
-                    const int chunk_rows = slot_row + 1;
-                    fence_proxy_async_shared();
-                    __syncthreads();
-                    if (tid == 0) {
-                        bulk_store_shared_to_global(out_base + (size_t)(yb - slot_row) * row_bytes,
-                                                    stage0 + (size_t)pending_slot * stage_bytes, (unsigned)chunk_rows * row_bytes);
-                        bulk_commit_group();
-                    }
-                    pending_slot ^= 1;
-                }
-            }
-            // slide the window down one row
-            raw[0][0] = raw[1][0]; raw[0][1] = raw[1][1];
-            raw[1][0] = raw[2][0]; raw[1][1] = raw[2][1];
-            raw[2][0] = raw[3][0]; raw[2][1] = raw[3][1];
-            raw[3][0] = A0;        raw[3][1] = A1;
-            h3[0][0] = h3[1][0]; h3[0][1] = h3[1][1];
-            h3[1][0] = h3[2][0]; h3[1][1] = h3[2][1];
-            h3[2][0] = t0;       h3[2][1] = t1;
-            h5[0][0] = h5[1][0]; h5[0][1] = h5[1][1];
-            h5[1][0] = f0;       h5[1][1] = f1;
+            if (inplace) continue;
         }
+        if (plane_busy) {
+            if (tid == 0) bulk_wait_group_read<0>();
+            __syncthreads();
+            plane_busy = false;
+        }
+        // 1. centres of this bucket -> plane (max ordinal per pixel) + occupancy
+        for (long long i = lo + tid; i < hi; i += kRasterThreads) {
+            const unsigned rec = __ldg(a.sorted + i);
+            const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
+            if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
+                smem_max_u16(plane, row * (unsigned)W + x, ord1);
+                atomicOr(&occ[row], 1u << (x >> 6));
+            }
+        }
+        __syncthreads();
+        // 2. dilation + colour + store, one (strip, row group) per warp
+        for (int task = warp; task < a.n_strips * a.n_groups; task += kRasterWarps) {
+            const int s = task % a.n_strips, g = task / a.n_strips;
+            const int y_lo = g * a.rows_per_group, y_hi = min(y_lo + a.rows_per_group, rows_out);
+            if (y_lo < y_hi) raster_strip<MODE>(a, plane, occ, zero_row, stage, seq, s, y_lo, y_hi, out_base, bg_base, inplace, lane);
+        }
+        __syncthreads();
+        // 3. restore the all-zero plane by revisiting the records
+        for (long long i = lo + tid; i < hi; i += kRasterThreads) {
+            const unsigned rec = __ldg(a.sorted + i);
+            const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits;
+            if (row < (unsigned)plane_rows && x < (unsigned)W) plane[row * (unsigned)W + x] = 0;
+        }
+        if (tid < plane_rows) occ[tid] = 0u;
+        if (MODE == 0) fence_proxy_async_shared();     // an empty band next stores straight from the plane
     }
     // staging memory must stay valid until the last bulk stores have read it
-    if (tid == 0) bulk_wait_group_read<0>();
+    if (lane == 0) bulk_wait_group_read<0>();
 }
 
 }  // namespace cama
@@ -494,7 +582,8 @@ namespace {
 
 struct ClipPlan {
     int mode;
-    int band_rows, n_bands;
+    int band_rows, n_bands, x_bits;
+    int n_strips, n_groups, rows_per_group;
     long long cap;          // records per frame
     int n_buckets;
     size_t raster_smem;
@@ -504,7 +593,8 @@ struct ClipPlan {
     size_t total;
 };
 
-constexpr size_t kRasterSmemBudget = 110 * 1024;     // two CTAs per SM
+constexpr size_t kRasterSmemBudget = 112 * 1024;     // two CTAs per SM
+constexpr size_t kRasterFixedSmem = kOccBytes + kStripBytes + (size_t)kRasterWarps * kSlots * kStripBytes;
 
 int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     CAMA_REQUIRE(d, "desc is NULL");
@@ -515,22 +605,32 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     CAMA_REQUIRE(d->vertex_layout == CAMA_VERTEX_F32X4 || d->vertex_layout == CAMA_VERTEX_F64X3, "bad vertex_layout");
     CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width < (1ll << 40), "clip too large");
     const int W = d->width, H = d->height;
-    // BINNED needs: 16-byte rows for the bulk stores, one 4-px strip per thread, 16-bit pixel index and ordinal
-    int band_rows = 0;
-    bool binned_ok = (W % 16 == 0) && (W / 4 <= kRasterThreads) && d->n_instances <= 65534;
+    // BINNED needs: 16-byte rows for the bulk stores, a 16-bit {plane row | x} pixel code with at least
+    // 8 plane rows, 32 occupancy segments of 64 px, a 16-bit ordinal
+    int band_rows = 0, x_bits = 0;
+    bool binned_ok = (W % 16 == 0) && W <= 2048 && d->n_instances <= 65534;
     if (binned_ok) {
-        const long long stage = 2ll * kStageRows * W * 3;
-        long long rows = ((long long)kRasterSmemBudget - stage) / (2ll * W) - 4;
-        rows = std::min<long long>(rows, 65536 / W - 4);
+        while ((1 << x_bits) < W) ++x_bits;
+        long long rows = ((long long)kRasterSmemBudget - (long long)kRasterFixedSmem) / (2ll * W) - 4;
+        rows = std::min<long long>(rows, (1ll << (16 - x_bits)) - 4);
+        rows = std::min<long long>(rows, kOccBytes / 4 - 4);
+        if (const char *env = getenv("CAMA_BAND_ROWS")) {        // tuning knob for experiments
+            const long long want = atoll(env);
+            if (want >= 1) rows = std::min(rows, want);
+        }
         rows = std::min<long long>(rows, H);
         if (rows < 4 && rows < H) binned_ok = false;
+        if (binned_ok) {                                          // even out the bands
+            const long long nb = (H + rows - 1) / rows;
+            rows = (H + nb - 1) / nb;
+        }
         band_rows = (int)rows;
     }
     int mode = d->mode;
     if (mode == CAMA_CLIP_AUTO) mode = binned_ok ? CAMA_CLIP_BINNED : CAMA_CLIP_PLANE;
     CAMA_REQUIRE(mode == CAMA_CLIP_PLANE || mode == CAMA_CLIP_BINNED, "bad mode");
     if (mode == CAMA_CLIP_BINNED && !binned_ok)
-        return fail(CAMA_E_UNSUPPORTED, "BINNED mode needs width %% 16 == 0, width <= %d, <= 65534 instances", 4 * kRasterThreads);
+        return fail(CAMA_E_UNSUPPORTED, "BINNED mode needs width %% 16 == 0, width <= 2048, <= 65534 instances");
     p = ClipPlan();
     p.mode = mode;
     size_t off = 0;
@@ -542,7 +642,11 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.off_plane = take(sizeof(unsigned) * (size_t)d->n_frames * d->n_cams * H * W);
     } else {
         p.band_rows = band_rows;
+        p.x_bits = x_bits;
         p.n_bands = (H + band_rows - 1) / band_rows;
+        p.n_strips = (W + kStripPx - 1) / kStripPx;
+        p.n_groups = std::max(1, std::min(kRasterWarps / p.n_strips, band_rows / 4));
+        p.rows_per_group = (band_rows + p.n_groups - 1) / p.n_groups;
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
         CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
         p.n_buckets = (int)nb;
@@ -550,7 +654,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         if (cap <= 0) cap = std::max<long long>(d->n_vertices, 4096);      // one visible camera per vertex and frame
         CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
         p.cap = cap;
-        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + 2 * (size_t)kStageRows * W * 3;
+        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + kRasterFixedSmem;
         p.off_zero = off;
         p.off_counter = take(256);
         p.off_fcount = take(sizeof(unsigned) * (size_t)std::max(d->n_frames, 1));
@@ -652,7 +756,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     }
 
     // BINNED
-    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.cap = p.cap;
+    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.cap = p.cap;
     a.fcount = reinterpret_cast<unsigned *>(ws + p.off_fcount);
     a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
     a.unsorted = reinterpret_cast<uint4 *>(ws + p.off_unsorted);
@@ -678,10 +782,16 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     RasterArgs r{};
     r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
     r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
+    r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.n_groups = p.n_groups; r.rows_per_group = p.rows_per_group;
     r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames; r.work_counter = counter;
-    CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * 2);
-    binned_raster_kernel<<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+    if (d->background) {
+        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+        binned_raster_kernel<1><<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+    } else {
+        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+        binned_raster_kernel<0><<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+    }
     CAMA_LAUNCHED(ctx);
     CAMA_CUDA_TRY(mark(4));
     return CAMA_OK;
