@@ -338,12 +338,12 @@ __device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix
     }
 }
 
-constexpr int kRasterThreads = 256;
+constexpr int kRasterThreads = 128;
 constexpr int kRasterWarps = kRasterThreads / 32;
 constexpr int kStripPx = 256;                  // pixels of one warp strip: 8 per lane
-constexpr int kStripBytes = kStripPx * 3;
-constexpr int kSlots = 4;                      // staging rows per warp (ring)
 constexpr int kOccBytes = 512;                 // per-plane-row occupancy words, padded
+constexpr int kZeroRows = 2;                   // image rows of zeros kept in shared memory (source of empty output)
+constexpr int kMaxGroupRows = 28;              // rows of one task: its plane rows (+4) fit one 32-bit ballot
 
 struct RasterArgs {
     int n_items;                           // F*C*NB
@@ -356,7 +356,6 @@ struct RasterArgs {
     const unsigned *lut;
     const uint8_t *bg;
     uint8_t *frames;
-    unsigned *work_counter;
 };
 
 // 24-bit colours of the 8 pixels of a lane (ids packed as u16x2 in m[4]) -> 24 output bytes.
@@ -374,35 +373,22 @@ __device__ __forceinline__ void colour8(const unsigned *__restrict__ lut, const 
         c[6] = (w[4] >> 16) | ((w[5] & 0xffu) << 16); c[7] = w[5] >> 8;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (m[k]) {
-            const unsigned lo = m[k] & 0xffffu, hi = m[k] >> 16;
-            if (lo) c[2 * k] = __ldg(lut + lo);
-            if (hi) c[2 * k + 1] = __ldg(lut + hi);
-        }
+    for (int k = 0; k < 4; ++k) {          // predicated loads, no branches
+        const unsigned lo = m[k] & 0xffffu, hi = m[k] >> 16;
+        if (lo) c[2 * k] = __ldg(lut + lo);
+        if (hi) c[2 * k + 1] = __ldg(lut + hi);
     }
     w[0] = c[0] | (c[1] << 24); w[1] = (c[1] >> 8) | (c[2] << 16); w[2] = (c[2] >> 16) | (c[3] << 8);
     w[3] = c[4] | (c[5] << 24); w[4] = (c[5] >> 8) | (c[6] << 16); w[5] = (c[6] >> 16) | (c[7] << 8);
 }
 
-// One warp renders output rows [y_lo, y_hi) of one 256-pixel column strip of the band: it walks
-// down the plane rows keeping the dilation window in registers (lane = 8 pixels = 4 u16x2 words);
-// plane rows without a centre near the strip (occupancy word) are neither loaded nor computed,
-// output rows whose 5-row window is empty are stored straight from a shared row of zeros.
+// One warp renders `n_rows` consecutive output rows of one 256-pixel column strip, starting at band
+// row y0: it walks down plane rows y0 .. y0+n_rows+3 keeping the dilation window in registers
+// (lane = 8 pixels = 4 u16x2 words) and stores 24 bytes per lane and row straight from registers.
 //   out(y) = max(raw[y-2], h3[y-1], h5[y], h3[y+1], raw[y+2])     (the 13-px L1 ball; h3/h5 = 3/5-wide row max)
 template <int MODE>
-__device__ __forceinline__ void raster_strip(const RasterArgs &a, const unsigned short *plane, const unsigned *occ,
-                                             const unsigned char *zero_row, unsigned char *stage, unsigned &seq, int s,
-                                             int y_lo, int y_hi, uint8_t *out_base, const uint8_t *bg_base, bool inplace, int lane) {
-    const int W = a.width;
-    const unsigned row_bytes = (unsigned)W * 3u;
-    const int xs = s * kStripPx;
-    const int x0 = xs + lane * 8;
-    const bool lane_on = x0 < W;
-    const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
-    // 64-px occupancy segments that can reach this strip (+-2 px)
-    const int seg_lo = max(4 * s - 1, 0), seg_hi = min(4 * s + 4, 31);
-    const unsigned seg_mask = (seg_hi == 31 ? 0xffffffffu : ((2u << seg_hi) - 1u)) & ~((1u << seg_lo) - 1u);
+__device__ __forceinline__ void raster_run(const unsigned short *plane, const unsigned *__restrict__ lut, int W, int x0, bool lane_on,
+                                           int y0, int n_rows, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes) {
     uint4 raw[4], h3[3], h5[2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) raw[k] = make_uint4(0u, 0u, 0u, 0u);
@@ -410,167 +396,220 @@ __device__ __forceinline__ void raster_strip(const RasterArgs &a, const unsigned
     for (int k = 0; k < 3; ++k) h3[k] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int k = 0; k < 2; ++k) h5[k] = make_uint4(0u, 0u, 0u, 0u);
-    unsigned nz = 0;                         // bit i: plane row j-i has a centre near the strip
-    const int j_end = y_hi + 4;              // plane rows y_lo .. y_hi+3 (plane row = band row + 2, window +-2)
-    for (int jb = y_lo; jb < j_end; jb += 12) {
+    const int xc = min(x0, W - 8);
+    const unsigned short *row = plane + (size_t)y0 * W + xc;
+    const bool has_l = xc > 0, has_r = xc + 8 < W;
+    const int n_iter = n_rows + 4;
+    for (int jb = 0; jb < n_iter; jb += 12) {
 #pragma unroll
         for (int jj = 0; jj < 12; ++jj) {    // 12 = lcm of the ring sizes: every ring index below is a compile-time constant
-            const int j = jb + jj;
-            if (j >= j_end) break;
-            const bool hit = (occ[j] & seg_mask) != 0u;
-            uint4 A = make_uint4(0u, 0u, 0u, 0u), t = A, f = A;
-            if (hit && lane_on) {
-                const unsigned short *row = plane + (size_t)j * W + x0;
-                A = *reinterpret_cast<const uint4 *>(row);
-                const unsigned L = x0 > 0 ? *reinterpret_cast<const unsigned *>(row - 2) : 0u;
-                const unsigned R = x0 + 8 < W ? *reinterpret_cast<const unsigned *>(row + 8) : 0u;
-                const unsigned S0 = __byte_perm(L, A.x, 0x5432);     // (p-1, p0)
-                const unsigned S1 = __byte_perm(A.x, A.y, 0x5432);   // (p1, p2)
-                const unsigned S2 = __byte_perm(A.y, A.z, 0x5432);   // (p3, p4)
-                const unsigned S3 = __byte_perm(A.z, A.w, 0x5432);   // (p5, p6)
-                const unsigned S4 = __byte_perm(A.w, R, 0x5432);     // (p7, p8)
-                t.x = max3_u16x2(S0, A.x, S1); t.y = max3_u16x2(S1, A.y, S2);
-                t.z = max3_u16x2(S2, A.z, S3); t.w = max3_u16x2(S3, A.w, S4);
-                f.x = max3_u16x2(t.x, L, A.y);   f.y = max3_u16x2(t.y, A.x, A.z);
-                f.z = max3_u16x2(t.z, A.y, A.w); f.w = max3_u16x2(t.w, A.z, R);
-            }
-            nz = ((nz << 1) | (hit ? 1u : 0u)) & 0x1fu;
-            if (j >= y_lo + 4) {
-                const int y = j - 4;         // band output row, centred on plane row j-2
-                uint8_t *gdst = out_base + (size_t)y * row_bytes + (size_t)xs * 3;
-                if (MODE == 0 && nz == 0u) {
-                    if (lane == 0) {
-                        bulk_store_shared_to_global(gdst, zero_row, strip_bytes);
-                        bulk_commit_group();
-                    }
-                } else if (!(MODE == 1 && nz == 0u && inplace)) {
+            if (jb + jj >= n_iter) break;
+            // (lanes past the image edge of the last strip recompute its last 8 pixels and store nothing)
+            const uint4 A = *reinterpret_cast<const uint4 *>(row);
+            const unsigned L = has_l ? *reinterpret_cast<const unsigned *>(row - 2) : 0u;
+            const unsigned R = has_r ? *reinterpret_cast<const unsigned *>(row + 8) : 0u;
+            row += W;
+            const unsigned S0 = __byte_perm(L, A.x, 0x5432);     // (p-1, p0)
+            const unsigned S1 = __byte_perm(A.x, A.y, 0x5432);   // (p1, p2)
+            const unsigned S2 = __byte_perm(A.y, A.z, 0x5432);   // (p3, p4)
+            const unsigned S3 = __byte_perm(A.z, A.w, 0x5432);   // (p5, p6)
+            const unsigned S4 = __byte_perm(A.w, R, 0x5432);     // (p7, p8)
+            uint4 t, f;
+            t.x = max3_u16x2(S0, A.x, S1); t.y = max3_u16x2(S1, A.y, S2);
+            t.z = max3_u16x2(S2, A.z, S3); t.w = max3_u16x2(S3, A.w, S4);
+            f.x = max3_u16x2(t.x, L, A.y);   f.y = max3_u16x2(t.y, A.x, A.z);
+            f.z = max3_u16x2(t.z, A.y, A.w); f.w = max3_u16x2(t.w, A.z, R);
+            if (jb + jj >= 4) {              // output row y0 + (j-4), centred on plane row j-2
+                const uint4 &r0 = raw[jj % 4], &a3 = h3[jj % 3], &a5 = h5[jj % 2], &b3 = h3[(jj + 2) % 3];
+                unsigned m[4];
+                m[0] = max3_u16x2(max3_u16x2(r0.x, a3.x, a5.x), b3.x, A.x);
+                m[1] = max3_u16x2(max3_u16x2(r0.y, a3.y, a5.y), b3.y, A.y);
+                m[2] = max3_u16x2(max3_u16x2(r0.z, a3.z, a5.z), b3.z, A.z);
+                m[3] = max3_u16x2(max3_u16x2(r0.w, a3.w, a5.w), b3.w, A.w);
+                if (lane_on) {
                     unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-                    if (MODE == 1 && lane_on) {
-                        const uint2 *b = reinterpret_cast<const uint2 *>(bg_base + (size_t)y * row_bytes + (size_t)x0 * 3);
+                    if (MODE == 1) {
+                        const uint2 *b = reinterpret_cast<const uint2 *>(bg_px);
                         const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
                         w[0] = b0.x; w[1] = b0.y; w[2] = b1.x; w[3] = b1.y; w[4] = b2.x; w[5] = b2.y;
                     }
-                    if (nz != 0u) {
-                        const uint4 &r0 = raw[jj % 4], &a3 = h3[jj % 3], &a5 = h5[jj % 2], &b3 = h3[(jj + 2) % 3];
-                        unsigned m[4];
-                        m[0] = max3_u16x2(max3_u16x2(r0.x, a3.x, a5.x), b3.x, A.x);
-                        m[1] = max3_u16x2(max3_u16x2(r0.y, a3.y, a5.y), b3.y, A.y);
-                        m[2] = max3_u16x2(max3_u16x2(r0.z, a3.z, a5.z), b3.z, A.z);
-                        m[3] = max3_u16x2(max3_u16x2(r0.w, a3.w, a5.w), b3.w, A.w);
-                        if (m[0] | m[1] | m[2] | m[3]) colour8<MODE>(a.lut, m, w);
-                    }
-                    unsigned char *sptr = stage + (seq % kSlots) * kStripBytes;
-                    if (lane == 0) bulk_wait_group_read<kSlots - 1>();      // the store that last read this slot is done with it
-                    __syncwarp();
-                    if (lane_on) {
-                        uint2 *d = reinterpret_cast<uint2 *>(sptr + lane * 24);
-                        d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
-                    }
-                    fence_proxy_async_shared();
-                    __syncwarp();
-                    if (lane == 0) {
-                        bulk_store_shared_to_global(gdst, sptr, strip_bytes);
-                        bulk_commit_group();
-                    }
-                    ++seq;
+                    if (m[0] | m[1] | m[2] | m[3]) colour8<MODE>(lut, m, w);
+                    uint2 *d = reinterpret_cast<uint2 *>(out_px);
+                    d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
                 }
+                out_px += row_bytes;
+                if (MODE == 1) bg_px += row_bytes;
             }
-            if (nz != 0u) {                  // (nz == 0 implies the whole window already holds zeros)
-                raw[jj % 4] = A; h3[jj % 3] = t; h5[jj % 2] = f;
-            }
+            raw[jj % 4] = A; h3[jj % 3] = t; h5[jj % 2] = f;
         }
     }
 }
 
-// One work item = one (frame, camera, band).  Shared memory: uint16 centre plane [(band_rows+4)][W] |
-// occupancy words | a strip row of zeros | per-warp staging rows.
+// One (strip, row group) task of a band.  Plane rows without a centre near the strip are known from
+// the occupancy words, so output rows split into runs: runs whose 5-row window is empty are zeros
+// (MODE 0: bulk-stored from shared zeros by one lane; rows empty across the whole width are written
+// once, by strip 0, in multi-row stores), the other runs go through raster_run.
 template <int MODE>
-__global__ void __launch_bounds__(kRasterThreads, 2) binned_raster_kernel(const RasterArgs a) {
+__device__ __forceinline__ void raster_task(const RasterArgs &a, const unsigned short *plane, const unsigned *occ,
+                                            const unsigned char *zeros, int s, int y_lo, int y_hi, uint8_t *out_base,
+                                            const uint8_t *bg_base, bool inplace, int lane) {
+    const int W = a.width;
+    const unsigned row_bytes = (unsigned)W * 3u;
+    const int xs = s * kStripPx;
+    const int x0 = xs + lane * 8;
+    const bool lane_on = x0 < W;
+    const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
+    const int n = y_hi - y_lo;               // <= kMaxGroupRows
+    // 64-px occupancy segments that can reach this strip (+-2 px)
+    const int seg_lo = max(4 * s - 1, 0), seg_hi = min(4 * s + 4, 31);
+    const unsigned seg_mask = (seg_hi == 31 ? 0xffffffffu : ((2u << seg_hi) - 1u)) & ~((1u << seg_lo) - 1u);
+    const unsigned o = lane < n + 4 ? occ[y_lo + lane] : 0u;
+    const unsigned hit = __ballot_sync(kFull, (o & seg_mask) != 0u);          // bit i: plane row y_lo+i matters to this strip
+    const unsigned hit_any = __ballot_sync(kFull, o != 0u);                   //        ... to any strip
+    const unsigned rows_mask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    unsigned act = (hit | (hit >> 1) | (hit >> 2) | (hit >> 3) | (hit >> 4)) & rows_mask;        // bit i: output row y_lo+i is lit here
+    const unsigned act_any = (hit_any | (hit_any >> 1) | (hit_any >> 2) | (hit_any >> 3) | (hit_any >> 4)) & rows_mask;
+    if (MODE == 1 && !inplace) act = rows_mask;                               // every row has to be copied
+    uint8_t *out_strip = out_base + (size_t)xs * 3;
+    int y = 0;
+    while (y < n) {
+        const unsigned rest = act >> y;
+        if (rest & 1u) {                     // lit run [y, y+len)
+            const unsigned inv = ~rest;
+            const int len = inv ? min(__ffs(inv) - 1, n - y) : n - y;
+            raster_run<MODE>(plane, a.lut, W, x0, lane_on, y_lo + y, len, out_strip + (size_t)(y_lo + y) * row_bytes + lane * 24,
+                             MODE == 1 ? bg_base + (size_t)(y_lo + y) * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes);
+            y += len;
+        } else {                             // dark run
+            const int len = rest ? __ffs(rest) - 1 : n - y;
+            if (MODE == 0 && lane == 0) {
+                int r = y;
+                while (r < y + len) {
+                    if ((act_any >> r) & 1u) {                                // lit elsewhere in the row: this strip's 768 bytes
+                        bulk_store_shared_to_global(out_strip + (size_t)(y_lo + r) * row_bytes, zeros, strip_bytes);
+                        ++r;
+                    } else {                                                   // dark across the width: strip 0 writes whole rows
+                        int e = r + 1;
+                        while (e < y + len && e - r < kZeroRows && !((act_any >> e) & 1u)) ++e;
+                        if (s == 0) bulk_store_shared_to_global(out_base + (size_t)(y_lo + r) * row_bytes, zeros, (unsigned)(e - r) * row_bytes);
+                        r = e;
+                    }
+                }
+                bulk_commit_group();
+            }
+            y += len;
+        }
+    }
+}
+
+// One work item = one (frame, camera, band), items dealt round-robin to the CTAs.  Shared memory:
+// uint16 centre plane [(band_rows+4)][W] | occupancy words | kZeroRows image rows of zeros.
+// Bands without a record cost one thread a few bulk stores from the zeros.
+template <int MODE>
+__global__ void __launch_bounds__(kRasterThreads, 4) binned_raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int s_item;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_task;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int W = a.width;
     const int plane_rows = a.band_rows + 4;
     const unsigned plane_bytes = (unsigned)(plane_rows * W) * 2u;
+    const unsigned row_bytes = (unsigned)W * 3u;
+    const unsigned zero_bytes = (unsigned)kZeroRows * row_bytes;
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
     unsigned *occ = reinterpret_cast<unsigned *>(smem + plane_bytes);
-    unsigned char *zero_row = smem + plane_bytes + kOccBytes;
-    unsigned char *stage = zero_row + kStripBytes + (size_t)warp * (kSlots * kStripBytes);
-    const unsigned row_bytes = (unsigned)W * 3u;
+    unsigned char *zeros = smem + plane_bytes + kOccBytes;
     const bool inplace = MODE == 1 && a.bg == a.frames;
     const unsigned x_mask = (1u << a.x_bits) - 1u;
-    {   // plane, occupancy and the zero row start out (and are kept) all-zero between items
+    {   // plane and occupancy start out (and are kept) all-zero between items; the zero rows stay zero
         uint4 *p4 = reinterpret_cast<uint4 *>(smem);
-        const int n16 = (int)((plane_bytes + kOccBytes + kStripBytes) >> 4);
+        const int n16 = (int)((plane_bytes + kOccBytes + zero_bytes) >> 4);
         for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) s_task = 0;
     }
     if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
-    unsigned seq = 0;                      // staging rows this warp has used
-    bool plane_busy = false;               // a bulk store may still be reading the (all-zero) plane
+    __syncthreads();
+    const int n_tasks = a.n_strips * a.n_groups;
 
-    for (;;) {
-        __syncthreads();                   // previous item: clean-up finished, s_item consumed
-        if (tid == 0) s_item = (int)atomicAdd(a.work_counter, 1u);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= a.n_items) break;
-        const int band = item % a.n_bands;
-        const long long image = item / a.n_bands;
-        const int y_first = band * a.band_rows;
-        const int rows_out = min(a.band_rows, a.height - y_first);
-        // (the bounds only matter after a capacity overflow, when the pool holds stale records)
-        const long long lo = a.start[item], hi = min((long long)a.start[item + 1], a.sorted_cap);
-        uint8_t *out_base = a.frames + ((size_t)image * a.height + y_first) * row_bytes;
-        const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
+    int item = blockIdx.x;
+    long long lo = 0, hi = 0;
+    if (item < a.n_items) { lo = a.start[item]; hi = min((long long)a.start[item + 1], a.sorted_cap); }
+    while (item < a.n_items) {
+        // bounds of the next item, fetched while this one is processed
+        const int next = item + (int)gridDim.x;
+        long long nlo = 0, nhi = 0;
+        if (next < a.n_items) { nlo = a.start[next]; nhi = a.start[next + 1]; }
 
-        if (hi <= lo) {                    // nothing lands in this band
-            if (MODE == 0) {
-                if (tid == 0) {            // the clean plane is the source of zeros
-                    unsigned left = (unsigned)rows_out * row_bytes, off = 0;
-                    while (left) {
-                        const unsigned n = min(left, plane_bytes);
-                        bulk_store_shared_to_global(out_base + off, plane, n);
-                        off += n; left -= n;
-                    }
-                    bulk_commit_group();
+        if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
+            if (tid == 0) {
+                const int y_first = (item % a.n_bands) * a.band_rows;
+                const int rows_out = min(a.band_rows, a.height - y_first);
+                uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
+                unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+                while (left) {
+                    const unsigned n = min(left, zero_bytes);
+                    bulk_store_shared_to_global(out_base + off, zeros, n);
+                    off += n; left -= n;
                 }
-                plane_busy = true;
-                continue;
+                bulk_commit_group();
             }
-            if (inplace) continue;
-        }
-        if (plane_busy) {
-            if (tid == 0) bulk_wait_group_read<0>();
+        } else if (!(hi <= lo && inplace)) {
+            const int band = item % a.n_bands;
+            const long long image = item / a.n_bands;
+            const int y_first = band * a.band_rows;
+            const int rows_out = min(a.band_rows, a.height - y_first);
+            uint8_t *out_base = a.frames + ((size_t)image * a.height + y_first) * row_bytes;
+            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
+            // 1. centres of this bucket -> plane (max ordinal per pixel) + occupancy; loads batched for latency
+            //    (the validity checks only matter after a capacity overflow, when the pool holds stale records)
+            for (long long base = lo + tid; base < hi; base += 4 * kRasterThreads) {
+                unsigned rec[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long i = base + q * kRasterThreads;
+                    rec[q] = i < hi ? __ldg(a.sorted + i) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned x = rec[q] & x_mask, row = (rec[q] & 0xffffu) >> a.x_bits, ord1 = rec[q] >> 16;
+                    if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
+                        smem_max_u16(plane, row * (unsigned)W + x, ord1);
+                        atomicOr(&occ[row], 1u << (x >> 6));
+                    }
+                }
+            }
             __syncthreads();
-            plane_busy = false;
-        }
-        // 1. centres of this bucket -> plane (max ordinal per pixel) + occupancy
-        for (long long i = lo + tid; i < hi; i += kRasterThreads) {
-            const unsigned rec = __ldg(a.sorted + i);
-            const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
-            if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
-                smem_max_u16(plane, row * (unsigned)W + x, ord1);
-                atomicOr(&occ[row], 1u << (x >> 6));
+            // 2. dilation + colour + store: (strip, row group) tasks claimed dynamically by the warps
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&s_task, 1);
+                task = __shfl_sync(kFull, task, 0);
+                if (task >= n_tasks) break;
+                const int s = task % a.n_strips, g = task / a.n_strips;
+                const int y_lo = g * a.rows_per_group, y_hi = min(y_lo + a.rows_per_group, rows_out);
+                if (y_lo < y_hi) raster_task<MODE>(a, plane, occ, zeros, s, y_lo, y_hi, out_base, bg_base, inplace, lane);
             }
+            __syncthreads();
+            // 3. restore the all-zero plane by revisiting the records
+            for (long long base = lo + tid; base < hi; base += 4 * kRasterThreads) {
+                unsigned rec[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long i = base + q * kRasterThreads;
+                    rec[q] = i < hi ? __ldg(a.sorted + i) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned x = rec[q] & x_mask, row = (rec[q] & 0xffffu) >> a.x_bits;
+                    if (row < (unsigned)plane_rows && x < (unsigned)W) plane[row * (unsigned)W + x] = 0;
+                }
+            }
+            if (tid < plane_rows) occ[tid] = 0u;
+            if (tid == 0) s_task = 0;
+            __syncthreads();
         }
-        __syncthreads();
-        // 2. dilation + colour + store, one (strip, row group) per warp
-        for (int task = warp; task < a.n_strips * a.n_groups; task += kRasterWarps) {
-            const int s = task % a.n_strips, g = task / a.n_strips;
-            const int y_lo = g * a.rows_per_group, y_hi = min(y_lo + a.rows_per_group, rows_out);
-            if (y_lo < y_hi) raster_strip<MODE>(a, plane, occ, zero_row, stage, seq, s, y_lo, y_hi, out_base, bg_base, inplace, lane);
-        }
-        __syncthreads();
-        // 3. restore the all-zero plane by revisiting the records
-        for (long long i = lo + tid; i < hi; i += kRasterThreads) {
-            const unsigned rec = __ldg(a.sorted + i);
-            const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits;
-            if (row < (unsigned)plane_rows && x < (unsigned)W) plane[row * (unsigned)W + x] = 0;
-        }
-        if (tid < plane_rows) occ[tid] = 0u;
-        if (MODE == 0) fence_proxy_async_shared();     // an empty band next stores straight from the plane
+        item = next; lo = nlo; hi = min(nhi, a.sorted_cap);
     }
-    // staging memory must stay valid until the last bulk stores have read it
+    // the shared zeros must stay valid until the last bulk stores have read them
     if (lane == 0) bulk_wait_group_read<0>();
 }
 
@@ -593,8 +632,9 @@ struct ClipPlan {
     size_t total;
 };
 
-constexpr size_t kRasterSmemBudget = 112 * 1024;     // two CTAs per SM
-constexpr size_t kRasterFixedSmem = kOccBytes + kStripBytes + (size_t)kRasterWarps * kSlots * kStripBytes;
+constexpr int kRasterCtasPerSm = 4;
+constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
+constexpr size_t kRasterStageSmem = kOccBytes;   // + the plane + kZeroRows image rows
 
 int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     CAMA_REQUIRE(d, "desc is NULL");
@@ -611,7 +651,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     bool binned_ok = (W % 16 == 0) && W <= 2048 && d->n_instances <= 65534;
     if (binned_ok) {
         while ((1 << x_bits) < W) ++x_bits;
-        long long rows = ((long long)kRasterSmemBudget - (long long)kRasterFixedSmem) / (2ll * W) - 4;
+        long long rows = ((long long)kRasterSmemBudget - (long long)kRasterStageSmem - (long long)kZeroRows * W * 3) / (2ll * W) - 4;
         rows = std::min<long long>(rows, (1ll << (16 - x_bits)) - 4);
         rows = std::min<long long>(rows, kOccBytes / 4 - 4);
         if (const char *env = getenv("CAMA_BAND_ROWS")) {        // tuning knob for experiments
@@ -645,7 +685,8 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.x_bits = x_bits;
         p.n_bands = (H + band_rows - 1) / band_rows;
         p.n_strips = (W + kStripPx - 1) / kStripPx;
-        p.n_groups = std::max(1, std::min(kRasterWarps / p.n_strips, band_rows / 4));
+        p.n_groups = std::max(1, std::min(4 * kRasterWarps / p.n_strips, band_rows / 10));
+        p.n_groups = std::max(p.n_groups, (band_rows + kMaxGroupRows - 1) / kMaxGroupRows);
         p.rows_per_group = (band_rows + p.n_groups - 1) / p.n_groups;
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
         CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
@@ -654,7 +695,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         if (cap <= 0) cap = std::max<long long>(d->n_vertices, 4096);      // one visible camera per vertex and frame
         CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
         p.cap = cap;
-        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + kRasterFixedSmem;
+        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         p.off_zero = off;
         p.off_counter = take(256);
         p.off_fcount = take(sizeof(unsigned) * (size_t)std::max(d->n_frames, 1));
@@ -762,7 +803,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     a.unsorted = reinterpret_cast<uint4 *>(ws + p.off_unsorted);
     unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
     unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
-    unsigned *counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
@@ -783,8 +823,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
     r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
     r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.n_groups = p.n_groups; r.rows_per_group = p.rows_per_group;
-    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames; r.work_counter = counter;
-    const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * 2);
+    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
     if (d->background) {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
         binned_raster_kernel<1><<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
