@@ -338,18 +338,20 @@ __device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix
     }
 }
 
-constexpr int kRasterThreads = 128;
+constexpr int kRasterThreads = 128;            // compute threads of a raster CTA
 constexpr int kRasterWarps = kRasterThreads / 32;
+constexpr int kRasterBlock = kRasterThreads + 32;   // + one warp that only issues the zero stores of empty bands (MODE 0)
 constexpr int kStripPx = 256;                  // pixels of one warp strip: 8 per lane
-constexpr int kOccBytes = 512;                 // per-plane-row occupancy words, padded
-constexpr int kZeroRows = 2;                   // image rows of zeros kept in shared memory (source of empty output)
-constexpr int kMaxGroupRows = 28;              // rows of one task: its plane rows (+4) fit one 32-bit ballot
+constexpr int kHitBytes = 128;                 // per-strip hit masks (+ one for "any strip"), padded
+constexpr int kZeroRows = 2;                   // image rows of zeros kept in shared memory (source of dark output)
+constexpr int kMaxPlaneRows = 32;              // band_rows + 4: one bit per plane row in a hit mask
 
 struct RasterArgs {
     int n_items;                           // F*C*NB
     int n_bands, band_rows, height, width, n_instances;
     int x_bits;                            // record = ord1 : 16 | plane row : 16 - x_bits | x : x_bits
-    int n_strips, n_groups, rows_per_group;
+    int n_strips;
+    int debug;                             // CAMA_RASTER_DEBUG experiments: 1 = every band empty, 2 = no colour lookup, 4 = no cells
     long long sorted_cap;
     const unsigned *start;                 // [n_items+1]
     const unsigned *sorted;
@@ -358,256 +360,273 @@ struct RasterArgs {
     uint8_t *frames;
 };
 
-// 24-bit colours of the 8 pixels of a lane (ids packed as u16x2 in m[4]) -> 24 output bytes.
+// 8 packed 24-bit values -> the 24 bytes of 8 BGR pixels (6 words), one byte-permute per word
+__device__ __forceinline__ void pack8x24(const unsigned (&c)[8], unsigned (&w)[6]) {
+    w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
+    w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
+}
+
+// Colours of the 8 pixels of a lane (ids packed as u16x2 in m[4]; lut[0] == 0) into w[6].
 // MODE 0: unlit pixels are black.  MODE 1: unlit pixels keep the background bytes already in w[].
 template <int MODE>
 __device__ __forceinline__ void colour8(const unsigned *__restrict__ lut, const unsigned (&m)[4], unsigned (&w)[6]) {
     unsigned c[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c[2 * k] = __ldg(lut + (m[k] & 0xffffu));
+        c[2 * k + 1] = __ldg(lut + (m[k] >> 16));
+    }
+    unsigned v[6];
+    pack8x24(c, v);
     if (MODE == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = 0u;
+        for (int k = 0; k < 6; ++k) w[k] = v[k];
     } else {
-        c[0] = w[0] & 0xffffffu;                   c[1] = (w[0] >> 24) | ((w[1] & 0xffffu) << 8);
-        c[2] = (w[1] >> 16) | ((w[2] & 0xffu) << 16); c[3] = w[2] >> 8;
-        c[4] = w[3] & 0xffffffu;                   c[5] = (w[3] >> 24) | ((w[4] & 0xffffu) << 8);
-        c[6] = (w[4] >> 16) | ((w[5] & 0xffu) << 16); c[7] = w[5] >> 8;
-    }
+        unsigned lit[8], keep[6];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {          // predicated loads, no branches
-        const unsigned lo = m[k] & 0xffffu, hi = m[k] >> 16;
-        if (lo) c[2 * k] = __ldg(lut + lo);
-        if (hi) c[2 * k + 1] = __ldg(lut + hi);
+        for (int k = 0; k < 4; ++k) {
+            lit[2 * k] = (m[k] & 0xffffu) ? 0xffffffu : 0u;
+            lit[2 * k + 1] = (m[k] >> 16) ? 0xffffffu : 0u;
+        }
+        pack8x24(lit, keep);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = (w[k] & ~keep[k]) | v[k];
     }
-    w[0] = c[0] | (c[1] << 24); w[1] = (c[1] >> 8) | (c[2] << 16); w[2] = (c[2] >> 16) | (c[3] << 8);
-    w[3] = c[4] | (c[5] << 24); w[4] = (c[5] >> 8) | (c[6] << 16); w[5] = (c[6] >> 16) | (c[7] << 8);
 }
 
-// One warp renders `n_rows` consecutive output rows of one 256-pixel column strip, starting at band
-// row y0: it walks down plane rows y0 .. y0+n_rows+3 keeping the dilation window in registers
-// (lane = 8 pixels = 4 u16x2 words) and stores 24 bytes per lane and row straight from registers.
+template <int MODE>
+__device__ __forceinline__ void store_row(const unsigned *__restrict__ lut, const unsigned (&m)[4], bool lane_on, uint8_t *out_px, const uint8_t *bg_px) {
+    if (!lane_on) return;
+    unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+    if (MODE == 1) {
+        const uint2 *b = reinterpret_cast<const uint2 *>(bg_px);
+        const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
+        w[0] = b0.x; w[1] = b0.y; w[2] = b1.x; w[3] = b1.y; w[4] = b2.x; w[5] = b2.y;
+    }
+    if (m[0] | m[1] | m[2] | m[3]) {
+        if (lut) colour8<MODE>(lut, m, w);
+        else { w[0] = m[0]; w[1] = m[1]; w[2] = m[2]; w[3] = m[3]; }
+    }
+    uint2 *d = reinterpret_cast<uint2 *>(out_px);
+    d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+}
+
+// 3-wide (t) and, optionally, 5-wide (f) horizontal max of one plane row held as 4 u16x2 words + halo words
+__device__ __forceinline__ void row_max(const uint4 &A, unsigned L, unsigned R, uint4 &t, uint4 *f) {
+    const unsigned S0 = __byte_perm(L, A.x, 0x5432);     // (p-1, p0)
+    const unsigned S1 = __byte_perm(A.x, A.y, 0x5432);   // (p1, p2)
+    const unsigned S2 = __byte_perm(A.y, A.z, 0x5432);   // (p3, p4)
+    const unsigned S3 = __byte_perm(A.z, A.w, 0x5432);   // (p5, p6)
+    const unsigned S4 = __byte_perm(A.w, R, 0x5432);     // (p7, p8)
+    t.x = max3_u16x2(S0, A.x, S1); t.y = max3_u16x2(S1, A.y, S2);
+    t.z = max3_u16x2(S2, A.z, S3); t.w = max3_u16x2(S3, A.w, S4);
+    if (f) {
+        f->x = max3_u16x2(t.x, L, A.y);   f->y = max3_u16x2(t.y, A.x, A.z);
+        f->z = max3_u16x2(t.z, A.y, A.w); f->w = max3_u16x2(t.w, A.z, R);
+    }
+}
+
+// One warp, one cell = output rows y, y+1 (band rows) of one 256-pixel strip; lane = 8 pixels.
+// Stateless: the six plane rows y .. y+5 are read from shared memory (14 independent loads).
 //   out(y) = max(raw[y-2], h3[y-1], h5[y], h3[y+1], raw[y+2])     (the 13-px L1 ball; h3/h5 = 3/5-wide row max)
 template <int MODE>
-__device__ __forceinline__ void raster_run(const unsigned short *plane, const unsigned *__restrict__ lut, int W, int x0, bool lane_on,
-                                           int y0, int n_rows, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes) {
-    uint4 raw[4], h3[3], h5[2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) raw[k] = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) h3[k] = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) h5[k] = make_uint4(0u, 0u, 0u, 0u);
-    const int xc = min(x0, W - 8);
-    const unsigned short *row = plane + (size_t)y0 * W + xc;
+__device__ __forceinline__ void raster_cell(const unsigned short *plane, const unsigned *__restrict__ lut, int W, int xc, bool lane_on,
+                                            int y, bool two, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes) {
+    const unsigned short *row = plane + (size_t)y * W + xc;
     const bool has_l = xc > 0, has_r = xc + 8 < W;
-    const int n_iter = n_rows + 4;
-    for (int jb = 0; jb < n_iter; jb += 12) {
+    uint4 A[6];
+    unsigned L[4], R[4];
 #pragma unroll
-        for (int jj = 0; jj < 12; ++jj) {    // 12 = lcm of the ring sizes: every ring index below is a compile-time constant
-            if (jb + jj >= n_iter) break;
-            // (lanes past the image edge of the last strip recompute its last 8 pixels and store nothing)
-            const uint4 A = *reinterpret_cast<const uint4 *>(row);
-            const unsigned L = has_l ? *reinterpret_cast<const unsigned *>(row - 2) : 0u;
-            const unsigned R = has_r ? *reinterpret_cast<const unsigned *>(row + 8) : 0u;
-            row += W;
-            const unsigned S0 = __byte_perm(L, A.x, 0x5432);     // (p-1, p0)
-            const unsigned S1 = __byte_perm(A.x, A.y, 0x5432);   // (p1, p2)
-            const unsigned S2 = __byte_perm(A.y, A.z, 0x5432);   // (p3, p4)
-            const unsigned S3 = __byte_perm(A.z, A.w, 0x5432);   // (p5, p6)
-            const unsigned S4 = __byte_perm(A.w, R, 0x5432);     // (p7, p8)
-            uint4 t, f;
-            t.x = max3_u16x2(S0, A.x, S1); t.y = max3_u16x2(S1, A.y, S2);
-            t.z = max3_u16x2(S2, A.z, S3); t.w = max3_u16x2(S3, A.w, S4);
-            f.x = max3_u16x2(t.x, L, A.y);   f.y = max3_u16x2(t.y, A.x, A.z);
-            f.z = max3_u16x2(t.z, A.y, A.w); f.w = max3_u16x2(t.w, A.z, R);
-            if (jb + jj >= 4) {              // output row y0 + (j-4), centred on plane row j-2
-                const uint4 &r0 = raw[jj % 4], &a3 = h3[jj % 3], &a5 = h5[jj % 2], &b3 = h3[(jj + 2) % 3];
-                unsigned m[4];
-                m[0] = max3_u16x2(max3_u16x2(r0.x, a3.x, a5.x), b3.x, A.x);
-                m[1] = max3_u16x2(max3_u16x2(r0.y, a3.y, a5.y), b3.y, A.y);
-                m[2] = max3_u16x2(max3_u16x2(r0.z, a3.z, a5.z), b3.z, A.z);
-                m[3] = max3_u16x2(max3_u16x2(r0.w, a3.w, a5.w), b3.w, A.w);
-                if (lane_on) {
-                    unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-                    if (MODE == 1) {
-                        const uint2 *b = reinterpret_cast<const uint2 *>(bg_px);
-                        const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
-                        w[0] = b0.x; w[1] = b0.y; w[2] = b1.x; w[3] = b1.y; w[4] = b2.x; w[5] = b2.y;
-                    }
-                    if (m[0] | m[1] | m[2] | m[3]) colour8<MODE>(lut, m, w);
-                    uint2 *d = reinterpret_cast<uint2 *>(out_px);
-                    d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
-                }
-                out_px += row_bytes;
-                if (MODE == 1) bg_px += row_bytes;
-            }
-            raw[jj % 4] = A; h3[jj % 3] = t; h5[jj % 2] = f;
-        }
+    for (int r = 0; r < 6; ++r) A[r] = *reinterpret_cast<const uint4 *>(row + (size_t)r * W);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        L[r] = has_l ? *reinterpret_cast<const unsigned *>(row + (size_t)(r + 1) * W - 2) : 0u;
+        R[r] = has_r ? *reinterpret_cast<const unsigned *>(row + (size_t)(r + 1) * W + 8) : 0u;
     }
-}
-
-// One (strip, row group) task of a band.  Plane rows without a centre near the strip are known from
-// the occupancy words, so output rows split into runs: runs whose 5-row window is empty are zeros
-// (MODE 0: bulk-stored from shared zeros by one lane; rows empty across the whole width are written
-// once, by strip 0, in multi-row stores), the other runs go through raster_run.
-template <int MODE>
-__device__ __forceinline__ void raster_task(const RasterArgs &a, const unsigned short *plane, const unsigned *occ,
-                                            const unsigned char *zeros, int s, int y_lo, int y_hi, uint8_t *out_base,
-                                            const uint8_t *bg_base, bool inplace, int lane) {
-    const int W = a.width;
-    const unsigned row_bytes = (unsigned)W * 3u;
-    const int xs = s * kStripPx;
-    const int x0 = xs + lane * 8;
-    const bool lane_on = x0 < W;
-    const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
-    const int n = y_hi - y_lo;               // <= kMaxGroupRows
-    // 64-px occupancy segments that can reach this strip (+-2 px)
-    const int seg_lo = max(4 * s - 1, 0), seg_hi = min(4 * s + 4, 31);
-    const unsigned seg_mask = (seg_hi == 31 ? 0xffffffffu : ((2u << seg_hi) - 1u)) & ~((1u << seg_lo) - 1u);
-    const unsigned o = lane < n + 4 ? occ[y_lo + lane] : 0u;
-    const unsigned hit = __ballot_sync(kFull, (o & seg_mask) != 0u);          // bit i: plane row y_lo+i matters to this strip
-    const unsigned hit_any = __ballot_sync(kFull, o != 0u);                   //        ... to any strip
-    const unsigned rows_mask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-    unsigned act = (hit | (hit >> 1) | (hit >> 2) | (hit >> 3) | (hit >> 4)) & rows_mask;        // bit i: output row y_lo+i is lit here
-    const unsigned act_any = (hit_any | (hit_any >> 1) | (hit_any >> 2) | (hit_any >> 3) | (hit_any >> 4)) & rows_mask;
-    if (MODE == 1 && !inplace) act = rows_mask;                               // every row has to be copied
-    uint8_t *out_strip = out_base + (size_t)xs * 3;
-    int y = 0;
-    while (y < n) {
-        const unsigned rest = act >> y;
-        if (rest & 1u) {                     // lit run [y, y+len)
-            const unsigned inv = ~rest;
-            const int len = inv ? min(__ffs(inv) - 1, n - y) : n - y;
-            raster_run<MODE>(plane, a.lut, W, x0, lane_on, y_lo + y, len, out_strip + (size_t)(y_lo + y) * row_bytes + lane * 24,
-                             MODE == 1 ? bg_base + (size_t)(y_lo + y) * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes);
-            y += len;
-        } else {                             // dark run
-            const int len = rest ? __ffs(rest) - 1 : n - y;
-            if (MODE == 0 && lane == 0) {
-                int r = y;
-                while (r < y + len) {
-                    if ((act_any >> r) & 1u) {                                // lit elsewhere in the row: this strip's 768 bytes
-                        bulk_store_shared_to_global(out_strip + (size_t)(y_lo + r) * row_bytes, zeros, strip_bytes);
-                        ++r;
-                    } else {                                                   // dark across the width: strip 0 writes whole rows
-                        int e = r + 1;
-                        while (e < y + len && e - r < kZeroRows && !((act_any >> e) & 1u)) ++e;
-                        if (s == 0) bulk_store_shared_to_global(out_base + (size_t)(y_lo + r) * row_bytes, zeros, (unsigned)(e - r) * row_bytes);
-                        r = e;
-                    }
-                }
-                bulk_commit_group();
-            }
-            y += len;
-        }
+    uint4 t1, t2, t3, t4, f2, f3;
+    row_max(A[1], L[0], R[0], t1, nullptr);
+    row_max(A[2], L[1], R[1], t2, &f2);
+    row_max(A[3], L[2], R[2], t3, &f3);
+    row_max(A[4], L[3], R[3], t4, nullptr);
+    unsigned m[4];
+    m[0] = max3_u16x2(max3_u16x2(A[0].x, t1.x, f2.x), t3.x, A[4].x);
+    m[1] = max3_u16x2(max3_u16x2(A[0].y, t1.y, f2.y), t3.y, A[4].y);
+    m[2] = max3_u16x2(max3_u16x2(A[0].z, t1.z, f2.z), t3.z, A[4].z);
+    m[3] = max3_u16x2(max3_u16x2(A[0].w, t1.w, f2.w), t3.w, A[4].w);
+    store_row<MODE>(lut, m, lane_on, out_px, bg_px);
+    if (two) {
+        m[0] = max3_u16x2(max3_u16x2(A[1].x, t2.x, f3.x), t4.x, A[5].x);
+        m[1] = max3_u16x2(max3_u16x2(A[1].y, t2.y, f3.y), t4.y, A[5].y);
+        m[2] = max3_u16x2(max3_u16x2(A[1].z, t2.z, f3.z), t4.z, A[5].z);
+        m[3] = max3_u16x2(max3_u16x2(A[1].w, t2.w, f3.w), t4.w, A[5].w);
+        store_row<MODE>(lut, m, lane_on, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr);
     }
 }
 
 // One work item = one (frame, camera, band), items dealt round-robin to the CTAs.  Shared memory:
-// uint16 centre plane [(band_rows+4)][W] | occupancy words | kZeroRows image rows of zeros.
-// Bands without a record cost one thread a few bulk stores from the zeros.
+// uint16 centre plane [(band_rows+5)][W] | hit masks (bit r of hits[s]: plane row r has a centre
+// within 2 px of strip s; hits[n_strips]: anywhere) | kZeroRows image rows of zeros.
+// Per item: scatter the bucket's records into the plane, then every warp takes (2 rows x 256 px)
+// cells: a cell whose 6-row window has no hit is dark and is bulk-stored from the shared zeros by
+// one lane (MODE 0; rows dark across the width go out as one store), a lit cell is computed and
+// stored from registers.  Bands without a record cost one thread a few bulk stores.
 template <int MODE>
-__global__ void __launch_bounds__(kRasterThreads, 4) binned_raster_kernel(const RasterArgs a) {
+__global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int s_task;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.width;
     const int plane_rows = a.band_rows + 4;
-    const unsigned plane_bytes = (unsigned)(plane_rows * W) * 2u;
+    const unsigned plane_bytes = (unsigned)((plane_rows + 1) * W) * 2u;      // one spare (always zero) row: the odd last row reads it
     const unsigned row_bytes = (unsigned)W * 3u;
     const unsigned zero_bytes = (unsigned)kZeroRows * row_bytes;
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
-    unsigned *occ = reinterpret_cast<unsigned *>(smem + plane_bytes);
-    unsigned char *zeros = smem + plane_bytes + kOccBytes;
+    unsigned *hits = reinterpret_cast<unsigned *>(smem + plane_bytes);
+    unsigned char *zeros = smem + plane_bytes + kHitBytes;
     const bool inplace = MODE == 1 && a.bg == a.frames;
     const unsigned x_mask = (1u << a.x_bits) - 1u;
-    {   // plane and occupancy start out (and are kept) all-zero between items; the zero rows stay zero
+    const int n_strips = a.n_strips;
+    {   // plane and hit masks start out (and are kept) all-zero between items; the zero rows stay zero
         uint4 *p4 = reinterpret_cast<uint4 *>(smem);
-        const int n16 = (int)((plane_bytes + kOccBytes + zero_bytes) >> 4);
-        for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) s_task = 0;
+        const int n16 = (int)((plane_bytes + kHitBytes + zero_bytes) >> 4);
+        for (int i = tid; i < n16; i += kRasterBlock) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
     __syncthreads();
-    const int n_tasks = a.n_strips * a.n_groups;
+    const int stride = (int)gridDim.x;
 
-    int item = blockIdx.x;
-    long long lo = 0, hi = 0;
-    if (item < a.n_items) { lo = a.start[item]; hi = min((long long)a.start[item + 1], a.sorted_cap); }
-    while (item < a.n_items) {
-        // bounds of the next item, fetched while this one is processed
-        const int next = item + (int)gridDim.x;
-        long long nlo = 0, nhi = 0;
-        if (next < a.n_items) { nlo = a.start[next]; nhi = a.start[next + 1]; }
-
-        if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
-            if (tid == 0) {
-                const int y_first = (item % a.n_bands) * a.band_rows;
-                const int rows_out = min(a.band_rows, a.height - y_first);
-                uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
-                unsigned left = (unsigned)rows_out * row_bytes, off = 0;
-                while (left) {
-                    const unsigned n = min(left, zero_bytes);
-                    bulk_store_shared_to_global(out_base + off, zeros, n);
-                    off += n; left -= n;
-                }
-                bulk_commit_group();
-            }
-        } else if (!(hi <= lo && inplace)) {
-            const int band = item % a.n_bands;
-            const long long image = item / a.n_bands;
-            const int y_first = band * a.band_rows;
-            const int rows_out = min(a.band_rows, a.height - y_first);
-            uint8_t *out_base = a.frames + ((size_t)image * a.height + y_first) * row_bytes;
-            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)image * a.height + y_first) * row_bytes : nullptr;
-            // 1. centres of this bucket -> plane (max ordinal per pixel) + occupancy; loads batched for latency
-            //    (the validity checks only matter after a capacity overflow, when the pool holds stale records)
-            for (long long base = lo + tid; base < hi; base += 4 * kRasterThreads) {
-                unsigned rec[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const long long i = base + q * kRasterThreads;
-                    rec[q] = i < hi ? __ldg(a.sorted + i) : 0xffffffffu;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned x = rec[q] & x_mask, row = (rec[q] & 0xffffu) >> a.x_bits, ord1 = rec[q] >> 16;
-                    if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
-                        smem_max_u16(plane, row * (unsigned)W + x, ord1);
-                        atomicOr(&occ[row], 1u << (x >> 6));
+    if (warp == kRasterWarps) {
+        // Filler warp: walks this CTA's items and, for every band no record landed in, streams zeros
+        // out of shared memory.  It never waits for the compute warps, so the store queue stays fed
+        // while they work on the lit bands.
+        if (MODE == 0) {
+            for (int base = blockIdx.x; base < a.n_items; base += 32 * stride) {
+                const int item = base + lane * stride;                    // 32 items per sweep, one per lane
+                bool empty = false;
+                if (item < a.n_items) empty = (a.debug & 1) || a.start[item + 1] <= a.start[item];
+                unsigned todo = __ballot_sync(kFull, empty);
+                if (lane == 0) {
+                    for (; todo; todo &= todo - 1u) {
+                        const int it = base + (__ffs(todo) - 1) * stride;
+                        const int y_first = (it % a.n_bands) * a.band_rows;
+                        const int rows_out = min(a.band_rows, a.height - y_first);
+                        uint8_t *out_base = a.frames + ((size_t)(it / a.n_bands) * a.height + y_first) * row_bytes;
+                        unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+                        while (left) {
+                            const unsigned n = min(left, zero_bytes);
+                            bulk_store_shared_to_global(out_base + off, zeros, n);
+                            off += n; left -= n;
+                        }
+                        bulk_commit_group();
                     }
                 }
             }
-            __syncthreads();
-            // 2. dilation + colour + store: (strip, row group) tasks claimed dynamically by the warps
-            for (;;) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(&s_task, 1);
-                task = __shfl_sync(kFull, task, 0);
-                if (task >= n_tasks) break;
-                const int s = task % a.n_strips, g = task / a.n_strips;
-                const int y_lo = g * a.rows_per_group, y_hi = min(y_lo + a.rows_per_group, rows_out);
-                if (y_lo < y_hi) raster_task<MODE>(a, plane, occ, zeros, s, y_lo, y_hi, out_base, bg_base, inplace, lane);
-            }
-            __syncthreads();
-            // 3. restore the all-zero plane by revisiting the records
-            for (long long base = lo + tid; base < hi; base += 4 * kRasterThreads) {
-                unsigned rec[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const long long i = base + q * kRasterThreads;
-                    rec[q] = i < hi ? __ldg(a.sorted + i) : 0xffffffffu;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned x = rec[q] & x_mask, row = (rec[q] & 0xffffu) >> a.x_bits;
-                    if (row < (unsigned)plane_rows && x < (unsigned)W) plane[row * (unsigned)W + x] = 0;
-                }
-            }
-            if (tid < plane_rows) occ[tid] = 0u;
-            if (tid == 0) s_task = 0;
-            __syncthreads();
+            if (lane == 0) bulk_wait_group_read<0>();
         }
-        item = next; lo = nlo; hi = min(nhi, a.sorted_cap);
+        return;
+    }
+    auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
+
+    auto scatter = [&](unsigned rec) {
+        // (the validity checks only matter after a capacity overflow, when the pool holds stale records)
+        const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
+        if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
+            smem_max_u16(plane, row * (unsigned)W + x, ord1);
+            const unsigned bit = 1u << row, s = x / kStripPx, off = x % kStripPx;
+            atomicOr(&hits[s], bit);
+            if (off < 2u && s > 0u) atomicOr(&hits[s - 1], bit);
+            if (off >= kStripPx - 2u && s + 1u < (unsigned)n_strips) atomicOr(&hits[s + 1], bit);
+            atomicOr(&hits[n_strips], bit);
+        }
+    };
+    auto fetch = [&](long long begin, long long end, unsigned (&rec)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long i = begin + tid + q * kRasterThreads;
+            rec[q] = i < end ? __ldg(a.sorted + i) : 0xffffffffu;
+        }
+    };
+
+    // software pipeline over this CTA's items: bounds two items ahead, first records one item ahead
+    int item = blockIdx.x;
+    long long lo = 0, hi = 0, nlo = 0, nhi = 0;
+    unsigned pre[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (item < a.n_items) { lo = a.start[item]; hi = min((long long)a.start[item + 1], a.sorted_cap); if (a.debug & 1) hi = lo; fetch(lo, hi, pre); }
+    if (item + stride < a.n_items) { nlo = a.start[item + stride]; nhi = min((long long)a.start[item + stride + 1], a.sorted_cap); if (a.debug & 1) nhi = nlo; }
+    while (item < a.n_items) {
+        long long n2lo = 0, n2hi = 0;
+        if (item + 2 * stride < a.n_items) { n2lo = a.start[item + 2 * stride]; n2hi = a.start[item + 2 * stride + 1]; if (a.debug & 1) n2hi = n2lo; }
+        unsigned pre_next[4];
+        fetch(nlo, nhi, pre_next);         // (nlo == nhi == 0 past the last item: nothing is loaded)
+
+        if (hi <= lo && MODE == 0) {       // nothing lands in this band: the filler warp writes its zeros
+        } else if (!(hi <= lo && inplace)) {
+            const int y_first = (item % a.n_bands) * a.band_rows;
+            const int rows_out = min(a.band_rows, a.height - y_first);
+            uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
+            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
+            // 1. centres of this bucket -> plane (max ordinal per pixel) + hit masks
+#pragma unroll
+            for (int q = 0; q < 4; ++q) scatter(pre[q]);
+            for (long long base = lo + 4 * kRasterThreads; base < hi; base += 4 * kRasterThreads) {
+                unsigned rec[4];
+                fetch(base, hi, rec);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) scatter(rec[q]);
+            }
+            sync_compute();
+            // 2. cells: dilation + colour + store
+            const unsigned hit_any = hits[n_strips];
+            const int n_pairs = (rows_out + 1) >> 1;
+            for (int c = warp; c < ((a.debug & 4) ? 0 : n_pairs * n_strips); c += kRasterWarps) {
+                const int p = c / n_strips, s = (c + p) % n_strips;           // rotate: a warp does not keep one strip
+                const int y = 2 * p;
+                const bool two = y + 1 < rows_out;
+                const unsigned window = two ? 0x3fu : 0x1fu;
+                const int xs = s * kStripPx;
+                uint8_t *out_row = out_base + (size_t)y * row_bytes;
+                const bool lit = ((hits[s] >> y) & window) != 0u;
+                if (lit || (MODE == 1 && !inplace)) {
+                    const int x0 = xs + lane * 8;
+                    const bool lane_on = x0 < W;
+                    const int xc = min(x0, W - 8);                             // lanes past the edge recompute the last 8 px, store nothing
+                    if (lit)
+                        raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_row + (size_t)x0 * 3,
+                                          MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes);
+                    else if (lane_on) {                                        // out-of-place composite of a dark cell: copy
+                        for (int r = 0; r < (two ? 2 : 1); ++r) {
+                            const uint2 *b = reinterpret_cast<const uint2 *>(bg_base + (size_t)(y + r) * row_bytes + (size_t)x0 * 3);
+                            uint2 *d = reinterpret_cast<uint2 *>(out_row + (size_t)r * row_bytes + (size_t)x0 * 3);
+                            const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
+                            d[0] = b0; d[1] = b1; d[2] = b2;
+                        }
+                    }
+                } else if (MODE == 0 && lane == 0) {
+                    if (((hit_any >> y) & window) == 0u) {                     // dark across the width: whoever has strip 0 writes whole rows
+                        if (s == 0) {
+                            bulk_store_shared_to_global(out_row, zeros, (two ? 2u : 1u) * row_bytes);
+                            bulk_commit_group();
+                        }
+                    } else {
+                        const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
+                        bulk_store_shared_to_global(out_row + (size_t)xs * 3, zeros, strip_bytes);
+                        if (two) bulk_store_shared_to_global(out_row + row_bytes + (size_t)xs * 3, zeros, strip_bytes);
+                        bulk_commit_group();
+                    }
+                }
+            }
+            sync_compute();
+            // 3. restore the all-zero plane: clear the rows that received a centre
+            for (unsigned rows = hit_any; rows; rows &= rows - 1u) {
+                uint4 *r4 = reinterpret_cast<uint4 *>(plane + (size_t)(__ffs(rows) - 1) * W);
+                for (int i = tid; i < W / 8; i += kRasterThreads) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (tid <= n_strips) hits[tid] = 0u;
+            sync_compute();
+        }
+        item += stride;
+        lo = nlo; hi = nhi; nlo = n2lo; nhi = min(n2hi, a.sorted_cap);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pre[q] = pre_next[q];
     }
     // the shared zeros must stay valid until the last bulk stores have read them
     if (lane == 0) bulk_wait_group_read<0>();
@@ -622,7 +641,7 @@ namespace {
 struct ClipPlan {
     int mode;
     int band_rows, n_bands, x_bits;
-    int n_strips, n_groups, rows_per_group;
+    int n_strips;
     long long cap;          // records per frame
     int n_buckets;
     size_t raster_smem;
@@ -634,7 +653,7 @@ struct ClipPlan {
 
 constexpr int kRasterCtasPerSm = 4;
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
-constexpr size_t kRasterStageSmem = kOccBytes;   // + the plane + kZeroRows image rows
+constexpr size_t kRasterStageSmem = kHitBytes;   // + the plane + kZeroRows image rows
 
 int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     CAMA_REQUIRE(d, "desc is NULL");
@@ -651,9 +670,9 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     bool binned_ok = (W % 16 == 0) && W <= 2048 && d->n_instances <= 65534;
     if (binned_ok) {
         while ((1 << x_bits) < W) ++x_bits;
-        long long rows = ((long long)kRasterSmemBudget - (long long)kRasterStageSmem - (long long)kZeroRows * W * 3) / (2ll * W) - 4;
+        long long rows = ((long long)kRasterSmemBudget - (long long)kRasterStageSmem - (long long)kZeroRows * W * 3) / (2ll * W) - 5;
         rows = std::min<long long>(rows, (1ll << (16 - x_bits)) - 4);
-        rows = std::min<long long>(rows, kOccBytes / 4 - 4);
+        rows = std::min<long long>(rows, kMaxPlaneRows - 4);
         if (const char *env = getenv("CAMA_BAND_ROWS")) {        // tuning knob for experiments
             const long long want = atoll(env);
             if (want >= 1) rows = std::min(rows, want);
@@ -685,9 +704,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.x_bits = x_bits;
         p.n_bands = (H + band_rows - 1) / band_rows;
         p.n_strips = (W + kStripPx - 1) / kStripPx;
-        p.n_groups = std::max(1, std::min(4 * kRasterWarps / p.n_strips, band_rows / 10));
-        p.n_groups = std::max(p.n_groups, (band_rows + kMaxGroupRows - 1) / kMaxGroupRows);
-        p.rows_per_group = (band_rows + p.n_groups - 1) / p.n_groups;
+
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
         CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
         p.n_buckets = (int)nb;
@@ -695,7 +712,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         if (cap <= 0) cap = std::max<long long>(d->n_vertices, 4096);      // one visible camera per vertex and frame
         CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
         p.cap = cap;
-        p.raster_smem = (size_t)(band_rows + 4) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
+        p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         p.off_zero = off;
         p.off_counter = take(256);
         p.off_fcount = take(sizeof(unsigned) * (size_t)std::max(d->n_frames, 1));
@@ -822,15 +839,16 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     RasterArgs r{};
     r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
     r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
-    r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.n_groups = p.n_groups; r.rows_per_group = p.rows_per_group;
+    r.x_bits = p.x_bits; r.n_strips = p.n_strips;
+    if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
     r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
     if (d->background) {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        binned_raster_kernel<1><<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+        binned_raster_kernel<1><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
     } else {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        binned_raster_kernel<0><<<raster_grid, kRasterThreads, p.raster_smem, s>>>(r);
+        binned_raster_kernel<0><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
     }
     CAMA_LAUNCHED(ctx);
     CAMA_CUDA_TRY(mark(4));

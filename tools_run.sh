@@ -1,5 +1,5 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for R in 0 16 12; do
+for R in 0 16 12 8; do
   echo "== CAMA_BAND_ROWS=$R"
   CAMA_BAND_ROWS=$R timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
 import sys,json
