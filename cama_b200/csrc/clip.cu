@@ -340,7 +340,7 @@ __device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix
 
 constexpr int kRasterThreads = 128;            // compute threads of a raster CTA
 constexpr int kRasterWarps = kRasterThreads / 32;
-constexpr int kRasterBlock = kRasterThreads + 32;   // + one warp that only issues the zero stores of empty bands (MODE 0)
+constexpr int kRasterBlock = kRasterThreads;
 constexpr int kStripPx = 256;                  // pixels of one warp strip: 8 per lane
 constexpr int kHitBytes = 128;                 // per-strip hit masks (+ one for "any strip"), padded
 constexpr int kZeroRows = 2;                   // image rows of zeros kept in shared memory (source of dark output)
@@ -494,36 +494,6 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     __syncthreads();
     const int stride = (int)gridDim.x;
 
-    if (warp == kRasterWarps) {
-        // Filler warp: walks this CTA's items and, for every band no record landed in, streams zeros
-        // out of shared memory.  It never waits for the compute warps, so the store queue stays fed
-        // while they work on the lit bands.
-        if (MODE == 0) {
-            for (int base = blockIdx.x; base < a.n_items; base += 32 * stride) {
-                const int item = base + lane * stride;                    // 32 items per sweep, one per lane
-                bool empty = false;
-                if (item < a.n_items) empty = (a.debug & 1) || a.start[item + 1] <= a.start[item];
-                unsigned todo = __ballot_sync(kFull, empty);
-                if (lane == 0) {
-                    for (; todo; todo &= todo - 1u) {
-                        const int it = base + (__ffs(todo) - 1) * stride;
-                        const int y_first = (it % a.n_bands) * a.band_rows;
-                        const int rows_out = min(a.band_rows, a.height - y_first);
-                        uint8_t *out_base = a.frames + ((size_t)(it / a.n_bands) * a.height + y_first) * row_bytes;
-                        unsigned left = (unsigned)rows_out * row_bytes, off = 0;
-                        while (left) {
-                            const unsigned n = min(left, zero_bytes);
-                            bulk_store_shared_to_global(out_base + off, zeros, n);
-                            off += n; left -= n;
-                        }
-                        bulk_commit_group();
-                    }
-                }
-            }
-            if (lane == 0) bulk_wait_group_read<0>();
-        }
-        return;
-    }
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
 
     auto scatter = [&](unsigned rec) {
@@ -558,7 +528,19 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         unsigned pre_next[4];
         fetch(nlo, nhi, pre_next);         // (nlo == nhi == 0 past the last item: nothing is loaded)
 
-        if (hi <= lo && MODE == 0) {       // nothing lands in this band: the filler warp writes its zeros
+        if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
+            if (tid == 0) {
+                const int y_first = (item % a.n_bands) * a.band_rows;
+                const int rows_out = min(a.band_rows, a.height - y_first);
+                uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
+                unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+                while (left) {
+                    const unsigned n = min(left, zero_bytes);
+                    bulk_store_shared_to_global(out_base + off, zeros, n);
+                    off += n; left -= n;
+                }
+                bulk_commit_group();
+            }
         } else if (!(hi <= lo && inplace)) {
             const int y_first = (item % a.n_bands) * a.band_rows;
             const int rows_out = min(a.band_rows, a.height - y_first);
@@ -652,6 +634,7 @@ struct ClipPlan {
 };
 
 constexpr int kRasterCtasPerSm = 4;
+constexpr int kDefaultBandRows = 16;
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
 constexpr size_t kRasterStageSmem = kHitBytes;   // + the plane + kZeroRows image rows
 
@@ -673,6 +656,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         long long rows = ((long long)kRasterSmemBudget - (long long)kRasterStageSmem - (long long)kZeroRows * W * 3) / (2ll * W) - 5;
         rows = std::min<long long>(rows, (1ll << (16 - x_bits)) - 4);
         rows = std::min<long long>(rows, kMaxPlaneRows - 4);
+        rows = std::min<long long>(rows, kDefaultBandRows);       // measured optimum on config 2 (profiles/)
         if (const char *env = getenv("CAMA_BAND_ROWS")) {        // tuning knob for experiments
             const long long want = atoll(env);
             if (want >= 1) rows = std::min(rows, want);
