@@ -559,14 +559,20 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
             // 2. cells: dilation + colour + store
             const unsigned hit_any = hits[n_strips];
             const int n_pairs = (rows_out + 1) >> 1;
-            for (int c = warp; c < ((a.debug & 4) ? 0 : n_pairs * n_strips); c += kRasterWarps) {
-                const int p = c / n_strips, s = (c + p) % n_strips;           // rotate: a warp does not keep one strip
+            // cell (pair p, strip s): warps take cells round-robin, the strip rotated by the pair index so
+            // that no warp keeps one strip; indices advance without integer division
+            int p = 0, s = warp, rot = 0;
+            for (;;) {
+                while (s >= n_strips) { s -= n_strips; ++p; if (++rot == n_strips) rot = 0; }
+                if (p >= n_pairs) break;
+                int sr = s + rot;
+                if (sr >= n_strips) sr -= n_strips;
                 const int y = 2 * p;
                 const bool two = y + 1 < rows_out;
                 const unsigned window = two ? 0x3fu : 0x1fu;
-                const int xs = s * kStripPx;
+                const int xs = sr * kStripPx;
                 uint8_t *out_row = out_base + (size_t)y * row_bytes;
-                const bool lit = ((hits[s] >> y) & window) != 0u;
+                const bool lit = ((hits[sr] >> y) & window) != 0u;
                 if (lit || (MODE == 1 && !inplace)) {
                     const int x0 = xs + lane * 8;
                     const bool lane_on = x0 < W;
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
                     }
                 } else if (MODE == 0 && lane == 0) {
                     if (((hit_any >> y) & window) == 0u) {                     // dark across the width: whoever has strip 0 writes whole rows
-                        if (s == 0) {
+                        if (sr == 0) {
                             bulk_store_shared_to_global(out_row, zeros, (two ? 2u : 1u) * row_bytes);
                             bulk_commit_group();
                         }
@@ -595,12 +601,15 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
                         bulk_commit_group();
                     }
                 }
+                s += kRasterWarps;
             }
             sync_compute();
-            // 3. restore the all-zero plane: clear the rows that received a centre
-            for (unsigned rows = hit_any; rows; rows &= rows - 1u) {
-                uint4 *r4 = reinterpret_cast<uint4 *>(plane + (size_t)(__ffs(rows) - 1) * W);
-                for (int i = tid; i < W / 8; i += kRasterThreads) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+            // 3. restore the all-zero plane (clearing all of it costs fewer instructions than picking the rows hit)
+            {
+                uint4 *p4 = reinterpret_cast<uint4 *>(plane);
+                const int n16 = (plane_rows * W) >> 3;
+#pragma unroll 4
+                for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             if (tid <= n_strips) hits[tid] = 0u;
             sync_compute();
