@@ -46,6 +46,7 @@ struct ClipArgs {
     unsigned *plane;                   // [F,C,H,W]
     // BINNED
     int band_rows, n_bands, x_bits;
+    unsigned band_magic;               // ceil(2^32 / band_rows): row / band_rows == umulhi(row, band_magic) for rows < 65536
     long long cap;                     // records per frame
     unsigned *fcount;                  // [F]
     unsigned *hist;                    // [F*C*NB]
@@ -78,56 +79,94 @@ __device__ __forceinline__ bool load_vertex(const ClipArgs &a, long long n, doub
     return true;
 }
 
-// One chassis-frame point against one camera (reference cama/dataset.py:110-115 + reproject.py:187-205).
-// The early exits only skip work whose result the visibility mask would discard anyway:
+// One chassis-frame point against one camera (reference cama/dataset.py:110-115 + reproject.py:187-205)
+// up to, but not including, the perspective divide.  Returns false for points the visibility mask
+// is certain to discard; the early exits only skip work whose result the mask would discard anyway:
 //  * K row 2 == (0,0,1) makes q_z == p_z bit-for-bit, so p_z <= 0 rejects before x,y are formed;
 //  * q_x < -q_z or q_x > (W+1) q_z (same for y) puts u (v) outside [0,W) by a whole pixel, far
 //    beyond what the rounding of the division could undo.
-__device__ __forceinline__ bool camera_visible(const CamBlock &cams, int c, double cx, double cy, double cz, int width, int height,
-                                               double &v, double &u) {
+__device__ __forceinline__ bool camera_candidate(const CamBlock &cams, int c, double cx, double cy, double cz, int width, int height,
+                                                 double &qx, double &qy, double &qz) {
     const double *E = cams.E[c];
     const double *K = cams.K[c];
     const double pz = affine_row(E + 8, cx, cy, cz);
     if (cams.k_row2_is_001[c] && !(pz > 0.0)) return false;
     const double px = affine_row(E, cx, cy, cz);
     const double py = affine_row(E + 4, cx, cy, cz);
-    const double qz = linear_row(K + 6, px, py, pz);
+    qz = linear_row(K + 6, px, py, pz);
     if (!((qz > 0.0) & (qz <= DBL_MAX))) return false;
-    const double qx = linear_row(K, px, py, pz);
-    const double qy = linear_row(K + 3, px, py, pz);
-    if ((qx < -qz) | (qx > (double)(width + 1) * qz) | (qy < -qz) | (qy > (double)(height + 1) * qz)) return false;
-    u = __ddiv_rn(qx, qz);
-    v = __ddiv_rn(qy, qz);
-    return (u >= 0.0) & (u < (double)width) & (v >= 0.0) & (v < (double)height);
+    qx = linear_row(K, px, py, pz);
+    qy = linear_row(K + 3, px, py, pz);
+    return !((qx < -qz) | (qx > (double)(width + 1) * qz) | (qy < -qz) | (qy > (double)(height + 1) * qz));
 }
 
-// Warp-collective append of one record per predicated lane: slot in the frame's record pool
-// (one atomic per warp) and rank inside the record's bucket (one atomic per distinct bucket).
+// Pixel of a candidate: trunc(fl(q_x / q_z)), trunc(fl(q_y / q_z)) and the in-image test of the reference,
+// bit-exact, without a double-precision division for almost every point: a float32 estimate of the
+// quotient (error < 1.1e-3 for |u| <= 2049: two conversions, an approximate reciprocal, a multiply)
+// decides the pixel whenever it is further than kPixelGuard from an integer; only the rest take
+// the IEEE divisions.  `exact_v/u` receive the quotients when `want_exact` (dense (v,u) output).
+constexpr float kPixelGuard = 4e-3f;
+__device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy, double qz, int width, int height, bool want_exact,
+                                                int &vi, int &ui, double &v, double &u) {
+    const float rz = __frcp_rn(__double2float_rn(qz));
+    const float ue = __double2float_rn(qx) * rz, ve = __double2float_rn(qy) * rz;
+    const float uf = floorf(ue), vf = floorf(ve);
+    const bool safe = (ue - uf > kPixelGuard) & (uf + 1.0f - ue > kPixelGuard) & (ve - vf > kPixelGuard) & (vf + 1.0f - ve > kPixelGuard) &
+                      (fabsf(ue) < 4096.0f) & (fabsf(ve) < 4096.0f);
+    bool vis = cand & (uf >= 0.0f) & (uf < (float)width) & (vf >= 0.0f) & (vf < (float)height);
+    ui = (int)uf; vi = (int)vf;
+    if (cand && (want_exact || !safe)) {
+        u = __ddiv_rn(qx, qz);
+        v = __ddiv_rn(qy, qz);
+        vis = (u >= 0.0) & (u < (double)width) & (v >= 0.0) & (v < (double)height);
+        ui = __double2int_rz(u);       // reference cama/reproject.py:249 (values are >= 0: trunc == floor)
+        vi = __double2int_rz(v);
+    }
+    return vis;
+}
+
+// Warp-collective append of one record per predicated lane: slot in the frame's record pool (one
+// atomic per warp) and rank inside the record's bucket (one atomic per distinct bucket; lanes hold
+// consecutive vertices of a polyline, so almost always a single one).
 __device__ __forceinline__ void warp_append(const ClipArgs &a, int f, bool pred, unsigned bucket, unsigned payload) {
     const unsigned mask = __ballot_sync(kFull, pred);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(&a.fcount[f], (unsigned)__popc(mask));
+    const unsigned lead_bucket = __shfl_sync(kFull, bucket, leader);
+    const unsigned same = __ballot_sync(kFull, pred && bucket == lead_bucket);
+    unsigned base = 0, first = 0;
+    if (lane == leader) {                                          // both atomics in flight together
+        base = atomicAdd(&a.fcount[f], (unsigned)__popc(mask));
+        first = atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(same));
+    }
+    unsigned rank;
+    if (same == mask) {
+        rank = __shfl_sync(kFull, first, leader) + __popc(mask & ((1u << lane) - 1u));
+    } else {
+        rank = __shfl_sync(kFull, first, leader) + __popc(same & ((1u << lane) - 1u));
+        unsigned rest = mask & ~same;
+        while (rest) {                                             // the other buckets, one round each
+            const int head = __ffs(rest) - 1;
+            const unsigned hb = __shfl_sync(kFull, bucket, head);
+            const unsigned grp = __ballot_sync(kFull, pred && bucket == hb) & rest;
+            unsigned f0 = 0;
+            if (lane == head) f0 = atomicAdd(&a.hist[hb], (unsigned)__popc(grp));
+            f0 = __shfl_sync(kFull, f0, head);
+            if ((grp >> lane) & 1u) rank = f0 + __popc(grp & ((1u << lane) - 1u));
+            rest &= ~grp;
+        }
+    }
     base = __shfl_sync(kFull, base, leader);
     if (pred) {
-        const unsigned peers = __match_any_sync(mask, bucket);
-        const int head = __ffs(peers) - 1;
-        unsigned first = 0;
-        if (lane == head) first = atomicAdd(&a.hist[bucket], (unsigned)__popc(peers));
-        first = __shfl_sync(peers, first, head);
-        const unsigned rank = first + __popc(peers & ((1u << lane) - 1u));
         const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
         if ((long long)slot < a.cap) a.unsorted[(size_t)f * a.cap + slot] = make_uint4(bucket, rank, payload, 0u);
     }
 }
 
-template <bool BINNED>
-__device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, bool vis, double v, double u, int ord, long long n) {
-    const int vi = vis ? __double2int_rz(v) : 0;   // reference cama/reproject.py:249 (values are >= 0: trunc == floor)
-    const int ui = vis ? __double2int_rz(u) : 0;
-    if (vis) {
+template <bool BINNED, bool DEBUG>
+__device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, bool vis, int vi, int ui, double v, double u, int ord, long long n) {
+    if (DEBUG && vis) {
         if (a.visible_counts) atomicAdd(&a.visible_counts[((size_t)f * a.n_cams + c) * a.n_instances + ord], 1);
         if (a.vu_dense) {
             double *o = a.vu_dense + (((size_t)f * a.n_cams + c) * a.n_vertices + n) * 2;
@@ -137,8 +176,14 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, boo
     if (!BINNED) {
         if (vis) atomicMax(&a.plane[(((size_t)f * a.n_cams + c) * a.height + vi) * a.width + ui], (unsigned)(ord + 1));
     } else {
+        // a centre equal to the previous lane's (same pixel, same instance: dense far-away vertices) adds nothing to a max
+        const unsigned code = ((unsigned)vi << 16) | (unsigned)ui;
+        const unsigned prev_code = __shfl_up_sync(kFull, vis ? code : 0xffffffffu, 1);
+        const int prev_ord = __shfl_up_sync(kFull, ord, 1);
+        if ((threadIdx.x & 31) != 0 && prev_code == code && prev_ord == ord) vis = false;
+        if (!__any_sync(kFull, vis)) return;
         const int rb = a.band_rows;
-        const int b0 = vi / rb;
+        const int b0 = (int)__umulhi((unsigned)vi, a.band_magic);   // vi / rb
         const int r = vi - b0 * rb;
         const unsigned bucket = (unsigned)((f * a.n_cams + c) * a.n_bands + b0);
         const unsigned key = (unsigned)(ord + 1) << 16;
@@ -146,28 +191,29 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, boo
         // the two rows next to a band edge also matter to the neighbouring band (dilation radius 2)
         const bool up = vis && r < 2 && b0 > 0;
         const bool down = vis && r >= rb - 2 && b0 + 1 < a.n_bands;
-        const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
-        const int r2 = up ? r + rb : r - rb;
-        warp_append(a, f, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
+        if (__any_sync(kFull, up || down)) {
+            const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
+            const int r2 = up ? r + rb : r - rb;
+            warp_append(a, f, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
+        }
     }
 }
 
 constexpr int kGeoThreads = 256;
-constexpr int kGeoV = 4;                   // vertices held in registers per thread
-constexpr int kGeoTile = kGeoThreads * kGeoV;
 constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads amortised over them)
 
-// Work unit = (tile of 1024 vertices, chunk of 8 frames).  A thread keeps its 4 vertices in
-// registers and walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).
-// Lanes hold consecutive vertices, so crop survival — and with it the expensive 6-camera tail —
-// is almost warp-uniform (polylines are spatially coherent).
-template <int LAYOUT, bool BINNED>
-__global__ void __launch_bounds__(kGeoThreads) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
+// Work unit = (tile of 256 vertices, chunk of 8 frames).  A thread keeps its vertex in registers and
+// walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).  Lanes hold
+// consecutive vertices, so crop survival — and with it the 6-camera tail — is almost warp-uniform
+// (polylines are spatially coherent).
+template <int LAYOUT, bool BINNED, bool DEBUG>
+__global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT[kGeoFrames][12];
     const int tid = threadIdx.x;
-    const long long n_tiles = (a.n_vertices + kGeoTile - 1) / kGeoTile;
+    const long long n_tiles = (a.n_vertices + kGeoThreads - 1) / kGeoThreads;
     const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
     const long long units = n_tiles * n_chunks;
+    const bool want_exact = DEBUG && a.vu_dense != nullptr;
     for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
@@ -175,30 +221,28 @@ __global__ void __launch_bounds__(kGeoThreads) clip_geometry_kernel(const ClipAr
         __syncthreads();
         if (tid < nf * 12) sT[tid / 12][tid % 12] = a.w2c64[(size_t)f0 * 12 + tid];
         __syncthreads();
-        double vx[kGeoV], vy[kGeoV], vz[kGeoV];
-        int vord[kGeoV];
-        bool valid[kGeoV];
-#pragma unroll
-        for (int k = 0; k < kGeoV; ++k)
-            valid[k] = load_vertex<LAYOUT>(a, tile * kGeoTile + k * kGeoThreads + tid, vx[k], vy[k], vz[k], vord[k]);
+        const long long n = tile * kGeoThreads + tid;
+        double vx, vy, vz;
+        int ord;
+        const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
         for (int fi = 0; fi < nf; ++fi) {
             const int f = f0 + fi;
             const double *T = sT[fi];
-#pragma unroll
-            for (int k = 0; k < kGeoV; ++k) {
-                // reference cama/dataset.py:99-105: world -> chassis, then the crop box
-                const double cx = affine_row(T, vx[k], vy[k], vz[k]);
-                const double cy = affine_row(T + 4, vx[k], vy[k], vz[k]);
-                const double cz = affine_row(T + 8, vx[k], vy[k], vz[k]);
-                const bool alive = valid[k] && in_box(cams.box, cx, cy, cz);
-                if (!__any_sync(kFull, alive)) continue;
-                if (alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + vord[k]], 1);
-                const long long n = tile * kGeoTile + k * kGeoThreads + tid;
-                for (int c = 0; c < a.n_cams; ++c) {
-                    double v = 0.0, u = 0.0;
-                    const bool vis = alive && camera_visible(cams, c, cx, cy, cz, a.width, a.height, v, u);
-                    if (!BINNED || __any_sync(kFull, vis)) emit_centre<BINNED>(a, f, c, vis, v, u, vord[k], n);
-                }
+            // reference cama/dataset.py:99-105: world -> chassis, then the crop box
+            const double cx = affine_row(T, vx, vy, vz);
+            const double cy = affine_row(T + 4, vx, vy, vz);
+            const double cz = affine_row(T + 8, vx, vy, vz);
+            const bool alive = valid && in_box(cams.box, cx, cy, cz);
+            if (!__any_sync(kFull, alive)) continue;
+            if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
+            for (int c = 0; c < a.n_cams; ++c) {
+                double qx = 0.0, qy = 0.0, qz = 1.0;
+                const bool cand = alive && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
+                if (!__any_sync(kFull, cand)) continue;
+                int vi = 0, ui = 0;
+                double v = 0.0, u = 0.0;
+                const bool vis = candidate_pixel(cand, qx, qy, qz, a.width, a.height, want_exact, vi, ui, v, u);
+                if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, f, c, vis, vi, ui, v, u, ord, n);
             }
         }
     }
@@ -644,6 +688,17 @@ struct ClipPlan {
 
 constexpr int kRasterCtasPerSm = 4;
 constexpr int kDefaultBandRows = 16;
+template <bool BINNED>
+void launch_geometry(bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
+    if (f32) {
+        if (debug) clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true><<<grid, kGeoThreads, 0, s>>>(a, cams);
+        else clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false><<<grid, kGeoThreads, 0, s>>>(a, cams);
+    } else {
+        if (debug) clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true><<<grid, kGeoThreads, 0, s>>>(a, cams);
+        else clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false><<<grid, kGeoThreads, 0, s>>>(a, cams);
+    }
+}
+
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
 constexpr size_t kRasterStageSmem = kHitBytes;   // + the plane + kZeroRows image rows
 
@@ -782,10 +837,11 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
                                                     d->instance_bgr, d->n_instances, lut);
         CAMA_LAUNCHED(ctx);
     }
-    const long long n_tiles = (d->n_vertices + kGeoTile - 1) / kGeoTile;
+    const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
     const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
-    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 8));
+    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 16));
     const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
+    const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;
 
     if (p.mode == CAMA_CLIP_PLANE) {
         a.plane = reinterpret_cast<unsigned *>(ws + p.off_plane);
@@ -793,8 +849,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
         CAMA_CUDA_TRY(mark(1));
         if (units > 0) {
-            if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
-            else clip_geometry_kernel<CAMA_VERTEX_F64X3, false><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+            launch_geometry<false>(f32, debug, geo_grid, s, a, cams);
             CAMA_LAUNCHED(ctx);
         }
         CAMA_CUDA_TRY(mark(2));
@@ -808,6 +863,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
 
     // BINNED
     a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.cap = p.cap;
+    a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
     a.fcount = reinterpret_cast<unsigned *>(ws + p.off_fcount);
     a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
     a.unsorted = reinterpret_cast<uint4 *>(ws + p.off_unsorted);
@@ -816,8 +872,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
-        if (f32) clip_geometry_kernel<CAMA_VERTEX_F32X4, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
-        else clip_geometry_kernel<CAMA_VERTEX_F64X3, true><<<geo_grid, kGeoThreads, 0, s>>>(a, cams);
+        launch_geometry<true>(f32, debug, geo_grid, s, a, cams);
         CAMA_LAUNCHED(ctx);
     }
     CAMA_CUDA_TRY(mark(2));
