@@ -47,10 +47,10 @@ struct ClipArgs {
     // BINNED
     int band_rows, n_bands, x_bits;
     unsigned band_magic;               // ceil(2^32 / band_rows): row / band_rows == umulhi(row, band_magic) for rows < 65536
-    long long cap;                     // records per frame
-    unsigned *fcount;                  // [F]
-    unsigned *hist;                    // [F*C*NB]
-    uint4 *unsorted;                   // [F*cap] {bucket, rank, payload, -}
+    long long pool_cap;                // records the pool holds
+    unsigned *pool_count;              // [1] records appended (attempted) so far
+    unsigned *hist;                    // [F*C*NB] records per bucket
+    uint2 *pool;                       // [pool_cap] {bucket, payload} in arrival order
 };
 
 // ------------------------------------------------------------------------------------------------ prep
@@ -125,47 +125,53 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
     return vis;
 }
 
-// Warp-collective append of one record per predicated lane: slot in the frame's record pool (one
-// atomic per warp) and rank inside the record's bucket (one atomic per distinct bucket; lanes hold
-// consecutive vertices of a polyline, so almost always a single one).
-__device__ __forceinline__ void warp_append(const ClipArgs &a, int f, bool pred, unsigned bucket, unsigned payload) {
+// Records are staged in shared memory and flushed to the global pool a few thousand at a time, so
+// the only global atomic whose result is waited for is one reservation per flush; the per-bucket
+// counts are fire-and-forget reductions.  (A version that reserved a pool slot and a bucket rank
+// with returning atomics per warp spent a quarter of its time waiting for them.)
+constexpr int kGeoThreads = 256;
+constexpr int kStageFlush = 1024;                                      // flush once this many records are staged ...
+constexpr int kStageCap = kStageFlush + kGeoThreads * 2 * CAMA_MAX_CAMERAS;   // ... so one more frame (<= 2 records per vertex and camera) always fits
+
+struct GeoStage {
+    uint2 rec[kStageCap];
+    unsigned count;
+    unsigned base;
+};
+
+__device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, bool pred, unsigned bucket, unsigned payload) {
     const unsigned mask = __ballot_sync(kFull, pred);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
     const unsigned lead_bucket = __shfl_sync(kFull, bucket, leader);
-    const unsigned same = __ballot_sync(kFull, pred && bucket == lead_bucket);
-    unsigned base = 0, first = 0;
-    if (lane == leader) {                                          // both atomics in flight together
-        base = atomicAdd(&a.fcount[f], (unsigned)__popc(mask));
-        first = atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(same));
+    const bool uniform = __ballot_sync(kFull, pred && bucket == lead_bucket) == mask;    // lanes = consecutive vertices of a polyline
+    unsigned slot = 0;
+    if (lane == leader) {
+        slot = atomicAdd(&st.count, (unsigned)__popc(mask));
+        if (uniform) atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(mask));            // result unused: a reduction
     }
-    unsigned rank;
-    if (same == mask) {
-        rank = __shfl_sync(kFull, first, leader) + __popc(mask & ((1u << lane) - 1u));
-    } else {
-        rank = __shfl_sync(kFull, first, leader) + __popc(same & ((1u << lane) - 1u));
-        unsigned rest = mask & ~same;
-        while (rest) {                                             // the other buckets, one round each
-            const int head = __ffs(rest) - 1;
-            const unsigned hb = __shfl_sync(kFull, bucket, head);
-            const unsigned grp = __ballot_sync(kFull, pred && bucket == hb) & rest;
-            unsigned f0 = 0;
-            if (lane == head) f0 = atomicAdd(&a.hist[hb], (unsigned)__popc(grp));
-            f0 = __shfl_sync(kFull, f0, head);
-            if ((grp >> lane) & 1u) rank = f0 + __popc(grp & ((1u << lane) - 1u));
-            rest &= ~grp;
-        }
-    }
-    base = __shfl_sync(kFull, base, leader);
-    if (pred) {
-        const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
-        if ((long long)slot < a.cap) a.unsorted[(size_t)f * a.cap + slot] = make_uint4(bucket, rank, payload, 0u);
-    }
+    if (!uniform && pred) atomicAdd(&a.hist[bucket], 1u);
+    slot = __shfl_sync(kFull, slot, leader) + __popc(mask & ((1u << lane) - 1u));
+    if (pred) st.rec[slot] = make_uint2(bucket, payload);
+}
+
+// CTA-wide: move the staged records to the pool.  Call with all threads, after a barrier that
+// follows the last append.
+__device__ __forceinline__ void stage_flush(const ClipArgs &a, GeoStage &st) {
+    const unsigned n = st.count;
+    if (threadIdx.x == 0) st.base = atomicAdd(a.pool_count, n);
+    __syncthreads();
+    const long long base = st.base;
+    for (unsigned i = threadIdx.x; i < n; i += kGeoThreads)
+        if (base + i < a.pool_cap) a.pool[base + i] = st.rec[i];
+    __syncthreads();
+    if (threadIdx.x == 0) st.count = 0;
+    __syncthreads();
 }
 
 template <bool BINNED, bool DEBUG>
-__device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, bool vis, int vi, int ui, double v, double u, int ord, long long n) {
+__device__ __forceinline__ void emit_centre(const ClipArgs &a, GeoStage &st, int f, int c, bool vis, int vi, int ui, double v, double u, int ord, long long n) {
     if (DEBUG && vis) {
         if (a.visible_counts) atomicAdd(&a.visible_counts[((size_t)f * a.n_cams + c) * a.n_instances + ord], 1);
         if (a.vu_dense) {
@@ -187,33 +193,36 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, int f, int c, boo
         const int r = vi - b0 * rb;
         const unsigned bucket = (unsigned)((f * a.n_cams + c) * a.n_bands + b0);
         const unsigned key = (unsigned)(ord + 1) << 16;
-        warp_append(a, f, vis, bucket, key | (unsigned)(((r + 2) << a.x_bits) | ui));
+        warp_append(a, st, vis, bucket, key | (unsigned)(((r + 2) << a.x_bits) | ui));
         // the two rows next to a band edge also matter to the neighbouring band (dilation radius 2)
         const bool up = vis && r < 2 && b0 > 0;
         const bool down = vis && r >= rb - 2 && b0 + 1 < a.n_bands;
         if (__any_sync(kFull, up || down)) {
             const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
             const int r2 = up ? r + rb : r - rb;
-            warp_append(a, f, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
+            warp_append(a, st, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
         }
     }
 }
 
-constexpr int kGeoThreads = 256;
 constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads amortised over them)
 
 // Work unit = (tile of 256 vertices, chunk of 8 frames).  A thread keeps its vertex in registers and
 // walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).  Lanes hold
 // consecutive vertices, so crop survival — and with it the 6-camera tail — is almost warp-uniform
 // (polylines are spatially coherent).
-template <int LAYOUT, bool BINNED, bool DEBUG>
+// NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls and every matrix entry
+// becomes a constant-bank operand of its DFMA instead of an indexed load (0 = any count up to 8).
+template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
 __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT[kGeoFrames][12];
+    __shared__ GeoStage stage;
     const int tid = threadIdx.x;
     const long long n_tiles = (a.n_vertices + kGeoThreads - 1) / kGeoThreads;
     const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
     const long long units = n_tiles * n_chunks;
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
+    if (BINNED && tid == 0) stage.count = 0;
     for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
@@ -233,18 +242,30 @@ __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const Cli
             const double cy = affine_row(T + 4, vx, vy, vz);
             const double cz = affine_row(T + 8, vx, vy, vz);
             const bool alive = valid && in_box(cams.box, cx, cy, cz);
-            if (!__any_sync(kFull, alive)) continue;
-            if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
-            for (int c = 0; c < a.n_cams; ++c) {
-                double qx = 0.0, qy = 0.0, qz = 1.0;
-                const bool cand = alive && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
-                if (!__any_sync(kFull, cand)) continue;
-                int vi = 0, ui = 0;
-                double v = 0.0, u = 0.0;
-                const bool vis = candidate_pixel(cand, qx, qy, qz, a.width, a.height, want_exact, vi, ui, v, u);
-                if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, f, c, vis, vi, ui, v, u, ord, n);
+            if (__any_sync(kFull, alive)) {
+                if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
+                const int n_cams = NCAMS ? NCAMS : a.n_cams;
+#pragma unroll
+                for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
+                    if (!NCAMS && c >= n_cams) break;
+                    double qx = 0.0, qy = 0.0, qz = 1.0;
+                    const bool cand = alive && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
+                    if (!__any_sync(kFull, cand)) continue;
+                    int vi = 0, ui = 0;
+                    double v = 0.0, u = 0.0;
+                    const bool vis = candidate_pixel(cand, qx, qy, qz, a.width, a.height, want_exact, vi, ui, v, u);
+                    if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, stage, f, c, vis, vi, ui, v, u, ord, n);
+                }
+            }
+            if (BINNED) {
+                // Every warp gets here once per frame.  The counter only grows, and the last warp to arrive
+                // reads its final value, so the OR over all threads is an exact, uniform decision.
+                if (__syncthreads_or(stage.count >= (unsigned)kStageFlush)) stage_flush(a, stage);
             }
         }
+    }
+    if (BINNED) {
+        if (__syncthreads_or(stage.count > 0u)) stage_flush(a, stage);
     }
 }
 
@@ -290,70 +311,85 @@ struct ClipStatsDev {
     unsigned pad;
 };
 
-// single CTA: start[b] = exclusive scan of hist, start[nb] = total; per-frame overflow check
+// single CTA: start[b] = exclusive scan of hist, start[nb] = total; pool overflow check.
+// 4096 buckets per round: one 16-byte load per thread, a warp scan, a scan of the 32 warp totals.
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, int nb,
-                                                           const unsigned *__restrict__ fcount, int n_frames, long long cap,
+                                                           const unsigned *__restrict__ pool_count, int n_frames, long long pool_cap,
                                                            ClipStatsDev *__restrict__ stats) {
     __shared__ unsigned warp_sum[32];
-    __shared__ unsigned carry;
-    __shared__ unsigned long long s_total, s_max;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; s_total = 0; s_max = 0; }
-    __syncthreads();
-    for (int base = 0; base < nb; base += 1024) {
-        const int idx = base + tid;
-        const unsigned v = idx < nb ? hist[idx] : 0u;
-        unsigned inc = v;
+    unsigned carry = 0;                                            // same value in every thread
+    for (int base = 0; base < nb; base += 4096) {
+        const int idx = base + 4 * tid;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (idx + 3 < nb) v = *reinterpret_cast<const uint4 *>(hist + idx);
+        else {
+            if (idx < nb) v.x = hist[idx];
+            if (idx + 1 < nb) v.y = hist[idx + 1];
+            if (idx + 2 < nb) v.z = hist[idx + 2];
+        }
+        const unsigned mine = v.x + v.y + v.z + v.w;
+        unsigned inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned t = __shfl_up_sync(kFull, inc, d);
             if (lane >= d) inc += t;
         }
+        __syncthreads();                                           // warp_sum of the previous round is consumed
         if (lane == 31) warp_sum[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            unsigned w = warp_sum[lane];
+        unsigned w = warp_sum[lane], wi = w;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned t = __shfl_up_sync(kFull, w, d);
-                if (lane >= d) w += t;
-            }
-            warp_sum[lane] = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, wi, d);
+            if (lane >= d) wi += t;
         }
-        __syncthreads();
-        const unsigned before = carry + (warp > 0 ? warp_sum[warp - 1] : 0u) + inc - v;
+        const unsigned warps_before = __shfl_sync(kFull, wi - w, warp);       // exclusive prefix of this warp's total
+        const unsigned round_total = __shfl_sync(kFull, wi, 31);
+        unsigned before = carry + warps_before + inc - mine;
         if (idx < nb) start[idx] = before;
-        __syncthreads();
-        if (tid == 1023) carry = before + v;
-        __syncthreads();
+        before += v.x; if (idx + 1 < nb) start[idx + 1] = before;
+        before += v.y; if (idx + 2 < nb) start[idx + 2] = before;
+        before += v.z; if (idx + 3 < nb) start[idx + 3] = before;
+        carry += round_total;
     }
-    unsigned long long tot = 0, mx = 0;
-    for (int f = tid; f < n_frames; f += 1024) {
-        const unsigned long long c = fcount[f];
-        tot += c;
-        mx = c > mx ? c : mx;
-    }
-    atomicAdd(&s_total, tot);
-    atomicMax(&s_max, mx);
-    __syncthreads();
     if (tid == 0) {
         start[nb] = carry;
-        stats->records_total = s_total;
-        stats->records_max_per_frame = s_max;
-        stats->overflow = s_max > (unsigned long long)cap ? 1u : 0u;
+        const unsigned long long total = *pool_count;
+        stats->records_total = total;
+        stats->records_max_per_frame = n_frames > 0 ? (total + n_frames - 1) / n_frames : 0;    // mean per frame: what a rerun must provision
+        stats->overflow = total > (unsigned long long)pool_cap ? 1u : 0u;
     }
 }
 
-__global__ void __launch_bounds__(256) record_scatter_kernel(const uint4 *__restrict__ unsorted, const unsigned *__restrict__ fcount,
-                                                            const unsigned *__restrict__ start, long long cap, long long sorted_cap,
+// pool (arrival order) -> sorted (bucket order).  A record's place inside its bucket is taken from
+// the bucket's count, counted down; runs of equal buckets (records of one warp) share one atomic.
+__global__ void __launch_bounds__(256) record_scatter_kernel(const uint2 *__restrict__ pool, const unsigned *__restrict__ pool_count, long long pool_cap,
+                                                            const unsigned *__restrict__ start, unsigned *__restrict__ hist, long long sorted_cap,
                                                             unsigned *__restrict__ sorted) {
-    const int f = blockIdx.y;
-    const long long n = min((long long)fcount[f], cap);
-    const uint4 *src = unsorted + (size_t)f * cap;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const uint4 r = src[i];
-        const long long pos = (long long)start[r.x] + r.y;
-        if (pos < sorted_cap) sorted[pos] = r.z;
+    const long long n = min((long long)*pool_count, pool_cap);
+    const int lane = threadIdx.x & 31;
+    for (long long i0 = (long long)blockIdx.x * 256; i0 < n; i0 += (long long)gridDim.x * 256) {
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n;
+        uint2 r = make_uint2(0u, 0u);
+        if (live) r = pool[i];
+        const unsigned mask = __ballot_sync(kFull, live);
+        if (mask == 0) continue;
+        const int leader = __ffs(mask) - 1;
+        const unsigned lead_bucket = __shfl_sync(kFull, r.x, leader);
+        const bool uniform = __ballot_sync(kFull, live && r.x == lead_bucket) == mask;
+        unsigned rank = 0;
+        if (uniform) {
+            if (lane == leader) rank = atomicSub(&hist[lead_bucket], (unsigned)__popc(mask));
+            rank = __shfl_sync(kFull, rank, leader) - 1u - __popc(mask & ((1u << lane) - 1u));
+        } else if (live) {
+            rank = atomicSub(&hist[r.x], 1u) - 1u;
+        }
+        if (live) {
+            const long long pos = (long long)start[r.x] + rank;
+            if (pos < sorted_cap) sorted[pos] = r.y;
+        }
     }
 }
 
@@ -681,8 +717,8 @@ struct ClipPlan {
     int n_buckets;
     size_t raster_smem;
     // workspace offsets
-    size_t off_zero, zero_bytes;     // region memset to 0 each call: work counter | fcount | hist
-    size_t off_counter, off_fcount, off_hist, off_start, off_stats, off_w2c64, off_lut, off_unsorted, off_sorted, off_plane;
+    size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
+    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane;
     size_t total;
 };
 
@@ -690,12 +726,14 @@ constexpr int kRasterCtasPerSm = 4;
 constexpr int kDefaultBandRows = 16;
 template <bool BINNED>
 void launch_geometry(bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
-    if (f32) {
-        if (debug) clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true><<<grid, kGeoThreads, 0, s>>>(a, cams);
-        else clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false><<<grid, kGeoThreads, 0, s>>>(a, cams);
+    if (f32 && !debug && a.n_cams == 6) {          // the production shape: six cameras, float32 vertices
+        clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6><<<grid, kGeoThreads, 0, s>>>(a, cams);
+    } else if (f32) {
+        if (debug) clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
+        else clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
     } else {
-        if (debug) clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true><<<grid, kGeoThreads, 0, s>>>(a, cams);
-        else clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false><<<grid, kGeoThreads, 0, s>>>(a, cams);
+        if (debug) clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
+        else clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
     }
 }
 
@@ -763,11 +801,10 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         p.off_zero = off;
         p.off_counter = take(256);
-        p.off_fcount = take(sizeof(unsigned) * (size_t)std::max(d->n_frames, 1));
         p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));
         p.zero_bytes = off - p.off_zero;
         p.off_start = take(sizeof(unsigned) * ((size_t)nb + 1));
-        p.off_unsorted = take(sizeof(uint4) * (size_t)d->n_frames * cap);
+        p.off_pool = take(sizeof(uint2) * (size_t)d->n_frames * cap);
         p.off_sorted = take(sizeof(unsigned) * (size_t)d->n_frames * cap);
     }
     p.total = std::max<size_t>(off, 256);
@@ -862,11 +899,11 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     }
 
     // BINNED
-    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.cap = p.cap;
+    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.pool_cap = (long long)d->n_frames * p.cap;
     a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
-    a.fcount = reinterpret_cast<unsigned *>(ws + p.off_fcount);
+    a.pool_count = reinterpret_cast<unsigned *>(ws + p.off_counter) + 1;      // word 0 of the counter block is spare
     a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
-    a.unsorted = reinterpret_cast<uint4 *>(ws + p.off_unsorted);
+    a.pool = reinterpret_cast<uint2 *>(ws + p.off_pool);
     unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
     unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
     CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
@@ -876,13 +913,13 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_LAUNCHED(ctx);
     }
     CAMA_CUDA_TRY(mark(2));
-    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.fcount, d->n_frames, p.cap, stats);
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats);
     CAMA_LAUNCHED(ctx);
-    {
-        const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((p.cap + 255) / 256, 64));
-        record_scatter_kernel<<<dim3(gx, (unsigned)d->n_frames), 256, 0, s>>>(a.unsorted, a.fcount, start, p.cap, (long long)d->n_frames * p.cap, sorted);
-        CAMA_LAUNCHED(ctx);
+    {   // one record per thread when the pool is full; CTAs past the records appended exit at once
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + 255) / 256, 1 << 20));
+        record_scatter_kernel<<<grid, 256, 0, s>>>(a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted);
     }
+    CAMA_LAUNCHED(ctx);
     CAMA_CUDA_TRY(mark(3));
     RasterArgs r{};
     r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;

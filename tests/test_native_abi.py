@@ -50,7 +50,7 @@ def test_descriptor_layout_and_workspace_query():
     need = ctypes.c_size_t()
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     binned = need.value
-    assert 40 * 100000 * 20 <= binned < 40 * 100000 * 20 + (1 << 22)
+    assert 40 * 100000 * 12 <= binned < 40 * 100000 * 12 + (1 << 22)      # 8-byte pool + 4-byte sorted records
     d.mode = N.CLIP_PLANE
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     assert need.value >= 40 * 6 * 540 * 960 * 4
