@@ -364,31 +364,44 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
 
 // pool (arrival order) -> sorted (bucket order).  A record's place inside its bucket is taken from
 // the bucket's count, counted down; runs of equal buckets (records of one warp) share one atomic.
+// Four independent records per thread keep four load -> atomic -> store chains in flight.
+constexpr int kScatterPerThread = 4;
 __global__ void __launch_bounds__(256) record_scatter_kernel(const uint2 *__restrict__ pool, const unsigned *__restrict__ pool_count, long long pool_cap,
                                                             const unsigned *__restrict__ start, unsigned *__restrict__ hist, long long sorted_cap,
                                                             unsigned *__restrict__ sorted) {
     const long long n = min((long long)*pool_count, pool_cap);
     const int lane = threadIdx.x & 31;
-    for (long long i0 = (long long)blockIdx.x * 256; i0 < n; i0 += (long long)gridDim.x * 256) {
-        const long long i = i0 + threadIdx.x;
-        const bool live = i < n;
-        uint2 r = make_uint2(0u, 0u);
-        if (live) r = pool[i];
-        const unsigned mask = __ballot_sync(kFull, live);
-        if (mask == 0) continue;
-        const int leader = __ffs(mask) - 1;
-        const unsigned lead_bucket = __shfl_sync(kFull, r.x, leader);
-        const bool uniform = __ballot_sync(kFull, live && r.x == lead_bucket) == mask;
-        unsigned rank = 0;
-        if (uniform) {
-            if (lane == leader) rank = atomicSub(&hist[lead_bucket], (unsigned)__popc(mask));
-            rank = __shfl_sync(kFull, rank, leader) - 1u - __popc(mask & ((1u << lane) - 1u));
-        } else if (live) {
-            rank = atomicSub(&hist[r.x], 1u) - 1u;
+    const long long tile = 256 * kScatterPerThread;
+    for (long long i0 = (long long)blockIdx.x * tile; i0 < n; i0 += (long long)gridDim.x * tile) {
+        uint2 r[kScatterPerThread];
+        bool live[kScatterPerThread];
+#pragma unroll
+        for (int k = 0; k < kScatterPerThread; ++k) {
+            const long long i = i0 + k * 256 + threadIdx.x;
+            live[k] = i < n;
+            r[k] = live[k] ? pool[i] : make_uint2(0u, 0u);
         }
-        if (live) {
-            const long long pos = (long long)start[r.x] + rank;
-            if (pos < sorted_cap) sorted[pos] = r.y;
+        // records of one geometry warp sit together, so a window of 32 holds a handful of runs:
+        // one atomic per distinct bucket (match.any groups the lanes), all four windows issued before any result is used
+        unsigned peers[kScatterPerThread], first[kScatterPerThread];
+#pragma unroll
+        for (int k = 0; k < kScatterPerThread; ++k) {
+            const unsigned mask = __ballot_sync(kFull, live[k]);
+            peers[k] = 0u; first[k] = 0u;
+            if (live[k]) {
+                peers[k] = __match_any_sync(mask, r[k].x);
+                if (lane == __ffs(peers[k]) - 1) first[k] = atomicSub(&hist[r[k].x], (unsigned)__popc(peers[k]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kScatterPerThread; ++k) {
+            const unsigned mask = __ballot_sync(kFull, live[k]);
+            if (live[k]) {
+                const unsigned got = __shfl_sync(mask, first[k], __ffs(peers[k]) - 1);
+                const unsigned place = got - 1u - (unsigned)__popc(peers[k] & ((1u << lane) - 1u));
+                const long long pos = (long long)start[r[k].x] + place;
+                if (pos < sorted_cap) sorted[pos] = r[k].y;
+            }
         }
     }
 }
@@ -916,7 +929,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats);
     CAMA_LAUNCHED(ctx);
     {   // one record per thread when the pool is full; CTAs past the records appended exit at once
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + 255) / 256, 1 << 20));
+        const long long tile = 256 * kScatterPerThread;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, 1 << 20));
         record_scatter_kernel<<<grid, 256, 0, s>>>(a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted);
     }
     CAMA_LAUNCHED(ctx);

@@ -37,7 +37,7 @@ def test_sass_is_sm100a_with_bulk_copy_and_fp64():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", B.ensure_built()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("DFMA", "UBLKCP", "VIMNMX3.U16x2", "ATOMS.CAS", "MUFU.RCP"):
+    for mnemonic in ("DFMA", "UBLKCP", "VIMNMX3.U16x2", "ATOMS.CAS", "MUFU.RCP", "MATCH.ANY"):
         assert mnemonic in sass, mnemonic
 
 
