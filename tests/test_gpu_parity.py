@@ -415,6 +415,17 @@ def test_frame_sharding_is_exact(rt, config2_clip):
     assert bool((again == whole).all())
 
 
+def test_render_sharded_single_process(rt, config2_clip):
+    """cama_b200.shard with no process group = the whole clip; the multi-rank path is covered by
+    tests/test_shard_gloo.py (CPU) and tools/multi_gpu_check.py (gpurun --gpus N)."""
+    from cama_b200 import shard
+    from cama_b200.batched import Reproject
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    idx, frames = shard.render_sharded(rp, "nuscenes")
+    assert idx == list(range(1, 41))
+    assert bool((frames == rp.render_device("nuscenes")).all())
+
+
 def test_cama_dense_labels_vs_oracle(rt, tmp_path):
     """CAMA-label branch (0.1 px densify, BEV height lookup, N ~ 1.0 M vertices), 4 frames."""
     from cama_b200.batched import Reproject

@@ -1,0 +1,67 @@
+"""Frame sharding + the all-gather of rendered frames, world size 2 and 3, gloo on CPU.
+
+The render itself needs a GPU (tests/test_gpu_parity.py::test_frame_sharding_is_exact proves that
+blocks rendered separately equal the whole clip); here the host-side partition and the collective
+are exercised with stand-in frames."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cama_b200 import shard
+
+
+def test_frame_block_partition():
+    for n in (0, 1, 5, 39, 40, 41, 320):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard.frame_block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))          # contiguous, ordered
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) == shard.block_size(n, world) and all(s >= 0 for s in sizes)
+    with pytest.raises(ValueError):
+        shard.frame_block(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_frames, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        whole = torch.from_numpy(rng.integers(0, 256, size=(n_frames, 2, 6, 8, 3), dtype=np.uint8))   # every rank: same "clip"
+        lo, hi = shard.frame_block(n_frames, rank, world)
+        got = shard.gather_frames(whole[lo:hi].clone(), n_frames)
+        ok = bool((got == whole).all()) and tuple(got.shape) == tuple(whole.shape)
+        try:                                       # a block of the wrong size is refused before any communication
+            shard.gather_frames(whole[lo:hi + 1 if hi < n_frames else hi - 1].clone(), n_frames)
+            ok = False
+        except ValueError:
+            pass
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 5), (2, 40), (3, 7), (3, 2)])
+def test_gather_frames_gloo(world, n_frames):
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        results = manager.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, results)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert dict(results) == {r: True for r in range(world)}

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Multi-GPU parity (run under torchrun on a box with N GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+
+Every rank renders its frame block of the same synthetic config-2 clip, the blocks are all-gathered
+over NCCL, and every rank checks the gathered clip bit for bit against its own single-GPU render.
+"""
+import os
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from cama_b200 import shard, synth
+from cama_b200.batched import Reproject
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    with tempfile.TemporaryDirectory() as root:
+        spec = synth.config2_spec(n_frames=37)            # not a multiple of the world size: padded last block
+        spec.write_cama = False
+        clip = synth.write_clip(spec, root)
+        rp = Reproject(synth.CAMA_CONFIGS, clip, device=local)
+        idx, gathered = shard.render_sharded(rp, "nuscenes", gather=True)
+        whole = rp.render_device("nuscenes")
+        ok = len(idx) == 37 and bool((gathered == whole).all())
+        lo, hi = shard.frame_block(37, rank, world)
+        idx_local, block = shard.render_sharded(rp, "nuscenes", gather=False)
+        ok = ok and idx_local == idx[lo:hi] and bool((block == whole[lo:hi]).all())
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"multi_gpu_check world={world}: {'OK' if int(flag.item()) else 'MISMATCH'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
