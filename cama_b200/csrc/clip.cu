@@ -125,18 +125,19 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
     return vis;
 }
 
-// Records are staged in shared memory and flushed to the global pool a few thousand at a time, so
+// Records are staged in shared memory, per warp, and flushed to the global pool >= 128 at a time, so
 // the only global atomic whose result is waited for is one reservation per flush; the per-bucket
-// counts are fire-and-forget reductions.  (A version that reserved a pool slot and a bucket rank
-// with returning atomics per warp spent a quarter of its time waiting for them.)
+// counts are fire-and-forget reductions, and no block-level barrier is involved.  (A version that
+// reserved a pool slot and a bucket rank with returning atomics per warp spent a quarter of its
+// time waiting for them; one that staged per CTA spent a third of it in the per-frame barrier.)
 constexpr int kGeoThreads = 256;
-constexpr int kStageFlush = 1024;                                      // flush once this many records are staged ...
-constexpr int kStageCap = kStageFlush + kGeoThreads * 2 * CAMA_MAX_CAMERAS;   // ... so one more frame (<= 2 records per vertex and camera) always fits
+constexpr int kStageFlush = 128;                                       // a warp flushes once this many records are staged ...
+constexpr int kStageCap = kStageFlush + 32 * 2 * CAMA_MAX_CAMERAS;     // ... so one more frame (<= 2 records per vertex and camera) always fits
 
-struct GeoStage {
+struct GeoStage {                          // one per warp
     uint2 rec[kStageCap];
     unsigned count;
-    unsigned base;
+    unsigned pad[3];
 };
 
 __device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, bool pred, unsigned bucket, unsigned payload) {
@@ -146,28 +147,30 @@ __device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, boo
     const int leader = __ffs(mask) - 1;
     const unsigned lead_bucket = __shfl_sync(kFull, bucket, leader);
     const bool uniform = __ballot_sync(kFull, pred && bucket == lead_bucket) == mask;    // lanes = consecutive vertices of a polyline
-    unsigned slot = 0;
-    if (lane == leader) {
-        slot = atomicAdd(&st.count, (unsigned)__popc(mask));
-        if (uniform) atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(mask));            // result unused: a reduction
+    if (uniform) {
+        if (lane == leader) atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(mask));     // result unused: a reduction
+    } else if (pred) {
+        atomicAdd(&a.hist[bucket], 1u);
     }
-    if (!uniform && pred) atomicAdd(&a.hist[bucket], 1u);
-    slot = __shfl_sync(kFull, slot, leader) + __popc(mask & ((1u << lane) - 1u));
+    const unsigned slot = st.count + __popc(mask & ((1u << lane) - 1u));                  // the warp owns its stage: no atomic
     if (pred) st.rec[slot] = make_uint2(bucket, payload);
+    __syncwarp();
+    if (lane == 0) st.count += (unsigned)__popc(mask);
+    __syncwarp();
 }
 
-// CTA-wide: move the staged records to the pool.  Call with all threads, after a barrier that
-// follows the last append.
+// Warp-wide: move the warp's staged records to the pool.
 __device__ __forceinline__ void stage_flush(const ClipArgs &a, GeoStage &st) {
+    const int lane = threadIdx.x & 31;
     const unsigned n = st.count;
-    if (threadIdx.x == 0) st.base = atomicAdd(a.pool_count, n);
-    __syncthreads();
-    const long long base = st.base;
-    for (unsigned i = threadIdx.x; i < n; i += kGeoThreads)
-        if (base + i < a.pool_cap) a.pool[base + i] = st.rec[i];
-    __syncthreads();
-    if (threadIdx.x == 0) st.count = 0;
-    __syncthreads();
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.pool_count, n);
+    const long long b = __shfl_sync(kFull, base, 0);
+    for (unsigned i = lane; i < n; i += 32)
+        if (b + i < a.pool_cap) a.pool[b + i] = st.rec[i];
+    __syncwarp();
+    if (lane == 0) st.count = 0;
+    __syncwarp();
 }
 
 template <bool BINNED, bool DEBUG>
@@ -216,13 +219,15 @@ constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads
 template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
 __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT[kGeoFrames][12];
-    __shared__ GeoStage stage;
+    __shared__ GeoStage stages[kGeoThreads / 32];
     const int tid = threadIdx.x;
+    GeoStage &stage = stages[tid >> 5];
     const long long n_tiles = (a.n_vertices + kGeoThreads - 1) / kGeoThreads;
     const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
     const long long units = n_tiles * n_chunks;
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
-    if (BINNED && tid == 0) stage.count = 0;
+    if (BINNED && (tid & 31) == 0) stage.count = 0;
+    __syncwarp();
     for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
@@ -257,16 +262,10 @@ __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const Cli
                     if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, stage, f, c, vis, vi, ui, v, u, ord, n);
                 }
             }
-            if (BINNED) {
-                // Every warp gets here once per frame.  The counter only grows, and the last warp to arrive
-                // reads its final value, so the OR over all threads is an exact, uniform decision.
-                if (__syncthreads_or(stage.count >= (unsigned)kStageFlush)) stage_flush(a, stage);
-            }
+            if (BINNED && stage.count >= (unsigned)kStageFlush) stage_flush(a, stage);     // (warp-uniform)
         }
     }
-    if (BINNED) {
-        if (__syncthreads_or(stage.count > 0u)) stage_flush(a, stage);
-    }
+    if (BINNED && stage.count > 0u) stage_flush(a, stage);
 }
 
 // ------------------------------------------------------------------------------------------------ PLANE raster
