@@ -356,6 +356,12 @@ def run_b200(args):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None                   # dram bytes of the raster kernel from the committed ncu --set full capture
+        try:
+            with open(os.path.join(REPO, "profiles", "raster_traffic.json")) as fh:
+                traffic = float(json.load(fh)["traffic_bytes"]) * cam_frames / 240.0
+        except (OSError, KeyError, ValueError):
+            pass
         raster_ms = float(np.mean(phases[:, 3]))
         frame_bytes = cam_frames * H * W * 3
         vertex_bytes = F * 12 * res.n_vertices
@@ -382,7 +388,8 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "binned_raster_kernel" if stats["mode"] == 2 else "plane_raster_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic": None, "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": raster_ms,
+                         "traffic": traffic, "traffic_source": "profiles/raster_traffic.json (ncu --set full, config 2, scaled by cam-frames)",
+                         "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": raster_ms,
                          "whole_step": {"algorithmic_bytes": int(frame_bytes + vertex_bytes),
                                         "achieved": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9,
                                         "frac": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},

@@ -738,7 +738,8 @@ constexpr int kRasterCtasPerSm = 4;
 constexpr int kDefaultBandRows = 16;
 template <bool BINNED>
 void launch_geometry(bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
-    if (f32 && !debug && a.n_cams == 6) {          // the production shape: six cameras, float32 vertices
+    static const bool generic_only = getenv("CAMA_GEO_GENERIC") != nullptr;     // experiment knob
+    if (f32 && !debug && a.n_cams == 6 && !generic_only) {          // the production shape: six cameras, float32 vertices
         clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6><<<grid, kGeoThreads, 0, s>>>(a, cams);
     } else if (f32) {
         if (debug) clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
