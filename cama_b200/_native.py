@@ -15,9 +15,11 @@ CAMA_E_INVALID, CAMA_E_CUDA, CAMA_E_WORKSPACE, CAMA_E_CAPACITY, CAMA_E_NODEVICE,
 VERTEX_F32X4, VERTEX_F64X3 = 0, 1
 CLIP_AUTO, CLIP_PLANE, CLIP_BINNED = 0, 1, 2
 MAX_CAMERAS = 8
+OVERLAY_RECORD_BYTES = 32
+OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
 CLIP_PHASES = 4
 PHASE_NAMES = ("prep", "geometry", "sort", "raster")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CamaError(RuntimeError):
@@ -42,6 +44,7 @@ class ClipDesc(Structure):
         ("instance_bgr", c_void_p), ("background", c_void_p), ("frames", c_void_p),
         ("crop_counts", c_void_p), ("visible_counts", c_void_p), ("vu_dense", c_void_p),
         ("record_capacity", c_int64),
+        ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
     ]
 
 
@@ -49,6 +52,7 @@ class ClipStats(Structure):
     _fields_ = [
         ("records_total", c_int64), ("records_max_per_frame", c_int64), ("record_capacity", c_int64),
         ("overflow", c_int32), ("mode", c_int32), ("band_rows", c_int32), ("n_bands", c_int32),
+        ("overlay_records", c_int64),
     ]
 
 
@@ -76,6 +80,7 @@ SIGNATURES = {
     "cama_clip_workspace_bytes": (c_int, [POINTER(ClipDesc), POINTER(c_size_t)]),
     "cama_clip_render": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_size_t, c_void_p]),
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),
+    "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int]),
 }
 
 _LIB = None

@@ -71,12 +71,13 @@ class ClipRenderer:
         self.height, self.width = int(height), int(width)
         self.crop_box = [float(v) for v in crop_box]
         self.capacity = {}            # (resident id, n_frames) -> records per frame that were enough
+        self.overlay_capacity = {}    # (resident id, n_frames) -> overlay records that were enough
         self.last_stats = None
 
     def resident(self, instances):
         return _Resident(self.rt, instances)
 
-    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug):
+    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None):
         d = N.ClipDesc()
         d.struct_bytes = ctypes.sizeof(N.ClipDesc)
         d.mode = _MODES[mode] if isinstance(mode, str) else int(mode)
@@ -92,11 +93,16 @@ class ClipRenderer:
         d.crop_box = (ctypes.c_double * 6)(*self.crop_box)
         d.instance_bgr = res.bgr.data_ptr() if res.n_instances else None
         d.background = background.data_ptr() if background is not None else None
-        d.frames = frames.data_ptr() if n_frames else None
+        d.frames = frames.data_ptr() if n_frames and frames is not None else None
         d.crop_counts = debug["crop_counts"].data_ptr() if debug else None
         d.visible_counts = debug["visible_counts"].data_ptr() if debug else None
         d.vu_dense = debug["vu_dense"].data_ptr() if debug and debug.get("vu_dense") is not None else None
         d.record_capacity = int(capacity)
+        if overlay is not None:
+            records, count = overlay
+            d.overlay_records = records.data_ptr()
+            d.overlay_count = count.data_ptr()
+            d.overlay_capacity = int(records.shape[0])
         return d
 
     def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False):
@@ -148,6 +154,48 @@ class ClipRenderer:
         return (out, dbg) if debug else out
 
 
+    def render_overlay(self, res, w2c_dev, mode="auto"):
+        """Sparse output of one clip: the lit 8-pixel chunks instead of dense frames.
+
+        -> (records: torch int32 [capacity, 8] on the device (cama_overlay_record), n_records)
+        Synchronises (the record count is read back); reruns with larger pools on overflow.
+        """
+        import torch
+        rt = self.rt
+        n_frames = int(w2c_dev.shape[0])
+        n_chunks = n_frames * self.n_cams * self.height * self.width // 8
+        key = (id(res), n_frames)
+        capacity = self.capacity.get(key, 0)
+        ov_cap = self.overlay_capacity.get(key, max(n_chunks // 8, 1024))
+        for attempt in range(4):
+            records = rt.scratch_tensor("overlay", (ov_cap, 8), torch.int32)
+            count = rt.scratch_tensor("overlay_count", (4,), torch.int32)
+            desc = self._desc(res, w2c_dev, n_frames, None, None, mode, capacity, None, overlay=(records, count))
+            need = ctypes.c_size_t()
+            N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+            ws = rt.scratch("clip", need.value)
+            if n_frames == 0:
+                return records, 0
+            N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
+            stats = N.ClipStats()
+            code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
+            self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
+            retry = False
+            if code == N.CAMA_E_CAPACITY:
+                capacity = int(stats.records_max_per_frame * 1.1) + 1024
+                self.capacity[key] = capacity
+                retry = True
+            else:
+                N.check(code)
+            if stats.overlay_records > ov_cap:
+                ov_cap = int(stats.overlay_records * 1.2) + 1024
+                self.overlay_capacity[key] = ov_cap
+                retry = True
+            if not retry:
+                return records, int(stats.overlay_records)
+        raise N.CamaError(N.CAMA_E_CAPACITY, "record pools kept overflowing")
+
+
 class Reproject:
     """Batched drop-in for the frame loop: ``Reproject(configs, clip_path)(dataset)``."""
 
@@ -164,6 +212,11 @@ class Reproject:
         self.rt = self.renderer.rt
         self._resident = {}
         self._pinned = {}
+        self._host_frames = None      # sparse transfer: the host frames of the last blank-background call ...
+        self._ov_prev = None          # ... and the records painted into them (blanked before the next paint)
+        self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
+        self._ov_flip = 0
+        self.last_transfer = None
 
     def resident(self, dataset):
         if dataset not in self._resident:
@@ -185,11 +238,59 @@ class Reproject:
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(self.rt.device)
         return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check)
 
-    def __call__(self, dataset, backgrounds=None, mode="auto"):
-        """-> (image_idx list, uint8 numpy [F',C,H,W,3]); ``backgrounds`` (same shape, host) are
-        composited under the overlay exactly like drawing in place on the camera images."""
+    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse"):
+        """-> (image_idx list, uint8 numpy [F',C,H,W,3] in host memory).
+
+        ``backgrounds`` (host uint8 array of that shape) are drawn on **in place**, exactly like the
+        reference draws on the camera images (cama/reproject.py:246-257), and returned.  Without
+        them the frames are black outside the overlay.
+
+        transfer="sparse" (default): the GPU returns only the lit 8-pixel chunks (about a tenth of the
+        dense bytes over PCIe) and libcama_b200's host routine writes them into the host frames;
+        transfer="dense": the whole uint8 frames are rendered in HBM and copied back (what a GPU-side
+        consumer of ``render_device`` gets).  Both give identical bytes.
+        """
         import torch
         idx, w2c = self.frame_poses(dataset)
+        if transfer == "dense" or _MODES.get(mode, mode) == N.CLIP_PLANE or not self._sparse_ok():
+            return idx, self._call_dense(dataset, w2c, backgrounds, mode)
+        rt = self.rt
+        shape = (len(idx), self.renderer.n_cams, self.renderer.height, self.renderer.width, 3)
+        w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(rt.device)
+        records, n = self.renderer.render_overlay(self.resident(dataset), w2c_dev, mode=mode)
+        # records -> pinned host memory
+        cur = self._ov_host[self._ov_flip]
+        if cur is None or cur.shape[0] < max(n, 1):
+            cur = torch.empty((max(int(n * 1.25), 4096), 8), dtype=torch.int32, pin_memory=True)
+            self._ov_host[self._ov_flip] = cur
+        if n:
+            cur[:n].copy_(records[:n], non_blocking=True)        # in flight while the host blanks the previous overlay
+        n_chunks = int(np.prod(shape[:4])) // 8
+        if backgrounds is not None:
+            frames = backgrounds
+            assert isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.shape == shape and frames.flags.c_contiguous \
+                and frames.flags.writeable, "backgrounds must be a writeable C-contiguous uint8 array [F',C,H,W,3]"
+        else:
+            frames = self._host_frames
+            if frames is None or frames.shape != shape:
+                frames = self._host_frames = np.zeros(shape, dtype=np.uint8)
+                self._ov_prev = None
+            if self._ov_prev is not None:                    # blank what the previous call painted into this buffer
+                prev, n_prev = self._ov_prev
+                N.check(N.lib().cama_overlay_apply_host(prev.data_ptr(), n_prev, frames.ctypes.data, n_chunks, N.OVERLAY_BLANK_CHUNKS, 0))
+            self._ov_prev = (cur, n)
+            self._ov_flip ^= 1
+        rt.synchronize()
+        op = N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS     # blank frames: unpainted pixels are black anyway
+        N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, frames.ctypes.data, n_chunks, op, 0))
+        self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES, "records": n}
+        return idx, frames
+
+    def _sparse_ok(self):
+        return self.renderer.width % 16 == 0 and self.renderer.width <= 2048
+
+    def _call_dense(self, dataset, w2c, backgrounds, mode):
+        import torch
         bg_dev = None
         if backgrounds is not None:
             bg_dev = torch.from_numpy(np.ascontiguousarray(backgrounds, dtype=np.uint8)).to(self.rt.device)
@@ -200,7 +301,12 @@ class Reproject:
             self._pinned = {tuple(frames.shape): host}
         host.copy_(frames, non_blocking=True)
         self.rt.synchronize()
-        return idx, host.numpy()
+        self.last_transfer = {"mode": "dense", "d2h_bytes": int(frames.numel()), "records": 0}
+        out = host.numpy()
+        if backgrounds is not None and isinstance(backgrounds, np.ndarray) and backgrounds.flags.writeable and backgrounds.shape == out.shape:
+            backgrounds[...] = out                           # in place, like the sparse path and the reference
+            return backgrounds
+        return out
 
     def as_image_dicts(self, frames):
         """[F',C,H,W,3] -> list of {camera_name: HxWx3}: the shape main.py hands to VideoGenerator."""

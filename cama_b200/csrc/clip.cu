@@ -450,7 +450,57 @@ struct RasterArgs {
     const unsigned *lut;
     const uint8_t *bg;
     uint8_t *frames;
+    uint4 *ov_records;                     // MODE 2: sparse output, 2 x uint4 per cama_overlay_record
+    unsigned *ov_count;
+    long long ov_cap;
 };
+
+// Sparse output (MODE 2): lit 8-pixel chunks are staged per warp and appended to the global record
+// list >= kOvFlush at a time (one returning atomic per flush).
+constexpr int kOvFlush = 64;
+constexpr int kOvCap = kOvFlush + 32;
+struct OvStage {
+    uint4 rec[kOvCap][2];
+    unsigned count;
+    unsigned pad[3];
+};
+struct OvSink {
+    OvStage *st;
+    uint4 *records;
+    unsigned *count;
+    long long cap;
+};
+
+__device__ __forceinline__ void ov_flush(const OvSink &o) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n = o.st->count;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(o.count, n);
+    const long long b = __shfl_sync(kFull, base, 0);
+    for (unsigned i = lane; i < 2u * n; i += 32) {
+        const long long pos = b + (i >> 1);
+        if (pos < o.cap) o.records[pos * 2 + (i & 1u)] = o.st->rec[i >> 1][i & 1u];
+    }
+    __syncwarp();
+    if (lane == 0) o.st->count = 0;
+    __syncwarp();
+}
+
+// warp-collective: every lane calls it; lanes with `lit` contribute one record
+__device__ __forceinline__ void ov_append(const OvSink &o, bool lit, unsigned chunk, unsigned mask, const unsigned (&w)[6]) {
+    const unsigned bal = __ballot_sync(kFull, lit);
+    if (bal == 0) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned slot = o.st->count + __popc(bal & ((1u << lane) - 1u));
+    if (lit) {
+        o.st->rec[slot][0] = make_uint4(chunk, mask, w[0], w[1]);
+        o.st->rec[slot][1] = make_uint4(w[2], w[3], w[4], w[5]);
+    }
+    __syncwarp();
+    if (lane == 0) o.st->count += (unsigned)__popc(bal);
+    __syncwarp();
+    if (o.st->count >= (unsigned)kOvFlush) ov_flush(o);
+}
 
 // 8 packed 24-bit values -> the 24 bytes of 8 BGR pixels (6 words), one byte-permute per word
 __device__ __forceinline__ void pack8x24(const unsigned (&c)[8], unsigned (&w)[6]) {
@@ -487,7 +537,20 @@ __device__ __forceinline__ void colour8(const unsigned *__restrict__ lut, const 
 }
 
 template <int MODE>
-__device__ __forceinline__ void store_row(const unsigned *__restrict__ lut, const unsigned (&m)[4], bool lane_on, uint8_t *out_px, const uint8_t *bg_px) {
+__device__ __forceinline__ void store_row(const unsigned *__restrict__ lut, const unsigned (&m)[4], bool lane_on, uint8_t *out_px, const uint8_t *bg_px,
+                                          const OvSink &ov, unsigned chunk) {
+    if (MODE == 2) {                           // sparse output: a record per lit chunk, nothing dense
+        const bool lit = lane_on && (m[0] | m[1] | m[2] | m[3]) != 0u;
+        unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        unsigned mask = 0u;
+        if (lit) {
+            colour8<0>(lut, m, w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mask |= ((m[k] & 0xffffu) ? 1u << (2 * k) : 0u) | ((m[k] >> 16) ? 2u << (2 * k) : 0u);
+        }
+        ov_append(ov, lit, chunk, mask, w);
+        return;
+    }
     if (!lane_on) return;
     unsigned w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
     if (MODE == 1) {
@@ -523,7 +586,8 @@ __device__ __forceinline__ void row_max(const uint4 &A, unsigned L, unsigned R, 
 //   out(y) = max(raw[y-2], h3[y-1], h5[y], h3[y+1], raw[y+2])     (the 13-px L1 ball; h3/h5 = 3/5-wide row max)
 template <int MODE>
 __device__ __forceinline__ void raster_cell(const unsigned short *plane, const unsigned *__restrict__ lut, int W, int xc, bool lane_on,
-                                            int y, bool two, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes) {
+                                            int y, bool two, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes,
+                                            const OvSink &ov, unsigned chunk) {
     const unsigned short *row = plane + (size_t)y * W + xc;
     const bool has_l = xc > 0, has_r = xc + 8 < W;
     uint4 A[6];
@@ -545,13 +609,13 @@ __device__ __forceinline__ void raster_cell(const unsigned short *plane, const u
     m[1] = max3_u16x2(max3_u16x2(A[0].y, t1.y, f2.y), t3.y, A[4].y);
     m[2] = max3_u16x2(max3_u16x2(A[0].z, t1.z, f2.z), t3.z, A[4].z);
     m[3] = max3_u16x2(max3_u16x2(A[0].w, t1.w, f2.w), t3.w, A[4].w);
-    store_row<MODE>(lut, m, lane_on, out_px, bg_px);
+    store_row<MODE>(lut, m, lane_on, out_px, bg_px, ov, chunk);
     if (two) {
         m[0] = max3_u16x2(max3_u16x2(A[1].x, t2.x, f3.x), t4.x, A[5].x);
         m[1] = max3_u16x2(max3_u16x2(A[1].y, t2.y, f3.y), t4.y, A[5].y);
         m[2] = max3_u16x2(max3_u16x2(A[1].z, t2.z, f3.z), t4.z, A[5].z);
         m[3] = max3_u16x2(max3_u16x2(A[1].w, t2.w, f3.w), t4.w, A[5].w);
-        store_row<MODE>(lut, m, lane_on, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr);
+        store_row<MODE>(lut, m, lane_on, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr, ov, chunk + (unsigned)(W >> 3));
     }
 }
 
@@ -574,6 +638,12 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
     unsigned *hits = reinterpret_cast<unsigned *>(smem + plane_bytes);
     unsigned char *zeros = smem + plane_bytes + kHitBytes;
+    OvSink ov{};
+    if (MODE == 2) {                                                     // per-warp staging of sparse records, after the zeros
+        ov.st = reinterpret_cast<OvStage *>(zeros + zero_bytes) + warp;
+        ov.records = a.ov_records; ov.count = a.ov_count; ov.cap = a.ov_cap;
+        if (lane == 0) ov.st->count = 0;
+    }
     const bool inplace = MODE == 1 && a.bg == a.frames;
     const unsigned x_mask = (1u << a.x_bits) - 1u;
     const int n_strips = a.n_strips;
@@ -620,7 +690,9 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         unsigned pre_next[4];
         fetch(nlo, nhi, pre_next);         // (nlo == nhi == 0 past the last item: nothing is loaded)
 
-        if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
+        if (hi <= lo && MODE == 2) {
+            // sparse output: an empty band produces nothing
+        } else if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
             if (tid == 0) {
                 const int y_first = (item % a.n_bands) * a.band_rows;
                 const int rows_out = min(a.band_rows, a.height - y_first);
@@ -638,6 +710,7 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
             const int rows_out = min(a.band_rows, a.height - y_first);
             uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
             const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
+            const unsigned chunk_base = (unsigned)((((size_t)(item / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
             // 1. centres of this bucket -> plane (max ordinal per pixel) + hit masks
 #pragma unroll
             for (int q = 0; q < 4; ++q) scatter(pre[q]);
@@ -671,7 +744,8 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
                     const int xc = min(x0, W - 8);                             // lanes past the edge recompute the last 8 px, store nothing
                     if (lit)
                         raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_row + (size_t)x0 * 3,
-                                          MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes);
+                                          MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes,
+                                          ov, chunk_base + (unsigned)((y * W + x0) >> 3));
                     else if (lane_on) {                                        // out-of-place composite of a dark cell: copy
                         for (int r = 0; r < (two ? 2 : 1); ++r) {
                             const uint2 *b = reinterpret_cast<const uint2 *>(bg_base + (size_t)(y + r) * row_bytes + (size_t)x0 * 3);
@@ -711,8 +785,9 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
 #pragma unroll
         for (int q = 0; q < 4; ++q) pre[q] = pre_next[q];
     }
+    if (MODE == 2 && ov.st->count > 0u) ov_flush(ov);
     // the shared zeros must stay valid until the last bulk stores have read them
-    if (lane == 0) bulk_wait_group_read<0>();
+    if (MODE == 0 && lane == 0) bulk_wait_group_read<0>();
 }
 
 }  // namespace cama
@@ -812,6 +887,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
         p.cap = cap;
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
+        if (d->overlay_records) p.raster_smem += sizeof(OvStage) * kRasterWarps;
         p.off_zero = off;
         p.off_counter = take(256);
         p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));
@@ -845,7 +921,15 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     if (!workspace || workspace_bytes < p.total) return fail(CAMA_E_WORKSPACE, "clip workspace: need %zu bytes, got %zu", p.total, workspace_bytes);
     CAMA_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (d->n_frames == 0) return CAMA_OK;
-    CAMA_REQUIRE(d->frames && d->world2chassis && d->chassis2cam && d->intrinsics, "NULL buffer in desc");
+    CAMA_REQUIRE(d->world2chassis && d->chassis2cam && d->intrinsics, "NULL buffer in desc");
+    CAMA_REQUIRE(d->frames || d->overlay_records, "neither frames nor overlay_records given");
+    if (d->overlay_records) {
+        if (p.mode != CAMA_CLIP_BINNED) return fail(CAMA_E_UNSUPPORTED, "the sparse overlay output needs BINNED mode");
+        CAMA_REQUIRE(!d->background, "the sparse overlay output takes no background (the host composites)");
+        CAMA_REQUIRE(d->overlay_count && d->overlay_capacity > 0, "overlay_count / overlay_capacity missing");
+        CAMA_REQUIRE(((uintptr_t)d->overlay_records & 15) == 0, "overlay_records must be 16-byte aligned");
+        CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width / 8 < (1ll << 32), "clip too large for 32-bit chunk indices");
+    }
     CAMA_REQUIRE(d->n_vertices == 0 || d->vertices, "vertices is NULL");
     CAMA_REQUIRE(d->n_instances == 0 || d->instance_bgr, "instance_bgr is NULL");
     CAMA_REQUIRE(d->vertex_layout != CAMA_VERTEX_F64X3 || d->n_vertices == 0 || d->vertex_instance, "vertex_instance is NULL");
@@ -942,7 +1026,12 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
     r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
-    if (d->background) {
+    if (d->overlay_records) {
+        r.ov_records = reinterpret_cast<uint4 *>(d->overlay_records); r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
+        CAMA_CUDA_TRY(cudaMemsetAsync(d->overlay_count, 0, sizeof(unsigned), s));
+        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+        binned_raster_kernel<2><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+    } else if (d->background) {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
         binned_raster_kernel<1><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
     } else {
@@ -970,6 +1059,13 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->mode = p.mode;
     out->band_rows = p.band_rows;
     out->n_bands = p.n_bands;
+    out->overlay_records = 0;
+    if (d->overlay_records && d->overlay_count) {
+        unsigned n = 0;
+        CAMA_CUDA_TRY(cudaMemcpyAsync(&n, d->overlay_count, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        out->overlay_records = n;
+    }
     if (h.overflow)
         return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", h.records_max_per_frame, p.cap);
     return CAMA_OK;

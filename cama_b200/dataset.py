@@ -106,14 +106,38 @@ class ClipManager:
         the pose is cast to float32 *before* ``np.linalg.inv``.
         """
         pt, stamps = self._trajectory(dataset)
-        out = []
-        for image_idx in range(1, len(stamps)):
-            try:
-                chassis2world = pt.seek_by_timestamp(stamps[image_idx], t_max_diff=0.5, interpolate=True).astype(np.float32)
-            except RuntimeError:
-                continue
-            out.append((image_idx, np.linalg.inv(chassis2world)))
-        return out
+        n = len(stamps)
+        if n <= 1:
+            return []
+        queries = np.asarray(stamps[1:], dtype=np.float64)
+        # Frames whose stamp coincides with a pose stamp (the usual case: the poses come from the same
+        # sync list) take seek_by_timestamp's first branch; resolve all of them with one comparison.
+        # The other frames go through the method itself (interpolation / RuntimeError).
+        pose_stamps = pt.timestamps[:, 0] if pt.timestamps.ndim == 2 else np.asarray(pt.timestamps, dtype=np.float64)
+        hit = np.isclose(pose_stamps[None, :], queries[:, None], rtol=1e-20, atol=1e-9)
+        has_hit = hit.any(axis=1)
+        first_hit = hit.argmax(axis=1)
+        pt._ensure_absolute()
+        absolute = pt.absolute_transform
+        sorted_stamps = bool(np.all(pose_stamps[1:] >= pose_stamps[:-1]))       # (seek_by_timestamp asserts this)
+        kept_idx, kept_pose = [], []
+        for k in range(n - 1):
+            image_idx = k + 1
+            if has_hit[k] and sorted_stamps and len(absolute) == len(pose_stamps):
+                chassis2world = absolute[first_hit[k]]
+            else:
+                try:
+                    chassis2world = pt.seek_by_timestamp(stamps[image_idx], t_max_diff=0.5, interpolate=True)
+                except RuntimeError:
+                    continue
+            kept_idx.append(image_idx)
+            kept_pose.append(chassis2world)
+        if not kept_idx:
+            return []
+        # one batched LAPACK call: np.linalg.inv loops the same float32 gesv over the stack, so every
+        # matrix is bit-identical to inverting it on its own (tests/test_host_golden.py)
+        inverses = np.linalg.inv(np.stack(kept_pose).astype(np.float32))
+        return [(i, inverses[j]) for j, i in enumerate(kept_idx)]
 
     # ------------------------------------------------------------------ the per-frame protocol of main.py
     def yield_frame(self, dataset):

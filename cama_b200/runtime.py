@@ -77,6 +77,15 @@ class Runtime:
             self._scratch[name] = buf
         return buf
 
+    def scratch_tensor(self, name, shape, dtype):
+        """A cached device tensor of at least ``shape`` rows (first dimension may be larger)."""
+        torch = _torch()
+        buf = self._scratch.get(name)
+        if buf is None or buf.dtype != dtype or tuple(buf.shape[1:]) != tuple(shape[1:]) or buf.shape[0] < shape[0]:
+            buf = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._scratch[name] = buf
+        return buf
+
     def to_device(self, array, dtype=None):
         torch = _torch()
         arr = np.ascontiguousarray(array, dtype=dtype)

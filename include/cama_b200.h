@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CAMA_ABI_VERSION 1
+#define CAMA_ABI_VERSION 2
 #define CAMA_MAX_CAMERAS 8
 
 typedef enum cama_status {
@@ -130,6 +130,17 @@ enum { CAMA_CLIP_AUTO = 0,      /* BINNED when the shape allows it, else PLANE *
        CAMA_CLIP_PLANE = 1,     /* global uint32 centre-id plane + per-pixel dilation (simple, any shape) */
        CAMA_CLIP_BINNED = 2 };  /* band-binned centre records + shared-memory plane + bulk-store raster */
 
+/* One lit 8-pixel chunk of the rendered clip (sparse "overlay" output, BINNED mode only): the chunk
+ * covers pixels 8*chunk .. 8*chunk+7 of the flattened [n_frames, n_cams, H, W] pixel array (W % 8 == 0,
+ * so a chunk never straddles a row), bit k of mask = pixel k is painted, bgr = the 24 output bytes
+ * (painted pixels: instance colour; the others: zero).  Every lit chunk appears exactly once, in no
+ * particular order.  cama_overlay_apply_host() draws such records into host frames. */
+typedef struct cama_overlay_record {
+    uint32_t chunk;
+    uint32_t mask;
+    uint8_t bgr[24];
+} cama_overlay_record;
+
 typedef struct cama_clip_desc {
     uint32_t struct_bytes;          /* sizeof(cama_clip_desc), ABI guard */
     int32_t mode;                   /* CAMA_CLIP_* */
@@ -150,6 +161,12 @@ typedef struct cama_clip_desc {
     int32_t *visible_counts;        /* device int32 [n_frames,n_cams,n_instances] or NULL; caller zero-fills */
     double *vu_dense;               /* device float64 [n_frames,n_cams,n_vertices,2] or NULL; NaN where not visible */
     int64_t record_capacity;        /* BINNED: centre records per frame the workspace is sized for; 0 = default */
+    /* Sparse output (BINNED mode, background must be NULL): when overlay_records != NULL the lit chunks are
+     * appended there and `frames` is not written (and may be NULL).  What a host consumer needs crosses PCIe
+     * as ~10 % of the dense bytes; the dense frames never exist. */
+    cama_overlay_record *overlay_records; /* device [overlay_capacity] or NULL */
+    uint32_t *overlay_count;        /* device [1]: records appended (may exceed the capacity: the excess was dropped) */
+    int64_t overlay_capacity;
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -160,6 +177,7 @@ typedef struct cama_clip_stats {
     int32_t mode;                   /* mode actually used (CAMA_CLIP_PLANE / CAMA_CLIP_BINNED) */
     int32_t band_rows;              /* BINNED: output rows per band */
     int32_t n_bands;
+    int64_t overlay_records;        /* lit chunks produced (sparse output), 0 otherwise */
 } cama_clip_stats;
 
 /* Workspace (device bytes) a cama_clip_render call with this descriptor needs. */
@@ -171,6 +189,18 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *desc, void *workspace,
  * workspace.  Returns CAMA_E_CAPACITY when the record pool overflowed. */
 int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *desc, const void *workspace, void *stream,
                          cama_clip_stats *stats);
+
+/* ---- host side of the sparse output ------------------------------------------------------------ */
+
+/* Applies `n` overlay records to host frames uint8 [n_frames,n_cams,H,W,3]; records whose chunk is
+ * >= n_chunks are ignored.  DRAW is the in-place draw of CameraManager.render_maps
+ * (cama/reproject.py:246-257) for pixels whose colour the GPU has already decided: only painted pixels
+ * are written.  BLANK sets them to 0,0,0.  The *_CHUNKS variants write all 24 bytes of each chunk: valid
+ * when the unpainted pixels of the frames are black anyway (frames without a background), and cheaper.
+ * Only moves bytes (n_threads <= 0: all cores). */
+enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS = 2, CAMA_OVERLAY_BLANK_CHUNKS = 3 };
+int cama_overlay_apply_host(const cama_overlay_record *records, int64_t n, uint8_t *frames, int64_t n_chunks,
+                            int op, int n_threads);
 
 #ifdef __cplusplus
 }

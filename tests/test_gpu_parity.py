@@ -426,6 +426,59 @@ def test_render_sharded_single_process(rt, config2_clip):
     assert bool((frames == rp.render_device("nuscenes")).all())
 
 
+def test_sparse_transfer_equals_dense(rt, config2_clip, clip_root):
+    """Reproject.__call__ default (sparse overlay records over PCIe + host draw) gives the same bytes
+    as the dense render, on blank frames (buffer reused across calls: previous overlay blanked), on
+    host backgrounds drawn in place, and on the golden clip."""
+    from cama_b200.batched import Reproject
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    idx, sparse = rp("nuscenes")
+    assert rp.last_transfer["mode"] == "sparse" and 0 < rp.last_transfer["d2h_bytes"] < sparse.size // 5
+    dense = rp("nuscenes", transfer="dense")[1].copy()           # (the dense path returns its reused pinned buffer)
+    assert rp.last_transfer["mode"] == "dense"
+    assert np.array_equal(sparse, dense)
+    # second call with other poses into the same host buffer: the old overlay must be gone
+    _, w2c = rp.frame_poses("nuscenes")
+    rp.cm._trajectory_cache["nuscenes"][0].transform(np.array([[1, 0, 0, 0.5], [0, 1, 0, -0.25], [0, 0, 1, 0], [0, 0, 0, 1.0]]))
+    _, sparse2 = rp("nuscenes")
+    dense2 = rp("nuscenes", transfer="dense")[1].copy()
+    assert sparse2 is sparse and np.array_equal(sparse2, dense2) and not np.array_equal(dense2, dense)
+    # host backgrounds: drawn in place like the reference draws on the camera images
+    rng = np.random.default_rng(11)
+    bg = rng.integers(0, 256, size=dense.shape, dtype=np.uint8)
+    keep = bg.copy()
+    _, out = rp("nuscenes", backgrounds=bg)
+    assert out is bg
+    want = rp("nuscenes", backgrounds=keep.copy(), transfer="dense")[1]
+    assert np.array_equal(bg, want) and not np.array_equal(bg, keep)
+    lit = (dense2 != 0).any(-1)
+    assert np.array_equal(bg[~lit], keep[~lit])
+    # golden clip through the sparse path
+    g = load_golden("golden_clip_cama_exact.npz")
+    clip = synth.write_clip(synth.tiny_spec(name="tiny_sparse"), clip_root)
+    idx, frames = Reproject(synth.CAMA_CONFIGS, clip, device=0)("cama")
+    assert idx == list(g["frame_idx"]) and np.array_equal(frames, g["frames"])
+
+
+def test_overlay_records_are_unique_chunks(rt):
+    """Raw C-ABI sparse output: every lit chunk exactly once, masks/colours consistent with the dense frames."""
+    g = load_golden("golden_clip_nuscenes_slerp.npz")
+    r = renderer_for(g)
+    res = r.resident(golden_instances(g))
+    records, n = r.render_overlay(res, to_dev(g["world2chassis"].reshape(-1, 16)))
+    rec = records[:n].cpu().numpy().view(np.uint8).reshape(n, 32)
+    chunk = rec[:, :4].copy().view("<u4")[:, 0]
+    mask = rec[:, 4:8].copy().view("<u4")[:, 0]
+    assert len(np.unique(chunk)) == n and mask.max() <= 0xFF and mask.min() >= 1
+    dense = g["frames"].reshape(-1, 8, 3)
+    lit_chunks = np.flatnonzero(dense.reshape(len(dense), -1).any(1))
+    assert set(lit_chunks) <= set(chunk.tolist())              # (a chunk painted pure black would be a record but not lit)
+    bits = (mask[:, None] >> np.arange(8)) & 1
+    bgr = rec[:, 8:].reshape(n, 8, 3)
+    assert np.array_equal(bgr * bits[:, :, None], dense[chunk] * bits[:, :, None])
+    assert not (bgr * (1 - bits)[:, :, None]).any() and not (dense[chunk] * (1 - bits)[:, :, None]).any()
+
+
 def test_cama_dense_labels_vs_oracle(rt, tmp_path):
     """CAMA-label branch (0.1 px densify, BEV height lookup, N ~ 1.0 M vertices), 4 frames."""
     from cama_b200.batched import Reproject
