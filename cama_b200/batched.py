@@ -238,7 +238,16 @@ class Reproject:
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(self.rt.device)
         return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check)
 
-    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse"):
+    def mosaic_tiles(self):
+        """tile index (row-major in the 2x3 grid of cama/tools.py:22-25) of every camera, or None when the
+        camera list is not the six mosaic cameras."""
+        from .tools import MOSAIC_ROWS
+        order = [name for row in MOSAIC_ROWS for name in row]
+        if sorted(order) != sorted(self.camera_names):
+            return None
+        return np.array([order.index(name) for name in self.camera_names], dtype=np.int32)
+
+    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse", layout="frames"):
         """-> (image_idx list, uint8 numpy [F',C,H,W,3] in host memory).
 
         ``backgrounds`` (host uint8 array of that shape) are drawn on **in place**, exactly like the
@@ -252,10 +261,18 @@ class Reproject:
         """
         import torch
         idx, w2c = self.frame_poses(dataset)
+        tiles = None
+        if layout == "mosaic":
+            tiles = self.mosaic_tiles()
+            if tiles is None or transfer == "dense" or not self._sparse_ok():
+                raise ValueError("layout='mosaic' needs the six mosaic cameras and the sparse transfer")
+        elif layout != "frames":
+            raise ValueError(f"unknown layout {layout!r}")
         if transfer == "dense" or _MODES.get(mode, mode) == N.CLIP_PLANE or not self._sparse_ok():
             return idx, self._call_dense(dataset, w2c, backgrounds, mode)
         rt = self.rt
-        shape = (len(idx), self.renderer.n_cams, self.renderer.height, self.renderer.width, 3)
+        H, W, C = self.renderer.height, self.renderer.width, self.renderer.n_cams
+        shape = (len(idx), C, H, W, 3) if tiles is None else (len(idx), 2 * H, 3 * W, 3)
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(rt.device)
         records, n = self.renderer.render_overlay(self.resident(dataset), w2c_dev, mode=mode)
         # records -> pinned host memory
@@ -265,11 +282,19 @@ class Reproject:
             self._ov_host[self._ov_flip] = cur
         if n:
             cur[:n].copy_(records[:n], non_blocking=True)        # in flight while the host blanks the previous overlay
-        n_chunks = int(np.prod(shape[:4])) // 8
+        n_chunks = len(idx) * C * H * W // 8
+
+        def apply(rec, count, op):
+            if tiles is None:
+                N.check(N.lib().cama_overlay_apply_host(rec.data_ptr(), count, frames.ctypes.data, n_chunks, op, 0))
+            else:
+                N.check(N.lib().cama_overlay_apply_host_mosaic(rec.data_ptr(), count, frames.ctypes.data, len(idx), C, H, W, 3,
+                                                               tiles.ctypes.data, op, 0))
+
         if backgrounds is not None:
             frames = backgrounds
             assert isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.shape == shape and frames.flags.c_contiguous \
-                and frames.flags.writeable, "backgrounds must be a writeable C-contiguous uint8 array [F',C,H,W,3]"
+                and frames.flags.writeable, "backgrounds must be a writeable C-contiguous uint8 array [F',C,H,W,3] (or [F',2H,3W,3] for the mosaic)"
         else:
             frames = self._host_frames
             if frames is None or frames.shape != shape:
@@ -277,12 +302,11 @@ class Reproject:
                 self._ov_prev = None
             if self._ov_prev is not None:                    # blank what the previous call painted into this buffer
                 prev, n_prev = self._ov_prev
-                N.check(N.lib().cama_overlay_apply_host(prev.data_ptr(), n_prev, frames.ctypes.data, n_chunks, N.OVERLAY_BLANK_CHUNKS, 0))
+                apply(prev, n_prev, N.OVERLAY_BLANK_CHUNKS)
             self._ov_prev = (cur, n)
             self._ov_flip ^= 1
         rt.synchronize()
-        op = N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS     # blank frames: unpainted pixels are black anyway
-        N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, frames.ctypes.data, n_chunks, op, 0))
+        apply(cur, n, N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS)   # blank frames: unpainted pixels are black anyway
         self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES, "records": n}
         return idx, frames
 

@@ -202,6 +202,13 @@ enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS =
 int cama_overlay_apply_host(const cama_overlay_record *records, int64_t n, uint8_t *frames, int64_t n_chunks,
                             int op, int n_threads);
 
+/* Same, into the camera mosaic that VideoGenerator.concate_image (cama/tools.py:22-25) builds before
+ * encoding: `mosaic` is uint8 [n_frames, rows*H, grid_cols*W, 3] with rows = ceil(n_cams / grid_cols), and
+ * camera c occupies tile tile_of_cam[c] (row-major).  Drawing there makes concate_image a no-op. */
+int cama_overlay_apply_host_mosaic(const cama_overlay_record *records, int64_t n, uint8_t *mosaic, int64_t n_frames,
+                                   int n_cams, int height, int width, int grid_cols, const int32_t *tile_of_cam,
+                                   int op, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -453,6 +453,13 @@ def test_sparse_transfer_equals_dense(rt, config2_clip, clip_root):
     assert np.array_equal(bg, want) and not np.array_equal(bg, keep)
     lit = (dense2 != 0).any(-1)
     assert np.array_equal(bg[~lit], keep[~lit])
+    # N4: straight into the 2x3 mosaic of cama/tools.py:22-25 (what VideoGenerator.add_frame takes)
+    from cama_b200.tools import concate_image
+    _, mosaic = rp("nuscenes", layout="mosaic")
+    assert mosaic.shape == (40, 1080, 2880, 3)
+    dicts = rp.as_image_dicts(dense2)
+    for f in (0, 17, 39):
+        assert np.array_equal(mosaic[f], concate_image(dicts[f]))
     # golden clip through the sparse path
     g = load_golden("golden_clip_cama_exact.npz")
     clip = synth.write_clip(synth.tiny_spec(name="tiny_sparse"), clip_root)

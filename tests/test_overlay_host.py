@@ -60,3 +60,28 @@ def test_apply_matches_numpy_and_erases():
     assert N.lib().cama_overlay_apply_host(recs.ctypes.data, 5, got.ctypes.data, n_chunks, 7, 0) == N.CAMA_E_INVALID
     assert N.lib().cama_overlay_apply_host(None, 5, got.ctypes.data, n_chunks, 0, 0) == N.CAMA_E_INVALID
     N.check(N.lib().cama_overlay_apply_host(None, 0, None, 0, 0, 0))
+
+
+def test_mosaic_layout_matches_concate_image():
+    """Drawing into the 2x3 mosaic == drawing into [F,C,H,W,3] frames and np.concatenate (reference cama/tools.py:22-25)."""
+    from cama_b200.tools import MOSAIC_ROWS, concate_image
+    rng = np.random.default_rng(4)
+    F, C, H, W = 3, 6, 16, 32
+    names = ["camera_rear", "camera_front_left", "camera_front", "camera_front_right", "camera_rear_left", "camera_rear_right"]   # any camera_list order
+    order = [n for row in MOSAIC_ROWS for n in row]
+    tiles = np.array([order.index(n) for n in names], np.int32)
+    n_chunks = F * C * H * W // 8
+    recs = np.zeros(600, REC)
+    recs["chunk"] = rng.permutation(n_chunks)[:600]
+    recs["mask"] = rng.integers(1, 256, 600)
+    recs["bgr"] = rng.integers(0, 256, (600, 24))
+    frames = rng.integers(0, 256, size=(F, C, H, W, 3), dtype=np.uint8)
+    mosaic = np.stack([concate_image({n: frames[f, c] for c, n in enumerate(names)}) for f in range(F)])
+    assert mosaic.shape == (F, 2 * H, 3 * W, 3)
+    for op in (N.OVERLAY_DRAW, N.OVERLAY_BLANK, N.OVERLAY_DRAW_CHUNKS, N.OVERLAY_BLANK_CHUNKS):
+        apply(recs, frames, erase=op)
+        N.check(N.lib().cama_overlay_apply_host_mosaic(recs.ctypes.data, len(recs), mosaic.ctypes.data, F, C, H, W, 3, tiles.ctypes.data, op, 0))
+        want = np.stack([concate_image({n: frames[f, c] for c, n in enumerate(names)}) for f in range(F)])
+        assert np.array_equal(mosaic, want), op
+    bad = tiles.copy(); bad[0] = 9
+    assert N.lib().cama_overlay_apply_host_mosaic(recs.ctypes.data, len(recs), mosaic.ctypes.data, F, C, H, W, 3, bad.ctypes.data, 0, 0) == N.CAMA_E_INVALID
