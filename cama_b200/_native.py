@@ -15,6 +15,7 @@ CAMA_E_INVALID, CAMA_E_CUDA, CAMA_E_WORKSPACE, CAMA_E_CAPACITY, CAMA_E_NODEVICE,
 VERTEX_F32X4, VERTEX_F64X3 = 0, 1
 CLIP_AUTO, CLIP_PLANE, CLIP_BINNED = 0, 1, 2
 MAX_CAMERAS = 8
+TILE_VERTICES = 256
 OVERLAY_RECORD_BYTES = 32
 OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
 CLIP_PHASES = 4
@@ -44,6 +45,7 @@ class ClipDesc(Structure):
         ("instance_bgr", c_void_p), ("background", c_void_p), ("frames", c_void_p),
         ("crop_counts", c_void_p), ("visible_counts", c_void_p), ("vu_dense", c_void_p),
         ("record_capacity", c_int64),
+        ("tile_bounds", c_void_p),
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
     ]
 

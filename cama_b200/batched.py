@@ -47,6 +47,20 @@ def pack_vertices(instances):
     return N.VERTEX_F64X3, np.ascontiguousarray(flat), ordinal, bgr
 
 
+def tile_bounds(xyz):
+    """float64 [ceil(n / TILE_VERTICES), 6]: centre and half-extent of the axis-aligned box of every tile of
+    consecutive vertices (``tile_bounds`` of cama_clip_desc).  Non-finite coordinates make a tile uncullable."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    n = xyz.shape[0]
+    starts = np.arange(0, n, N.TILE_VERTICES)
+    lo = np.minimum.reduceat(xyz, starts, axis=0)
+    hi = np.maximum.reduceat(xyz, starts, axis=0)
+    out = np.concatenate([(lo + hi) / 2, (hi - lo) / 2], axis=1)
+    bad = ~np.isfinite(np.add.reduceat(xyz, starts, axis=0)).all(axis=1) | ~np.isfinite(out).all(axis=1)
+    out[bad] = [0, 0, 0, np.inf, np.inf, np.inf]
+    return np.ascontiguousarray(out)
+
+
 class _Resident:
     """Device copies of what does not change from frame to frame."""
 
@@ -55,6 +69,7 @@ class _Resident:
         self.n_vertices = int(verts.shape[0])
         self.n_instances = len(instances)
         self.vertices = rt.to_device(verts)
+        self.tile_bounds = rt.to_device(tile_bounds(verts[:, :3])) if self.n_vertices else None
         self.ordinal = rt.to_device(ordinal) if ordinal is not None else None
         self.bgr = rt.to_device(bgr)
 
@@ -98,6 +113,7 @@ class ClipRenderer:
         d.visible_counts = debug["visible_counts"].data_ptr() if debug else None
         d.vu_dense = debug["vu_dense"].data_ptr() if debug and debug.get("vu_dense") is not None else None
         d.record_capacity = int(capacity)
+        d.tile_bounds = res.tile_bounds.data_ptr() if getattr(res, "tile_bounds", None) is not None else None
         if overlay is not None:
             records, count = overlay
             d.overlay_records = records.data_ptr()

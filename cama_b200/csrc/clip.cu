@@ -39,6 +39,9 @@ struct ClipArgs {
     const void *vertices;
     const int *vertex_instance;
     const double *w2c64;               // [F,12]
+    const double *tile_bounds;         // [n_tiles,6] centre + half-extent, or nullptr
+    const unsigned long long *worklist; // live units {unit << 8 | frame mask} from geometry_cull_kernel, or nullptr (all units)
+    const unsigned *n_live;
     int *crop_counts;
     int *visible_counts;
     double *vu_dense;
@@ -209,6 +212,47 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, GeoStage &st, int
 }
 
 constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads amortised over them)
+static_assert(kGeoThreads == CAMA_TILE_VERTICES, "tile_bounds are per geometry tile");
+
+// Tile culling: the tile's bounding box, moved to the chassis frame of a frame (centre by the affine
+// map, half-extent by |R|), against the crop box.  Conservative: the slack is ~1e7 times the rounding
+// error of these few operations, and a surviving tile is decided vertex by vertex as before.
+// Non-finite bounds or poses never cull (comparisons with NaN are false).
+__device__ __forceinline__ bool tile_may_survive(const double *__restrict__ b, const double *__restrict__ T, const double *box) {
+    bool out = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double c = T[4 * k] * b[0] + T[4 * k + 1] * b[1] + T[4 * k + 2] * b[2] + T[4 * k + 3];
+        const double e = fabs(T[4 * k]) * b[3] + fabs(T[4 * k + 1]) * b[4] + fabs(T[4 * k + 2]) * b[5];
+        const double slack = 1e-6 + 1e-9 * (fabs(c) + e);
+        out = out || (c - e - slack > box[2 * k + 1]) || (c + e + slack < box[2 * k]);
+    }
+    return !out;
+}
+
+// Large clips (sites): most (tile, 8-frame chunk) units contain nothing near the vehicle.  One thread
+// per unit evaluates the 8 culling tests and appends the live units {unit index, frame mask} to a
+// work list, so that the geometry kernel only ever starts units with something to do.
+__global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__restrict__ tile_bounds, const double *__restrict__ w2c64,
+                                                           long long units, int n_chunks, int n_frames, const __grid_constant__ CamBlock cams,
+                                                           unsigned long long *__restrict__ worklist, unsigned *__restrict__ n_live) {
+    const long long unit = (long long)blockIdx.x * 256 + threadIdx.x;
+    unsigned mask = 0;
+    if (unit < units) {
+        const long long tile = unit / n_chunks;
+        const int f0 = (int)(unit % n_chunks) * kGeoFrames;
+        const int nf = min(kGeoFrames, n_frames - f0);
+        for (int fi = 0; fi < nf; ++fi)
+            if (tile_may_survive(tile_bounds + tile * 6, w2c64 + (size_t)(f0 + fi) * 12, cams.box)) mask |= 1u << fi;
+    }
+    const unsigned live = __ballot_sync(kFull, mask != 0u);
+    if (live == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(live) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(n_live, (unsigned)__popc(live));
+    base = __shfl_sync(kFull, base, leader);
+    if (mask) worklist[base + __popc(live & ((1u << lane) - 1u))] = ((unsigned long long)unit << 8) | mask;
+}
 
 // Work unit = (tile of 256 vertices, chunk of 8 frames).  A thread keeps its vertex in registers and
 // walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).  Lanes hold
@@ -219,6 +263,7 @@ constexpr int kGeoFrames = 8;              // frames per work unit (vertex loads
 template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
 __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT[kGeoFrames][12];
+    __shared__ int s_frame_live[kGeoFrames];
     __shared__ GeoStage stages[kGeoThreads / 32];
     const int tid = threadIdx.x;
     GeoStage &stage = stages[tid >> 5];
@@ -228,18 +273,33 @@ __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const Cli
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
     if (BINNED && (tid & 31) == 0) stage.count = 0;
     __syncwarp();
-    for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const long long n_work = a.worklist ? (long long)*a.n_live : units;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+        long long unit = w;
+        unsigned live_mask = 0xffu;
+        if (a.worklist) {
+            const unsigned long long e = a.worklist[w];
+            unit = (long long)(e >> 8);
+            live_mask = (unsigned)(e & 0xffu);
+        }
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
         const int nf = min(kGeoFrames, a.n_frames - f0);
         __syncthreads();
         if (tid < nf * 12) sT[tid / 12][tid % 12] = a.w2c64[(size_t)f0 * 12 + tid];
         __syncthreads();
+        if (tid < kGeoFrames) {
+            int live = (live_mask >> tid) & 1u;
+            if (live && !a.worklist && a.tile_bounds && tid < nf) live = tile_may_survive(a.tile_bounds + tile * 6, sT[tid], cams.box) ? 1 : 0;
+            s_frame_live[tid] = live;
+        }
+        __syncthreads();
         const long long n = tile * kGeoThreads + tid;
         double vx, vy, vz;
         int ord;
         const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
         for (int fi = 0; fi < nf; ++fi) {
+            if (!s_frame_live[fi]) continue;                   // (uniform over the CTA)
             const int f = f0 + fi;
             const double *T = sT[fi];
             // reference cama/dataset.py:99-105: world -> chassis, then the crop box
@@ -805,7 +865,8 @@ struct ClipPlan {
     size_t raster_smem;
     // workspace offsets
     size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
-    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane;
+    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist;
+    long long geo_units;
     size_t total;
 };
 
@@ -871,6 +932,8 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
     p.off_w2c64 = take(sizeof(double) * 12 * (size_t)std::max(d->n_frames, 1));
     p.off_lut = take(sizeof(unsigned) * ((size_t)d->n_instances + 1));
     p.off_stats = take(sizeof(ClipStatsDev));
+    p.geo_units = ((d->n_vertices + kGeoThreads - 1) / kGeoThreads) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
+    p.off_worklist = take(sizeof(unsigned long long) * (size_t)std::max<long long>(p.geo_units, 1));
     if (mode == CAMA_CLIP_PLANE) {
         p.off_plane = take(sizeof(unsigned) * (size_t)d->n_frames * d->n_cams * H * W);
     } else {
@@ -959,6 +1022,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     a.vertices = d->vertices; a.vertex_instance = d->vertex_instance;
     a.w2c64 = reinterpret_cast<const double *>(ws + p.off_w2c64);
     a.crop_counts = d->crop_counts; a.visible_counts = d->visible_counts; a.vu_dense = d->vu_dense;
+    a.tile_bounds = d->tile_bounds;
     unsigned *lut = reinterpret_cast<unsigned *>(ws + p.off_lut);
     ClipStatsDev *stats = reinterpret_cast<ClipStatsDev *>(ws + p.off_stats);
 
@@ -1006,6 +1070,16 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
+        // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
+        if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
+            unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
+            unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
+            geometry_cull_kernel<<<(unsigned)((units + 255) / 256), 256, 0, s>>>(d->tile_bounds, a.w2c64, units, (d->n_frames + kGeoFrames - 1) / kGeoFrames,
+                                                                                d->n_frames, cams, worklist, n_live);
+            CAMA_LAUNCHED(ctx);
+            a.worklist = worklist;
+            a.n_live = n_live;
+        }
         launch_geometry<true>(f32, debug, geo_grid, s, a, cams);
         CAMA_LAUNCHED(ctx);
     }

@@ -39,6 +39,7 @@ extern "C" {
 
 #define CAMA_ABI_VERSION 2
 #define CAMA_MAX_CAMERAS 8
+#define CAMA_TILE_VERTICES 256
 
 typedef enum cama_status {
     CAMA_OK = 0,
@@ -164,6 +165,10 @@ typedef struct cama_clip_desc {
     /* Sparse output (BINNED mode, background must be NULL): when overlay_records != NULL the lit chunks are
      * appended there and `frames` is not written (and may be NULL).  What a host consumer needs crosses PCIe
      * as ~10 % of the dense bytes; the dense frames never exist. */
+    /* Optional culling aid: for every tile of CAMA_TILE_VERTICES consecutive vertices the centre and
+     * half-extent {cx,cy,cz,ex,ey,ez} of an axis-aligned box containing them.  A (tile, frame) whose
+     * transformed box misses the crop box is skipped as a whole; results are unchanged. */
+    const double *tile_bounds;      /* device float64 [ceil(n_vertices / CAMA_TILE_VERTICES), 6] or NULL */
     cama_overlay_record *overlay_records; /* device [overlay_capacity] or NULL */
     uint32_t *overlay_count;        /* device [1]: records appended (may exceed the capacity: the excess was dropped) */
     int64_t overlay_capacity;

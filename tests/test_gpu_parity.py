@@ -528,6 +528,14 @@ def test_config3_site_properties(rt, tmp_path):
     sample = [0, 1, 77, 160, 250, 319]
     want, _, _ = oracle_c.clip_render(flat, offs, bgr_of(classes), w2c[sample], c2c, K, BOX6, H, W)
     assert np.array_equal(whole[sample].cpu().numpy(), want)
+    # tile culling (tile_bounds) only skips work: without it the frames are the same
+    res = rp.resident("nuscenes")
+    bounds, res.tile_bounds = res.tile_bounds, None
+    try:
+        unculled = rp.render_device("nuscenes", w2c=w2c[40:80])
+    finally:
+        res.tile_bounds = bounds
+    assert bool((unculled == whole[40:80]).all())
     block = rp.render_device("nuscenes", w2c=w2c[100:140], mode="plane")
     assert bool((block == whole[100:140]).all())
     halves = torch.cat([rp.render_device("nuscenes", w2c=w2c[:160]), rp.render_device("nuscenes", w2c=w2c[160:])])
