@@ -57,9 +57,16 @@ struct ClipArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ prep
+// (also clears the per-call counters, so that a clip costs kernel launches only: zero_words 32-bit words at `zero`,
+// the statistics block, the sparse-output counter)
 __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
-                            const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut) {
+                            const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
+                            unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
+                            unsigned *__restrict__ overlay_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
+    if (i < stats_words) stats[i] = 0u;
+    if (i == 0 && overlay_count) *overlay_count = 0u;
     if (i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
     if (i <= n_inst) lut[i] = i == 0 ? 0u
                                       : (unsigned)inst_bgr[3 * (i - 1)] | ((unsigned)inst_bgr[3 * (i - 1) + 1] << 8) |
@@ -1028,11 +1035,15 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
 
     if (d->vu_dense)
         CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
-    CAMA_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(ClipStatsDev), s));
     {
-        const int n = std::max(d->n_frames * 12, d->n_instances + 1);
-        prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
-                                                    d->instance_bgr, d->n_instances, lut);
+        const bool binned = p.mode == CAMA_CLIP_BINNED;
+        const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
+        const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
+        prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
+                                                               d->instance_bgr, d->n_instances, lut,
+                                                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : nullptr, zero_words,
+                                                               reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
+                                                               d->overlay_records ? d->overlay_count : nullptr);
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
@@ -1067,7 +1078,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     a.pool = reinterpret_cast<uint2 *>(ws + p.off_pool);
     unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
     unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
-    CAMA_CUDA_TRY(cudaMemsetAsync(ws + p.off_zero, 0, p.zero_bytes, s));
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
         // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
@@ -1102,7 +1112,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
     if (d->overlay_records) {
         r.ov_records = reinterpret_cast<uint4 *>(d->overlay_records); r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
-        CAMA_CUDA_TRY(cudaMemsetAsync(d->overlay_count, 0, sizeof(unsigned), s));
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
         binned_raster_kernel<2><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
     } else if (d->background) {
