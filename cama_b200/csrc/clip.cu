@@ -381,10 +381,14 @@ struct ClipStatsDev {
 // 4096 buckets per round: one 16-byte load per thread, a warp scan, a scan of the 32 warp totals.
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, int nb,
                                                            const unsigned *__restrict__ pool_count, int n_frames, long long pool_cap,
-                                                           ClipStatsDev *__restrict__ stats) {
+                                                           ClipStatsDev *__restrict__ stats, unsigned *__restrict__ lists /* [4][nb] */,
+                                                           unsigned *__restrict__ list_counts /* [4] */) {
     __shared__ unsigned warp_sum[32];
+    __shared__ unsigned s_cursor[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned carry = 0;                                            // same value in every thread
+    if (tid < 4) s_cursor[tid] = 0;
+    __syncthreads();
     for (int base = 0; base < nb; base += 4096) {
         const int idx = base + 4 * tid;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -418,7 +422,43 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
         before += v.y; if (idx + 2 < nb) start[idx + 2] = before;
         before += v.z; if (idx + 3 < nb) start[idx + 3] = before;
         carry += round_total;
+        // Work lists for the raster, one per weight class: buckets with >= 2048, >= 256, >= 1 records (claimed
+        // dynamically, heaviest class first) and the empty ones (dealt out statically).  One shared-memory
+        // atomic per warp, class and element.
+        const unsigned vals[4] = {v.x, v.y, v.z, v.w};
+        int cls[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cls[e] = idx + e < nb ? (vals[e] == 0u ? 3 : vals[e] >= 2048u ? 0 : vals[e] >= 256u ? 1 : 2) : -1;
+        unsigned mine_j[4], incl[4], slot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                              // per class: how many of my four, warp prefix, one atomic per warp
+            mine_j[j] = (cls[0] == j) + (cls[1] == j) + (cls[2] == j) + (cls[3] == j);
+            incl[j] = mine_j[j];
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned t = __shfl_up_sync(kFull, incl[j], d);
+                if (lane >= d) incl[j] += t;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            slot[j] = 0;
+            if (lane == 31 && incl[j]) slot[j] = atomicAdd(&s_cursor[j], incl[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) slot[j] = __shfl_sync(kFull, slot[j], 31) + incl[j] - mine_j[j];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (cls[e] == j) lists[(size_t)j * nb + slot[j]++] = (unsigned)(idx + e);
+        }
     }
+    __syncthreads();
+    if (tid < 4) list_counts[tid] = s_cursor[tid];
     if (tid == 0) {
         start[nb] = carry;
         const unsigned long long total = *pool_count;
@@ -510,13 +550,16 @@ struct RasterArgs {
     int n_bands, band_rows, height, width, n_instances;
     int x_bits;                            // record = ord1 : 16 | plane row : 16 - x_bits | x : x_bits
     int n_strips;
-    int debug;                             // CAMA_RASTER_DEBUG experiments: 1 = every band empty, 2 = no colour lookup, 4 = no cells
+    int debug;                             // CAMA_RASTER_DEBUG experiments: 2 = no colour lookup
     long long sorted_cap;
     const unsigned *start;                 // [n_items+1]
     const unsigned *sorted;
     const unsigned *lut;
     const uint8_t *bg;
     uint8_t *frames;
+    const unsigned *lists;                 // [4][n_items]: buckets with >= 2048 / >= 256 / >= 1 records (claimed dynamically, in this order) | empty buckets (dealt round-robin)
+    const unsigned *list_counts;           // [4]
+    unsigned *work_counter;                // claims of active buckets beyond the first three of every CTA
     uint4 *ov_records;                     // MODE 2: sparse output, 2 x uint4 per cama_overlay_record
     unsigned *ov_count;
     long long ov_cap;
@@ -721,8 +764,6 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     }
     if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
     __syncthreads();
-    const int stride = (int)gridDim.x;
-
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
 
     auto scatter = [&](unsigned rec) {
@@ -745,39 +786,72 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         }
     };
 
-    // software pipeline over this CTA's items: bounds two items ahead, first records one item ahead
-    int item = blockIdx.x;
-    long long lo = 0, hi = 0, nlo = 0, nhi = 0;
-    unsigned pre[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    if (item < a.n_items) { lo = a.start[item]; hi = min((long long)a.start[item + 1], a.sorted_cap); if (a.debug & 1) hi = lo; fetch(lo, hi, pre); }
-    if (item + stride < a.n_items) { nlo = a.start[item + stride]; nhi = min((long long)a.start[item + stride + 1], a.sorted_cap); if (a.debug & 1) nhi = nlo; }
-    while (item < a.n_items) {
-        long long n2lo = 0, n2hi = 0;
-        if (item + 2 * stride < a.n_items) { n2lo = a.start[item + 2 * stride]; n2hi = a.start[item + 2 * stride + 1]; if (a.debug & 1) n2hi = n2lo; }
-        unsigned pre_next[4];
-        fetch(nlo, nhi, pre_next);         // (nlo == nhi == 0 past the last item: nothing is loaded)
-
-        if (hi <= lo && MODE == 2) {
-            // sparse output: an empty band produces nothing
-        } else if (hi <= lo && MODE == 0) {       // nothing lands in this band: zeros, no synchronisation at all
-            if (tid == 0) {
-                const int y_first = (item % a.n_bands) * a.band_rows;
-                const int rows_out = min(a.band_rows, a.height - y_first);
-                uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
-                unsigned left = (unsigned)rows_out * row_bytes, off = 0;
-                while (left) {
-                    const unsigned n = min(left, zero_bytes);
-                    bulk_store_shared_to_global(out_base + off, zeros, n);
-                    off += n; left -= n;
-                }
-                bulk_commit_group();
-            }
-        } else if (!(hi <= lo && inplace)) {
+    // Work distribution.  Buckets with records ("active") come from a list ordered heaviest class first
+    // and are claimed dynamically, two claims ahead of use, so the claim, the bucket bounds and the first
+    // records of the next bucket are in flight while the current one is processed.  Buckets without
+    // records are dealt round-robin; their zeros are issued by thread 0 a few at a time between active
+    // buckets, so that the store queue stays fed while the warps compute.
+    __shared__ int s_claim[2];
+    const unsigned G = gridDim.x;
+    const unsigned n0 = a.list_counts[0], n1 = a.list_counts[1], n2 = a.list_counts[2], n_emp = a.list_counts[3];
+    const unsigned n_act = n0 + n1 + n2;
+    const unsigned *empty_list = a.lists + (size_t)3 * a.n_items;
+    const bool copy_empties = MODE == 1 && !inplace;          // out-of-place composite: empty bands are copied by the active path
+    const unsigned n_work = n_act + (copy_empties ? n_emp : 0u);
+    auto item_at = [&](unsigned pos) -> int {
+        if (pos < n0) return (int)a.lists[pos];
+        if (pos < n0 + n1) return (int)a.lists[(size_t)a.n_items + (pos - n0)];
+        if (pos < n_act) return (int)a.lists[(size_t)2 * a.n_items + (pos - n0 - n1)];
+        if (pos < n_work) return (int)empty_list[pos - n_act];
+        return -1;
+    };
+    auto bounds = [&](int item, long long &blo, long long &bhi) {
+        blo = bhi = 0;
+        if (item >= 0) { blo = a.start[item]; bhi = min((long long)a.start[item + 1], a.sorted_cap); }
+    };
+    unsigned e_pos = blockIdx.x;                               // (thread 0) next position of this CTA in the empty list
+    const unsigned my_emp = e_pos < n_emp ? (n_emp - e_pos + G - 1u) / G : 0u;
+    const unsigned my_act = max(1u, (n_act + G - 1u) / G);
+    const unsigned empties_per_active = (my_emp + my_act - 1u) / my_act;
+    auto issue_empties = [&](unsigned k) {
+        if (MODE != 0 || tid != 0) return;
+        for (; k > 0u && e_pos < n_emp; --k, e_pos += G) {
+            const int item = (int)empty_list[e_pos];
             const int y_first = (item % a.n_bands) * a.band_rows;
             const int rows_out = min(a.band_rows, a.height - y_first);
             uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
-            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
-            const unsigned chunk_base = (unsigned)((((size_t)(item / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
+            unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+            while (left) {
+                const unsigned n = min(left, zero_bytes);
+                bulk_store_shared_to_global(out_base + off, zeros, n);
+                off += n; left -= n;
+            }
+            bulk_commit_group();
+        }
+    };
+
+    unsigned a2 = blockIdx.x + 2u * G;
+    int item0 = item_at(blockIdx.x), item1 = item_at(blockIdx.x + G);
+    long long lo, hi, nlo, nhi;
+    unsigned pre[4];
+    bounds(item0, lo, hi);
+    bounds(item1, nlo, nhi);
+    fetch(lo, hi, pre);
+    for (int it = 0; item0 >= 0; ++it) {
+        int claim = 0;
+        if (tid == 0) claim = (int)(3u * G + atomicAdd(a.work_counter, 1u));     // list position for three iterations from now
+        const int item2 = item_at(a2);
+        long long n2lo, n2hi;
+        bounds(item2, n2lo, n2hi);
+        unsigned pre_next[4];
+        fetch(nlo, nhi, pre_next);         // (nlo == nhi == 0 past the last bucket: nothing is loaded)
+        issue_empties(empties_per_active);
+        {
+            const int y_first = (item0 % a.n_bands) * a.band_rows;
+            const int rows_out = min(a.band_rows, a.height - y_first);
+            uint8_t *out_base = a.frames + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes;
+            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
+            const unsigned chunk_base = (unsigned)((((size_t)(item0 / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
             // 1. centres of this bucket -> plane (max ordinal per pixel) + hit masks
 #pragma unroll
             for (int q = 0; q < 4; ++q) scatter(pre[q]);
@@ -845,13 +919,17 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
                 for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             if (tid <= n_strips) hits[tid] = 0u;
-            sync_compute();
         }
-        item += stride;
-        lo = nlo; hi = nhi; nlo = n2lo; nhi = min(n2hi, a.sorted_cap);
+        // publish the claim (this barrier also orders the clean-up before the next scatter) and advance the pipeline
+        if (tid == 0) s_claim[it & 1] = claim;
+        __syncthreads();
+        item0 = item1; lo = nlo; hi = nhi;
 #pragma unroll
         for (int q = 0; q < 4; ++q) pre[q] = pre_next[q];
+        item1 = item2; nlo = n2lo; nhi = n2hi;
+        a2 = (unsigned)s_claim[it & 1];
     }
+    issue_empties(0xffffffffu);
     if (MODE == 2 && ov.st->count > 0u) ov_flush(ov);
     // the shared zeros must stay valid until the last bulk stores have read them
     if (MODE == 0 && lane == 0) bulk_wait_group_read<0>();
@@ -872,7 +950,7 @@ struct ClipPlan {
     size_t raster_smem;
     // workspace offsets
     size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
-    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist;
+    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists;
     long long geo_units;
     size_t total;
 };
@@ -963,6 +1041,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));
         p.zero_bytes = off - p.off_zero;
         p.off_start = take(sizeof(unsigned) * ((size_t)nb + 1));
+        p.off_lists = take(sizeof(unsigned) * 4 * (size_t)nb);             // bucket lists of the raster, one per weight class
         p.off_pool = take(sizeof(uint2) * (size_t)d->n_frames * cap);
         p.off_sorted = take(sizeof(unsigned) * (size_t)d->n_frames * cap);
     }
@@ -1094,7 +1173,9 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_LAUNCHED(ctx);
     }
     CAMA_CUDA_TRY(mark(2));
-    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats);
+    unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
+    unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats, lists, list_counts);
     CAMA_LAUNCHED(ctx);
     {   // one record per thread when the pool is full; CTAs past the records appended exit at once
         const long long tile = 256 * kScatterPerThread;
@@ -1109,6 +1190,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     r.x_bits = p.x_bits; r.n_strips = p.n_strips;
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
     r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    r.lists = lists; r.list_counts = list_counts;
+    r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
     if (d->overlay_records) {
         r.ov_records = reinterpret_cast<uint4 *>(d->overlay_records); r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;

@@ -109,17 +109,20 @@ class ClipManager:
         n = len(stamps)
         if n <= 1:
             return []
-        queries = np.asarray(stamps[1:], dtype=np.float64)
         # Frames whose stamp coincides with a pose stamp (the usual case: the poses come from the same
         # sync list) take seek_by_timestamp's first branch; resolve all of them with one comparison.
-        # The other frames go through the method itself (interpolation / RuntimeError).
+        # The other frames go through the method itself (interpolation / RuntimeError).  The comparison
+        # depends on the two stamp lists only, which never change for a loaded clip: done once.
         pose_stamps = pt.timestamps[:, 0] if pt.timestamps.ndim == 2 else np.asarray(pt.timestamps, dtype=np.float64)
-        hit = np.isclose(pose_stamps[None, :], queries[:, None], rtol=1e-20, atol=1e-9)
-        has_hit = hit.any(axis=1)
-        first_hit = hit.argmax(axis=1)
+        hits = self.__dict__.setdefault("_stamp_hits", {})
+        if dataset not in hits or hits[dataset][0] is not pt.timestamps:
+            queries = np.asarray(stamps[1:], dtype=np.float64)
+            hit = np.isclose(pose_stamps[None, :], queries[:, None], rtol=1e-20, atol=1e-9)
+            hits[dataset] = (pt.timestamps, hit.any(axis=1), hit.argmax(axis=1),
+                             bool(np.all(pose_stamps[1:] >= pose_stamps[:-1])))       # (seek_by_timestamp asserts sortedness)
+        _, has_hit, first_hit, sorted_stamps = hits[dataset]
         pt._ensure_absolute()
         absolute = pt.absolute_transform
-        sorted_stamps = bool(np.all(pose_stamps[1:] >= pose_stamps[:-1]))       # (seek_by_timestamp asserts this)
         kept_idx, kept_pose = [], []
         for k in range(n - 1):
             image_idx = k + 1
