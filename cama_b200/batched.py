@@ -64,11 +64,14 @@ def tile_bounds(xyz):
 class _Resident:
     """Device copies of what does not change from frame to frame."""
 
-    def __init__(self, rt, instances):
+    def __init__(self, rt, instances, device_vertices=None):
         self.layout, verts, ordinal, bgr = pack_vertices(instances)
         self.n_vertices = int(verts.shape[0])
         self.n_instances = len(instances)
-        self.vertices = rt.to_device(verts)
+        if device_vertices is not None and self.layout == N.VERTEX_F32X4 and tuple(device_vertices.shape) == tuple(verts.shape):
+            self.vertices = device_vertices                   # densified on the device: already resident
+        else:
+            self.vertices = rt.to_device(verts)
         self.tile_bounds = rt.to_device(tile_bounds(verts[:, :3])) if self.n_vertices else None
         self.ordinal = rt.to_device(ordinal) if ordinal is not None else None
         self.bgr = rt.to_device(bgr)
@@ -89,8 +92,8 @@ class ClipRenderer:
         self.overlay_capacity = {}    # (resident id, n_frames) -> overlay records that were enough
         self.last_stats = None
 
-    def resident(self, instances):
-        return _Resident(self.rt, instances)
+    def resident(self, instances, device_vertices=None):
+        return _Resident(self.rt, instances, device_vertices)
 
     def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None):
         d = N.ClipDesc()
@@ -215,8 +218,8 @@ class ClipRenderer:
 class Reproject:
     """Batched drop-in for the frame loop: ``Reproject(configs, clip_path)(dataset)``."""
 
-    def __init__(self, configs, clip_path=None, device=None, clip_manager=None):
-        self.cm = clip_manager if clip_manager is not None else ClipManager(configs, clip_path, device=device, progress=False)
+    def __init__(self, configs, clip_path=None, device=None, clip_manager=None, densify="device"):
+        self.cm = clip_manager if clip_manager is not None else ClipManager(configs, clip_path, device=device, progress=False, densify=densify)
         self.configs = configs
         cams = self.cm.cm_list
         assert len({(c.height, c.width) for c in cams}) == 1, "all cameras must share one output size"
@@ -236,7 +239,8 @@ class Reproject:
 
     def resident(self, dataset):
         if dataset not in self._resident:
-            self._resident[dataset] = self.renderer.resident(self.cm.instance_maps[dataset])
+            instances = self.cm.instance_maps[dataset]
+            self._resident[dataset] = self.renderer.resident(instances, self.cm.mm.device_vertices(instances))
         return self._resident[dataset]
 
     def frame_poses(self, dataset):

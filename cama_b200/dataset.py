@@ -31,11 +31,11 @@ except Exception:                       # pragma: no cover
 
 
 class ClipManager:
-    def __init__(self, configs, clip_path=None, device=None, progress=True):
+    def __init__(self, configs, clip_path=None, device=None, progress=True, densify="host"):
         self.configs = configs
         self._device = device
         self._progress = progress
-        self.mm = MapManager(device=device)
+        self.mm = MapManager(device=device, densify=densify)
         self.instance_maps = dict()
         if clip_path is not None:
             self.clip_path = clip_path

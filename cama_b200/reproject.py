@@ -95,8 +95,14 @@ def densify_polyline(points, resolution):
 
 
 class MapManager(BaseManager):
-    def __init__(self, device=None):
+    def __init__(self, device=None, densify="host"):
+        """``densify="device"`` runs the load-time densify (and the BEV height lookup) on the GPU
+        (cama_densify_*); the dense vertices then stay resident for the batched renderer and only a copy
+        comes back for the list-of-instances API.  ``"host"`` is the vectorised NumPy version."""
         super(MapManager, self).__init__()
+        assert densify in ("host", "device")
+        self._densify = densify
+        self._device_dense = {}        # id(instance list) -> (instance list, device float4 vertices)
         self.solution = 0.1      # metre per BEV pixel, also the densify step
         self.center_x = 0
         self.center_y = 0
@@ -112,8 +118,30 @@ class MapManager(BaseManager):
         worlds_xy[:, 1] = pixel_xy[:, 0] * self.solution - self.map_height / 2 + self.center_y
         return worlds_xy
 
+    def _densify_on_device(self, maps_2d, bev_height):
+        items = [item for item in maps_2d if len(item["data"]) > 1]
+        polylines = [np.array(item["data"]).astype(np.float32) for item in items]
+        verts, counts = get_runtime(self._device).densify(
+            polylines, self.solution, bev_height=bev_height, solution=self.solution, half_width=self.map_width / 2,
+            half_height=self.map_height / 2, center_x=self.center_x, center_y=self.center_y)
+        if len(counts) and int(counts.min()) == 0:
+            # the reference indexes an empty 1-D array here and raises the same exception type
+            raise IndexError("polyline has no segment of at least one resolution step")
+        host = verts[:, :3].cpu().numpy()
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        instance_list = [{"class": item["attrs"]["type"], "points": host[offsets[i]:offsets[i + 1]]} for i, item in enumerate(items)]
+        self._device_dense[id(instance_list)] = (instance_list, verts)
+        return instance_list
+
+    def device_vertices(self, instance_list):
+        """The resident float4 vertices of an instance list produced by the device densify, else None."""
+        hit = self._device_dense.get(id(instance_list))
+        return hit[1] if hit is not None and hit[0] is instance_list else None
+
     def load_3d_instance_maps(self, maps_2d):
         """Metric (nuScenes-style) labels -> dense instances on the z = 0 plane."""
+        if self._densify == "device":
+            return self._densify_on_device(maps_2d, None)
         instance_list = []
         for item in maps_2d:
             if len(item["data"]) <= 1:
@@ -125,6 +153,8 @@ class MapManager(BaseManager):
 
     def calculate_3d_instance_maps(self, bev_height, maps_2d):
         """BEV-pixel (CAMA) labels + height map -> dense world instances."""
+        if self._densify == "device" and bev_height.dtype == np.float32 and bev_height.ndim == 2:
+            return self._densify_on_device(maps_2d, np.ascontiguousarray(bev_height))
         instance_list = []
         for item in maps_2d:
             if len(item["data"]) <= 1:

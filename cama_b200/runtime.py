@@ -97,6 +97,41 @@ class Runtime:
     def ptr(tensor):
         return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None and tensor.numel() > 0 else ctypes.c_void_p(0)
 
+    # -------------------------------------------------------------- load-time densify (scope row N2)
+    def densify(self, polylines, resolution, bev_height=None, solution=0.1, half_width=300.0, half_height=300.0,
+                center_x=0.0, center_y=0.0):
+        """cama_densify_plan + cama_densify_fill.
+
+        polylines   list of (k_i, 2) arrays, k_i >= 2 (label vertices; float32 after the reference's astype)
+        bev_height  None (metric labels: z = 0) or float32 [rows, cols] height map (CAMA pixel labels)
+        -> (vertices: torch float32 [total, 4] on the device in CAMA_VERTEX_F32X4 layout, per-polyline point counts)
+        """
+        torch = _torch()
+        raw = np.concatenate([np.asarray(p, dtype=np.float32).reshape(-1, 2) for p in polylines], axis=0) if polylines else np.zeros((0, 2), np.float32)
+        sizes = np.array([len(p) for p in polylines], dtype=np.int64)
+        raw_poly = np.repeat(np.arange(len(polylines), dtype=np.int32), sizes)
+        n_raw = int(raw.shape[0])
+        d_raw, d_poly = self.to_device(raw), self.to_device(raw_poly)
+        d_start = torch.empty(n_raw + 1, dtype=torch.int64, device=self.device)
+        N.check(N.lib().cama_densify_plan(self.ctx, self.ptr(d_raw), self.ptr(d_poly), n_raw, ctypes.c_float(float(np.float32(resolution))),
+                                          ctypes.c_void_p(d_start.data_ptr()), self.stream()))
+        seg_start = d_start.cpu().numpy()
+        total = int(seg_start[-1])
+        first_raw = np.concatenate([[0], np.cumsum(sizes)])
+        counts = seg_start[first_raw[1:]] - seg_start[first_raw[:-1]] if len(polylines) else np.zeros(0, np.int64)
+        verts = torch.empty((total, 4), dtype=torch.float32, device=self.device)
+        d_bev = None
+        rows = cols = 0
+        if bev_height is not None:
+            assert bev_height.dtype == np.float32 and bev_height.ndim == 2
+            d_bev = self.to_device(bev_height)
+            rows, cols = bev_height.shape
+        f = lambda v: ctypes.c_float(float(np.float32(v)))
+        N.check(N.lib().cama_densify_fill(self.ctx, self.ptr(d_raw), self.ptr(d_poly), n_raw, ctypes.c_void_p(d_start.data_ptr()), total,
+                                          self.ptr(d_bev) if d_bev is not None else None, rows, cols, f(solution), f(half_width), f(half_height),
+                                          f(center_x), f(center_y), self.ptr(verts), self.stream()))
+        return verts, counts
+
     # -------------------------------------------------------------- per-call operators (numpy in / numpy out)
     def transform_points(self, points, T):
         """cama_transform_points: (n,3) float32/float64 -> (n,3) float64 = (T @ [p;1])[:3]."""

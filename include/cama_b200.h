@@ -123,6 +123,29 @@ int cama_render_points(cama_ctx *ctx, const double *vu, int64_t n, const int64_t
                        int64_t n_inst, const uint8_t *inst_bgr, uint8_t *image, int height, int width,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- load-time densify on the device (scope row N2) ------------------------------------------- */
+
+/* MapManager.load_3d_instance_maps / calculate_3d_instance_maps (cama/reproject.py:42-106, pixel2world_xy
+ * :36-40): every polyline segment becomes num = int(len / resolution) float32 points start + (end-start)/num*j,
+ * j < num (segment end excluded, num == 0 segments dropped); CAMA (pixel) labels also look the height up in
+ * the BEV map and move to world metres.  Bit-identical to the reference's float32 NumPy arithmetic.
+ *   raw_xy     device float32 [n_raw,2]  label vertices of all polylines, polyline-major (polylines with
+ *              fewer than 2 vertices removed by the caller, as the reference skips them)
+ *   raw_poly   device int32 [n_raw]      instance ordinal of each raw vertex (non-decreasing)
+ * Two steps, because the output size is data dependent:
+ *   cama_densify_plan  -> seg_start device int64 [n_raw+1]: exclusive scan of the per-segment point counts
+ *                         (seg_start[n_raw] = total; the caller reads it back to size the output)
+ *   cama_densify_fill  -> out_vertices device float4 [total] {x,y,z, bit-cast int32 ordinal}: the
+ *                         CAMA_VERTEX_F32X4 layout cama_clip_render takes, so the dense map never visits the host.
+ *                         bev_height == NULL: metric labels (x,y kept, z = 0, cama/reproject.py:42-70);
+ *                         else float32 [bev_rows,bev_cols] and x = p1*solution - half_width + center_x,
+ *                         y = p0*solution - half_height + center_y, z = bev[clip(round(p1)), clip(round(p0))]. */
+int cama_densify_plan(cama_ctx *ctx, const float *raw_xy, const int32_t *raw_poly, int64_t n_raw, float resolution,
+                      int64_t *seg_start, void *stream);
+int cama_densify_fill(cama_ctx *ctx, const float *raw_xy, const int32_t *raw_poly, int64_t n_raw, const int64_t *seg_start,
+                      int64_t total, const float *bev_height, int bev_rows, int bev_cols, float solution, float half_width,
+                      float half_height, float center_x, float center_y, float *out_vertices, void *stream);
+
 /* ---- the batched clip path: the loop of cama/dataset.py:78-126 in one call ------------------- */
 
 enum { CAMA_VERTEX_F32X4 = 0,   /* float4 {x,y,z, bit-cast int32 instance ordinal} */

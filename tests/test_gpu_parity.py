@@ -486,6 +486,50 @@ def test_overlay_records_are_unique_chunks(rt):
     assert not (bgr * (1 - bits)[:, :, None]).any() and not (dense[chunk] * (1 - bits)[:, :, None]).any()
 
 
+def test_device_densify_matches_host_and_oracle(rt):
+    """Scope row N2: cama_densify_plan/fill against the NumPy restatement of cama/reproject.py:42-106 and the
+    C oracle, bit for bit: segment lengths on both sides of multiples of the resolution, sub-resolution
+    segments, negative / large coordinates, the BEV height lookup with clipping, a polyline without points."""
+    from cama_b200.reproject import MapManager
+    rng = np.random.default_rng(21)
+    labels = []
+    for k in range(60):
+        n = int(rng.integers(2, 9))
+        steps = rng.choice([0.05, 0.0999999, 0.1, 0.1000001, 0.3, 0.7, 2.35, 17.0], size=n - 1) * rng.choice([1.0, 1.0, 10.0])
+        ang = rng.uniform(0, 2 * np.pi, n - 1)
+        pts = np.cumsum(np.concatenate([rng.uniform(-300, 6300, (1, 2)), np.stack([steps * np.cos(ang), steps * np.sin(ang)], 1)]), axis=0)
+        if not (np.linalg.norm(np.diff(pts.astype(np.float32), axis=0), axis=1) / np.float32(0.1)).astype(np.int64).any():
+            pts[-1] += 3.0                      # keep every polyline drawable here; the empty case is checked below
+        labels.append({"attrs": {"type": synth.MAP_CLASSES[k % 3]}, "data": pts.tolist()})
+    labels.insert(7, {"attrs": {"type": "lane_marking"}, "data": [[5.0, 5.0]]})            # skipped by the reference
+    labels.append({"attrs": {"type": "lane_marking"}, "data": [[0, 0], [1, 0], [1.05, 0], [1.35, 0]]})
+    host, dev = MapManager(device=0, densify="host"), MapManager(device=0, densify="device")
+    a, b = host.load_3d_instance_maps(labels), dev.load_3d_instance_maps(labels)
+    assert [i["class"] for i in a] == [i["class"] for i in b] and len(a) == 61
+    for x, y in zip(a, b):
+        assert y["points"].dtype == np.float32 and np.array_equal(x["points"], y["points"])
+    assert np.array_equal(b[-1]["points"][:, :2], oracle_c.densify(np.array(labels[-1]["data"])))
+    assert dev.device_vertices(b) is not None and dev.device_vertices(a) is None
+    verts = dev.device_vertices(b).cpu().numpy()
+    assert np.array_equal(verts[:, :3], np.concatenate([i["points"] for i in b]))
+    assert np.array_equal(verts[:, 3].view(np.int32), np.repeat(np.arange(61, dtype=np.int32), [len(i["points"]) for i in b]))
+    # pixel labels + height map (indices beyond the map are clipped, both with shape[0]-1)
+    bev = rng.standard_normal((500, 700)).astype(np.float32)
+    a, b = host.calculate_3d_instance_maps(bev, labels), dev.calculate_3d_instance_maps(bev, labels)
+    for x, y in zip(a, b):
+        assert np.array_equal(x["points"], y["points"])
+    want = orc.instances_from_pixel_labels(bev, labels)
+    assert all(np.array_equal(x["points"], y["points"]) for x, y in zip(want, b))
+    # a float64 height map promotes the points to float64: that branch stays on the host
+    c = dev.calculate_3d_instance_maps(bev.astype(np.float64), labels)
+    assert c[0]["points"].dtype == np.float64 and dev.device_vertices(c) is None
+    # a polyline whose segments are all shorter than the resolution: the reference raises IndexError
+    for mm in (host, dev):
+        with pytest.raises(IndexError):
+            mm.load_3d_instance_maps([{"attrs": {"type": "lane_marking"}, "data": [[0, 0], [0.05, 0]]}])
+    assert dev.load_3d_instance_maps([]) == []
+
+
 def test_cama_dense_labels_vs_oracle(rt, tmp_path):
     """CAMA-label branch (0.1 px densify, BEV height lookup, N ~ 1.0 M vertices), 4 frames."""
     from cama_b200.batched import Reproject
