@@ -82,6 +82,7 @@ SIGNATURES = {
     "cama_densify_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float, c_void_p, c_void_p]),
     "cama_densify_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int] + [ctypes.c_float] * 5
                           + [c_void_p, c_void_p]),
+    "cama_remap_bilinear": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "cama_clip_workspace_bytes": (c_int, [POINTER(ClipDesc), POINTER(c_size_t)]),
     "cama_clip_render": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_size_t, c_void_p]),
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),

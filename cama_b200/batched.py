@@ -173,6 +173,20 @@ class ClipRenderer:
         return (out, dbg) if debug else out
 
 
+    def remap(self, raw, map_x, map_y, out=None):
+        """cama_remap_bilinear: raw torch uint8 [n, Hs, Ws, 3] (n = frames x cameras, camera-minor) through
+        per-camera maps torch float32 [n_maps, H, W] -> torch uint8 [n, H, W, 3] (cv2.remap INTER_LINEAR, bit-exact)."""
+        import torch
+        rt = self.rt
+        n, hs, ws = int(raw.shape[0]), int(raw.shape[1]), int(raw.shape[2])
+        assert raw.dtype == torch.uint8 and raw.is_contiguous() and raw.shape[3] == 3
+        assert map_x.dtype == torch.float32 and map_x.is_contiguous() and map_y.is_contiguous() and map_x.shape == map_y.shape
+        n_maps, h, w = (int(v) for v in map_x.shape)
+        if out is None:
+            out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=rt.device)
+        N.check(N.lib().cama_remap_bilinear(rt.ctx, rt.ptr(raw), n, hs, ws, rt.ptr(map_x), rt.ptr(map_y), n_maps, rt.ptr(out), h, w, rt.stream()))
+        return out
+
     def render_overlay(self, res, w2c_dev, mode="auto"):
         """Sparse output of one clip: the lit 8-pixel chunks instead of dense frames.
 
@@ -231,6 +245,7 @@ class Reproject:
         self.rt = self.renderer.rt
         self._resident = {}
         self._pinned = {}
+        self._maps_dev = None
         self._host_frames = None      # sparse transfer: the host frames of the last blank-background call ...
         self._ov_prev = None          # ... and the records painted into them (blanked before the next paint)
         self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
@@ -250,11 +265,31 @@ class Reproject:
         w2c = np.stack([m for _, m in poses]).reshape(-1, 16) if poses else np.zeros((0, 16), np.float32)
         return idx, np.ascontiguousarray(w2c, dtype=np.float32)
 
-    def render_device(self, dataset, w2c=None, out=None, background=None, mode="auto", check=True):
-        """Frames as a torch uint8 [F',C,H,W,3] tensor on the GPU (w2c: host float32 [F',16])."""
+    def undistort_maps_device(self):
+        """Per-camera cv2.initUndistortRectifyMap maps on the device: (map_x, map_y) float32 [C,H,W]."""
+        import torch
+        if self._maps_dev is None:
+            maps = [c.undistort_maps() for c in self.cm.cm_list]
+            self._maps_dev = (torch.from_numpy(np.ascontiguousarray(np.stack([m[0] for m in maps]), dtype=np.float32)).to(self.rt.device),
+                              torch.from_numpy(np.ascontiguousarray(np.stack([m[1] for m in maps]), dtype=np.float32)).to(self.rt.device))
+        return self._maps_dev
+
+    def render_device(self, dataset, w2c=None, out=None, background=None, mode="auto", check=True, raw_backgrounds=None):
+        """Frames as a torch uint8 [F',C,H,W,3] tensor on the GPU (w2c: host float32 [F',16]).
+
+        ``raw_backgrounds``: torch uint8 [F',C,Hs,Ws,3] camera images at their native size on this device;
+        they are undistort-resized (cama/reproject.py:232-240) into the frames, then drawn on in place — the
+        whole of ClipManager.render_vectors (cama/dataset.py:119-126) after the JPEG decode."""
         import torch
         if w2c is None:
             _, w2c = self.frame_poses(dataset)
+        if raw_backgrounds is not None:
+            assert background is None, "give either background or raw_backgrounds"
+            mx, my = self.undistort_maps_device()
+            f, c = int(raw_backgrounds.shape[0]), int(raw_backgrounds.shape[1])
+            flat = raw_backgrounds.reshape(f * c, *raw_backgrounds.shape[2:])
+            resized = self.renderer.remap(flat, mx, my, out=None if out is None else out.reshape(f * c, *out.shape[2:]))
+            background = out = resized.reshape(f, c, *resized.shape[1:])
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(self.rt.device)
         return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check)
 

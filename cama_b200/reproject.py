@@ -281,11 +281,21 @@ class CameraManager(BaseManager):
     def read_resized_image_by_index(self, index, sync=True):
         return self.read_resized_image(self.get_image_path(index, sync))
 
+    def undistort_maps(self):
+        """(map_x, map_y) float32 [H,W] of cv2.initUndistortRectifyMap for this camera (reference :236-238),
+        computed once: they depend on the calibration only (the reference recomputes them per image)."""
+        maps = self.__dict__.get("_undistort_maps")
+        if maps is None:
+            import cv2
+            distortion = self.d_origin if self.d == [] else self.d
+            maps = cv2.initUndistortRectifyMap(self.K_origin, distortion, None, self.K, (self.width, self.height), cv2.CV_32FC1)
+            self.__dict__["_undistort_maps"] = maps
+        return maps
+
     def resize_image(self, image, interpolation=1):
         """Undistort + resize to the output size (reference :232-240; interpolation 1 = cv2.INTER_LINEAR)."""
         import cv2
-        distortion = self.d_origin if self.d == [] else self.d
-        mapx, mapy = cv2.initUndistortRectifyMap(self.K_origin, distortion, None, self.K, (self.width, self.height), cv2.CV_32FC1)
+        mapx, mapy = self.undistort_maps()
         return cv2.remap(image, mapx, mapy, interpolation=interpolation)
 
     def read_resized_image(self, image_path):

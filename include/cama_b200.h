@@ -146,6 +146,19 @@ int cama_densify_fill(cama_ctx *ctx, const float *raw_xy, const int32_t *raw_pol
                       int64_t total, const float *bev_height, int bev_rows, int bev_cols, float solution, float half_width,
                       float half_height, float center_x, float center_y, float *out_vertices, void *stream);
 
+/* ---- undistort-resize of the camera images (scope row N1) --------------------------------------- */
+
+/* CameraManager.resize_image (cama/reproject.py:232-240): cv2.remap(image, map_x, map_y, INTER_LINEAR) on uint8
+ * BGR images, bit-identical to OpenCV's fixed-point bilinear path (5 fractional bits, 15-bit weights, border 0).
+ *   src    device uint8 [n_images, src_height, src_width, 3]
+ *   map_x, map_y  device float32 [n_maps, dst_height, dst_width] from cv2.initUndistortRectifyMap — computed once
+ *          per camera (the reference recomputes them per image); image i uses map i % n_maps, so frame-major /
+ *          camera-minor images take n_maps = n_cams
+ *   dst    device uint8 [n_images, dst_height, dst_width, 3] (may be the `background`/`frames` of cama_clip_render) */
+int cama_remap_bilinear(cama_ctx *ctx, const uint8_t *src, int64_t n_images, int src_height, int src_width,
+                        const float *map_x, const float *map_y, int64_t n_maps, uint8_t *dst, int dst_height, int dst_width,
+                        void *stream);
+
 /* ---- the batched clip path: the loop of cama/dataset.py:78-126 in one call ------------------- */
 
 enum { CAMA_VERTEX_F32X4 = 0,   /* float4 {x,y,z, bit-cast int32 instance ordinal} */

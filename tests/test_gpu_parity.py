@@ -530,6 +530,58 @@ def test_device_densify_matches_host_and_oracle(rt):
     assert dev.load_3d_instance_maps([]) == []
 
 
+def test_remap_matches_cv2(rt):
+    """Scope row N1: cama_remap_bilinear == cv2.remap(INTER_LINEAR) on uint8 BGR, including taps that
+    leave the source (border constant 0) and maps cycling per camera."""
+    import cv2
+    import torch
+    from cama_b200.batched import ClipRenderer
+    rng = np.random.default_rng(8)
+    r = ClipRenderer(np.eye(4)[None], np.eye(3)[None], H, W, BOX6, device=0)
+    src = rng.integers(0, 256, size=(4, 900, 1600, 3), dtype=np.uint8)
+    maps = []
+    for cam in ("camera_front", "camera_rear"):
+        K = synth.camera_intrinsics(cam)
+        Kn = K.copy()
+        Kn[0] *= W / 1600
+        Kn[1] *= H / 900
+        maps.append(cv2.initUndistortRectifyMap(K, np.zeros(8), None, Kn, (W, H), cv2.CV_32FC1))
+    maps[1] = (maps[1][0] * np.float32(1.1) - np.float32(40.3), maps[1][1] * np.float32(1.2) - np.float32(60.7))   # leaves the image on all sides
+    mx = to_dev(np.stack([m[0] for m in maps]))
+    my = to_dev(np.stack([m[1] for m in maps]))
+    got = r.remap(to_dev(src), mx, my).cpu().numpy()
+    for i in range(4):
+        want = cv2.remap(src[i], maps[i % 2][0], maps[i % 2][1], interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(got[i], want), i
+    assert (got[1] == 0).all(-1).any()                         # the border value really occurs
+    # exact half-way fractions: cvRound is round-half-to-even
+    half = np.tile((np.arange(W, dtype=np.float32) + np.float32(0.5)) / np.float32(32), (H, 1))
+    flipped = np.ascontiguousarray(half[:, ::-1])
+    want = cv2.remap(src[0], half, flipped, interpolation=cv2.INTER_LINEAR)
+    got = r.remap(to_dev(src[:1]), to_dev(half[None]), to_dev(flipped[None])).cpu().numpy()[0]
+    assert np.array_equal(got, want)
+
+
+def test_render_vectors_with_raw_camera_images(rt, clip_root):
+    """ClipManager.render_vectors after the JPEG decode, batched on the device: undistort-resize + draw in
+    place == cv2.remap of each image, then the reference's render_maps (here: the golden overlay on top)."""
+    import cv2
+    import torch
+    from cama_b200.batched import Reproject
+    g = load_golden("golden_clip_nuscenes_exact.npz")
+    clip = synth.write_clip(synth.tiny_spec(name="tiny_raw"), clip_root)
+    rp = Reproject(synth.CAMA_CONFIGS, clip, device=0)
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 256, size=(3, 6, 900, 1600, 3), dtype=np.uint8)
+    frames = rp.render_device("nuscenes", raw_backgrounds=to_dev(raw)).cpu().numpy()
+    lit = g["frames"].any(-1)
+    for f in range(3):
+        for c, cam in enumerate(rp.cm.cm_list):
+            bg = cam.resize_image(raw[f, c])                  # cv2.remap with the camera's maps (reference :232-240)
+            want = np.where(lit[f, c][..., None], g["frames"][f, c], bg)
+            assert np.array_equal(frames[f, c], want), (f, c)
+
+
 def test_cama_dense_labels_vs_oracle(rt, tmp_path):
     """CAMA-label branch (0.1 px densify, BEV height lookup, N ~ 1.0 M vertices), 4 frames."""
     from cama_b200.batched import Reproject
