@@ -16,7 +16,8 @@ VERTEX_F32X4, VERTEX_F64X3 = 0, 1
 CLIP_AUTO, CLIP_PLANE, CLIP_BINNED = 0, 1, 2
 MAX_CAMERAS = 8
 TILE_VERTICES = 256
-OVERLAY_RECORD_BYTES = 32
+OVERLAY_BGR, OVERLAY_PALETTE = 0, 1
+OVERLAY_RECORD_BYTES = {OVERLAY_BGR: 32, OVERLAY_PALETTE: 12}
 OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
 CLIP_PHASES = 4
 PHASE_NAMES = ("prep", "geometry", "sort", "raster")
@@ -47,7 +48,13 @@ class ClipDesc(Structure):
         ("record_capacity", c_int64),
         ("tile_bounds", c_void_p),
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
+        ("overlay_format", c_int32), ("reserved0", c_int32), ("instance_palette", c_void_p),
     ]
+
+
+class OverlayTarget(Structure):
+    _fields_ = [("pixels", c_void_p), ("n_frames", c_int64), ("n_cams", c_int32), ("height", c_int32), ("width", c_int32),
+                ("grid_cols", c_int32), ("tile_of_cam", c_void_p)]
 
 
 class ClipStats(Structure):
@@ -86,8 +93,7 @@ SIGNATURES = {
     "cama_clip_workspace_bytes": (c_int, [POINTER(ClipDesc), POINTER(c_size_t)]),
     "cama_clip_render": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_size_t, c_void_p]),
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),
-    "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int]),
-    "cama_overlay_apply_host_mosaic": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+    "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(OverlayTarget), c_int, c_int]),
 }
 
 _LIB = None

@@ -73,6 +73,14 @@ class _Resident:
         else:
             self.vertices = rt.to_device(verts)
         self.tile_bounds = rt.to_device(tile_bounds(verts[:, :3])) if self.n_vertices else None
+        # palette of the distinct instance colours (compact sparse records): entry 0 = not painted
+        colours, index = (np.unique(bgr, axis=0, return_inverse=True) if len(bgr) else (np.zeros((0, 3), np.uint8), np.zeros(0, np.int64)))
+        self.palette = None
+        self.palette_index = None
+        if 0 < len(colours) <= 255:
+            self.palette = np.zeros((256, 3), dtype=np.uint8)
+            self.palette[1:len(colours) + 1] = colours
+            self.palette_index = rt.to_device((np.asarray(index).reshape(-1) + 1).astype(np.uint8))
         self.ordinal = rt.to_device(ordinal) if ordinal is not None else None
         self.bgr = rt.to_device(bgr)
 
@@ -118,10 +126,12 @@ class ClipRenderer:
         d.record_capacity = int(capacity)
         d.tile_bounds = res.tile_bounds.data_ptr() if getattr(res, "tile_bounds", None) is not None else None
         if overlay is not None:
-            records, count = overlay
+            records, count, fmt = overlay
             d.overlay_records = records.data_ptr()
             d.overlay_count = count.data_ptr()
             d.overlay_capacity = int(records.shape[0])
+            d.overlay_format = fmt
+            d.instance_palette = res.palette_index.data_ptr() if fmt == N.OVERLAY_PALETTE else None
         return d
 
     def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False):
@@ -187,12 +197,17 @@ class ClipRenderer:
         N.check(N.lib().cama_remap_bilinear(rt.ctx, rt.ptr(raw), n, hs, ws, rt.ptr(map_x), rt.ptr(map_y), n_maps, rt.ptr(out), h, w, rt.stream()))
         return out
 
-    def render_overlay(self, res, w2c_dev, mode="auto"):
+    def render_overlay(self, res, w2c_dev, mode="auto", fmt=None):
         """Sparse output of one clip: the lit 8-pixel chunks instead of dense frames.
 
-        -> (records: torch int32 [capacity, 8] on the device (cama_overlay_record), n_records)
+        fmt  N.OVERLAY_PALETTE (12-byte records, needs <= 255 distinct instance colours), N.OVERLAY_BGR (32-byte
+             records) or None = palette when possible
+        -> (records: torch int32 [capacity, 3 or 8] on the device, n_records, fmt)
         Synchronises (the record count is read back); reruns with larger pools on overflow.
         """
+        if fmt is None:
+            fmt = N.OVERLAY_PALETTE if res.palette_index is not None else N.OVERLAY_BGR
+        words = N.OVERLAY_RECORD_BYTES[fmt] // 4
         import torch
         rt = self.rt
         n_frames = int(w2c_dev.shape[0])
@@ -201,14 +216,14 @@ class ClipRenderer:
         capacity = self.capacity.get(key, 0)
         ov_cap = self.overlay_capacity.get(key, max(n_chunks // 8, 1024))
         for attempt in range(4):
-            records = rt.scratch_tensor("overlay", (ov_cap, 8), torch.int32)
+            records = rt.scratch_tensor(f"overlay{words}", (ov_cap, words), torch.int32)
             count = rt.scratch_tensor("overlay_count", (4,), torch.int32)
-            desc = self._desc(res, w2c_dev, n_frames, None, None, mode, capacity, None, overlay=(records, count))
+            desc = self._desc(res, w2c_dev, n_frames, None, None, mode, capacity, None, overlay=(records, count, fmt))
             need = ctypes.c_size_t()
             N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
             ws = rt.scratch("clip", need.value)
             if n_frames == 0:
-                return records, 0
+                return records, 0, fmt
             N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
             stats = N.ClipStats()
             code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
@@ -225,7 +240,7 @@ class ClipRenderer:
                 self.overlay_capacity[key] = ov_cap
                 retry = True
             if not retry:
-                return records, int(stats.overlay_records)
+                return records, int(stats.overlay_records), fmt
         raise N.CamaError(N.CAMA_E_CAPACITY, "record pools kept overflowing")
 
 
@@ -329,22 +344,22 @@ class Reproject:
         H, W, C = self.renderer.height, self.renderer.width, self.renderer.n_cams
         shape = (len(idx), C, H, W, 3) if tiles is None else (len(idx), 2 * H, 3 * W, 3)
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(rt.device)
-        records, n = self.renderer.render_overlay(self.resident(dataset), w2c_dev, mode=mode)
+        res = self.resident(dataset)
+        records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode)
+        words = int(records.shape[1])
         # records -> pinned host memory
         cur = self._ov_host[self._ov_flip]
-        if cur is None or cur.shape[0] < max(n, 1):
-            cur = torch.empty((max(int(n * 1.25), 4096), 8), dtype=torch.int32, pin_memory=True)
+        if cur is None or cur.shape[0] < max(n, 1) or cur.shape[1] != words:
+            cur = torch.empty((max(int(n * 1.25), 4096), words), dtype=torch.int32, pin_memory=True)
             self._ov_host[self._ov_flip] = cur
         if n:
             cur[:n].copy_(records[:n], non_blocking=True)        # in flight while the host blanks the previous overlay
-        n_chunks = len(idx) * C * H * W // 8
 
-        def apply(rec, count, op):
-            if tiles is None:
-                N.check(N.lib().cama_overlay_apply_host(rec.data_ptr(), count, frames.ctypes.data, n_chunks, op, 0))
-            else:
-                N.check(N.lib().cama_overlay_apply_host_mosaic(rec.data_ptr(), count, frames.ctypes.data, len(idx), C, H, W, 3,
-                                                               tiles.ctypes.data, op, 0))
+        def apply(rec, count, rec_fmt, palette, op):
+            target = N.OverlayTarget(frames.ctypes.data, len(idx), C, H, W, 0 if tiles is None else 3,
+                                     None if tiles is None else tiles.ctypes.data)
+            N.check(N.lib().cama_overlay_apply_host(rec.data_ptr(), count, rec_fmt, None if palette is None else palette.ctypes.data,
+                                                    ctypes.byref(target), op, 0))
 
         if backgrounds is not None:
             frames = backgrounds
@@ -356,13 +371,14 @@ class Reproject:
                 frames = self._host_frames = np.zeros(shape, dtype=np.uint8)
                 self._ov_prev = None
             if self._ov_prev is not None:                    # blank what the previous call painted into this buffer
-                prev, n_prev = self._ov_prev
-                apply(prev, n_prev, N.OVERLAY_BLANK_CHUNKS)
-            self._ov_prev = (cur, n)
+                prev, n_prev, prev_fmt, prev_palette = self._ov_prev
+                apply(prev, n_prev, prev_fmt, prev_palette, N.OVERLAY_BLANK_CHUNKS)
+            self._ov_prev = (cur, n, fmt, res.palette)
             self._ov_flip ^= 1
         rt.synchronize()
-        apply(cur, n, N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS)   # blank frames: unpainted pixels are black anyway
-        self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES, "records": n}
+        apply(cur, n, fmt, res.palette, N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS)   # blank frames: unpainted pixels are black anyway
+        self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES[fmt], "records": n,
+                              "format": "palette" if fmt == N.OVERLAY_PALETTE else "bgr"}
         return idx, frames
 
     def _sparse_ok(self):

@@ -62,15 +62,16 @@ struct ClipArgs {
 __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
                             const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
-                            unsigned *__restrict__ overlay_count) {
+                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
     if (i < stats_words) stats[i] = 0u;
     if (i == 0 && overlay_count) *overlay_count = 0u;
     if (i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
+    // lut[ordinal+1] = B | G << 8 | R << 16 | palette entry << 24 (the raster never looks at the top byte of a colour)
     if (i <= n_inst) lut[i] = i == 0 ? 0u
                                       : (unsigned)inst_bgr[3 * (i - 1)] | ((unsigned)inst_bgr[3 * (i - 1) + 1] << 8) |
-                                            ((unsigned)inst_bgr[3 * (i - 1) + 2] << 16);
+                                            ((unsigned)inst_bgr[3 * (i - 1) + 2] << 16) | (inst_palette ? (unsigned)inst_palette[i - 1] << 24 : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
@@ -560,56 +561,58 @@ struct RasterArgs {
     const unsigned *lists;                 // [4][n_items]: buckets with >= 2048 / >= 256 / >= 1 records (claimed dynamically, in this order) | empty buckets (dealt round-robin)
     const unsigned *list_counts;           // [4]
     unsigned *work_counter;                // claims of active buckets beyond the first three of every CTA
-    uint4 *ov_records;                     // MODE 2: sparse output, 2 x uint4 per cama_overlay_record
+    void *ov_records;                      // MODE 2 / 3: sparse output records
     unsigned *ov_count;
     long long ov_cap;
 };
 
-// Sparse output (MODE 2): lit 8-pixel chunks are staged per warp and appended to the global record
-// list >= kOvFlush at a time (one returning atomic per flush).
+// Sparse output (MODE 2: 32-byte BGR records, MODE 3: 12-byte palette records): lit 8-pixel chunks are
+// staged per warp and appended to the global record list >= kOvFlush at a time (one returning atomic
+// per flush).  RW = 32-bit words per record.
 constexpr int kOvFlush = 64;
 constexpr int kOvCap = kOvFlush + 32;
 struct OvStage {
-    uint4 rec[kOvCap][2];
+    unsigned words[kOvCap * 8];
     unsigned count;
     unsigned pad[3];
 };
 struct OvSink {
     OvStage *st;
-    uint4 *records;
+    unsigned *records;
     unsigned *count;
     long long cap;
 };
 
+template <int RW>
 __device__ __forceinline__ void ov_flush(const OvSink &o) {
     const int lane = threadIdx.x & 31;
     const unsigned n = o.st->count;
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(o.count, n);
     const long long b = __shfl_sync(kFull, base, 0);
-    for (unsigned i = lane; i < 2u * n; i += 32) {
-        const long long pos = b + (i >> 1);
-        if (pos < o.cap) o.records[pos * 2 + (i & 1u)] = o.st->rec[i >> 1][i & 1u];
-    }
+    const long long room = o.cap > b ? o.cap - b : 0;                  // records that still fit
+    const unsigned n_words = (unsigned)min((long long)n, room) * RW;
+    for (unsigned i = lane; i < n_words; i += 32) o.records[b * RW + i] = o.st->words[i];
     __syncwarp();
     if (lane == 0) o.st->count = 0;
     __syncwarp();
 }
 
-// warp-collective: every lane calls it; lanes with `lit` contribute one record
-__device__ __forceinline__ void ov_append(const OvSink &o, bool lit, unsigned chunk, unsigned mask, const unsigned (&w)[6]) {
+// warp-collective: every lane calls it; lanes with `lit` contribute one record of RW words
+template <int RW>
+__device__ __forceinline__ void ov_append(const OvSink &o, bool lit, const unsigned (&rec)[RW]) {
     const unsigned bal = __ballot_sync(kFull, lit);
     if (bal == 0) return;
     const int lane = threadIdx.x & 31;
     const unsigned slot = o.st->count + __popc(bal & ((1u << lane) - 1u));
     if (lit) {
-        o.st->rec[slot][0] = make_uint4(chunk, mask, w[0], w[1]);
-        o.st->rec[slot][1] = make_uint4(w[2], w[3], w[4], w[5]);
+#pragma unroll
+        for (int k = 0; k < RW; ++k) o.st->words[slot * RW + k] = rec[k];
     }
     __syncwarp();
     if (lane == 0) o.st->count += (unsigned)__popc(bal);
     __syncwarp();
-    if (o.st->count >= (unsigned)kOvFlush) ov_flush(o);
+    if (o.st->count >= (unsigned)kOvFlush) ov_flush<RW>(o);
 }
 
 // 8 packed 24-bit values -> the 24 bytes of 8 BGR pixels (6 words), one byte-permute per word
@@ -658,7 +661,21 @@ __device__ __forceinline__ void store_row(const unsigned *__restrict__ lut, cons
 #pragma unroll
             for (int k = 0; k < 4; ++k) mask |= ((m[k] & 0xffffu) ? 1u << (2 * k) : 0u) | ((m[k] >> 16) ? 2u << (2 * k) : 0u);
         }
-        ov_append(ov, lit, chunk, mask, w);
+        const unsigned rec[8] = {chunk, mask, w[0], w[1], w[2], w[3], w[4], w[5]};
+        ov_append<8>(ov, lit, rec);
+        return;
+    }
+    if (MODE == 3) {                           // sparse output, palette form: one byte per pixel (lut[id] >> 24, 0 = not painted)
+        const bool lit = lane_on && (m[0] | m[1] | m[2] | m[3]) != 0u;
+        unsigned rec[3] = {chunk, 0u, 0u};
+        if (lit) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned p_lo = __ldg(lut + (m[k] & 0xffffu)) >> 24, p_hi = __ldg(lut + (m[k] >> 16)) >> 24;
+                rec[1 + (k >> 1)] |= (p_lo | (p_hi << 8)) << (16 * (k & 1));
+            }
+        }
+        ov_append<3>(ov, lit, rec);
         return;
     }
     if (!lane_on) return;
@@ -749,9 +766,9 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     unsigned *hits = reinterpret_cast<unsigned *>(smem + plane_bytes);
     unsigned char *zeros = smem + plane_bytes + kHitBytes;
     OvSink ov{};
-    if (MODE == 2) {                                                     // per-warp staging of sparse records, after the zeros
+    if (MODE >= 2) {                                                     // per-warp staging of sparse records, after the zeros
         ov.st = reinterpret_cast<OvStage *>(zeros + zero_bytes) + warp;
-        ov.records = a.ov_records; ov.count = a.ov_count; ov.cap = a.ov_cap;
+        ov.records = reinterpret_cast<unsigned *>(a.ov_records); ov.count = a.ov_count; ov.cap = a.ov_cap;
         if (lane == 0) ov.st->count = 0;
     }
     const bool inplace = MODE == 1 && a.bg == a.frames;
@@ -930,7 +947,8 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         a2 = (unsigned)s_claim[it & 1];
     }
     issue_empties(0xffffffffu);
-    if (MODE == 2 && ov.st->count > 0u) ov_flush(ov);
+    if (MODE == 2 && ov.st->count > 0u) ov_flush<8>(ov);
+    if (MODE == 3 && ov.st->count > 0u) ov_flush<3>(ov);
     // the shared zeros must stay valid until the last bulk stores have read them
     if (MODE == 0 && lane == 0) bulk_wait_group_read<0>();
 }
@@ -1077,6 +1095,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_REQUIRE(!d->background, "the sparse overlay output takes no background (the host composites)");
         CAMA_REQUIRE(d->overlay_count && d->overlay_capacity > 0, "overlay_count / overlay_capacity missing");
         CAMA_REQUIRE(((uintptr_t)d->overlay_records & 15) == 0, "overlay_records must be 16-byte aligned");
+        CAMA_REQUIRE(d->overlay_format == CAMA_OVERLAY_BGR || d->overlay_format == CAMA_OVERLAY_PALETTE, "bad overlay_format");
+        CAMA_REQUIRE(d->overlay_format != CAMA_OVERLAY_PALETTE || d->n_instances == 0 || d->instance_palette, "the palette overlay format needs instance_palette");
         CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width / 8 < (1ll << 32), "clip too large for 32-bit chunk indices");
     }
     CAMA_REQUIRE(d->n_vertices == 0 || d->vertices, "vertices is NULL");
@@ -1122,7 +1142,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
                                                                d->instance_bgr, d->n_instances, lut,
                                                                binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : nullptr, zero_words,
                                                                reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                                                               d->overlay_records ? d->overlay_count : nullptr);
+                                                               d->overlay_records ? d->overlay_count : nullptr, d->instance_palette);
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
@@ -1194,9 +1214,14 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
     if (d->overlay_records) {
-        r.ov_records = reinterpret_cast<uint4 *>(d->overlay_records); r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
-        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        binned_raster_kernel<2><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+        r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
+        if (d->overlay_format == CAMA_OVERLAY_PALETTE) {
+            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+            binned_raster_kernel<3><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+        } else {
+            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+            binned_raster_kernel<2><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+        }
     } else if (d->background) {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
         binned_raster_kernel<1><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);

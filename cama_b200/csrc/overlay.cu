@@ -1,6 +1,7 @@
 // libcama_b200: host side of the sparse overlay output — draws the lit 8-pixel chunks the GPU
 // produced into host frames (the in-place draw of /root/reference/cama/reproject.py:246-257 for
-// pixels whose colour is already decided).  Pure byte movement, OpenMP over the records.
+// pixels whose colour is already decided), either plain [F,C,H,W,3] frames or the 2x3 camera mosaic of
+// /root/reference/cama/tools.py:22-25.  Pure byte movement, OpenMP over the records.
 #include <cstring>
 #include <omp.h>
 
@@ -8,85 +9,125 @@
 
 using namespace cama;
 
-extern "C" int cama_overlay_apply_host(const cama_overlay_record *records, int64_t n, uint8_t *frames, int64_t n_chunks,
-                                       int op, int n_threads) {
-    CAMA_REQUIRE(n >= 0 && n_chunks >= 0, "negative size");
-    CAMA_REQUIRE(op >= CAMA_OVERLAY_DRAW && op <= CAMA_OVERLAY_BLANK_CHUNKS, "bad op");
-    if (n == 0) return CAMA_OK;
-    CAMA_REQUIRE(records && frames, "NULL buffer");
-    int threads = n_threads > 0 ? n_threads : omp_get_max_threads();
-    if (n < 4096) threads = 1;
-    constexpr int64_t kAhead = 24;             // the destination lines are scattered: prefetch them for writing
-#pragma omp parallel for num_threads(threads) schedule(static)
-    for (int64_t i = 0; i < n; ++i) {
-        if (i + kAhead < n) {
-            const uint32_t c = records[i + kAhead].chunk;
-            if ((int64_t)c < n_chunks) __builtin_prefetch(frames + (size_t)c * 24, 1, 0);
-        }
-        const cama_overlay_record &r = records[i];
-        if ((int64_t)r.chunk >= n_chunks) continue;
-        uint8_t *dst = frames + (size_t)r.chunk * 24;
-        const unsigned mask = r.mask & 0xffu;
-        if (op == CAMA_OVERLAY_DRAW_CHUNKS || (op == CAMA_OVERLAY_DRAW && mask == 0xffu)) {
-            memcpy(dst, r.bgr, 24);
-        } else if (op == CAMA_OVERLAY_BLANK_CHUNKS || (op == CAMA_OVERLAY_BLANK && mask == 0xffu)) {
-            memset(dst, 0, 24);
-        } else {
-            const bool blank = op == CAMA_OVERLAY_BLANK;
-            for (int k = 0; k < 8; ++k) {
-                if ((mask >> k) & 1u) {
-                    dst[3 * k] = blank ? 0 : r.bgr[3 * k];
-                    dst[3 * k + 1] = blank ? 0 : r.bgr[3 * k + 1];
-                    dst[3 * k + 2] = blank ? 0 : r.bgr[3 * k + 2];
-                }
+namespace {
+
+struct Target {
+    uint8_t *pixels;
+    int64_t n_chunks, chunks_per_row, chunks_per_image;
+    int n_cams, height, width, grid_cols;
+    const int32_t *tile_of_cam;
+    size_t mosaic_pitch, mosaic_frame;
+
+    inline uint8_t *chunk_ptr(uint32_t chunk) const {
+        if (grid_cols == 0) return pixels + (size_t)chunk * 24;
+        const int64_t image = chunk / chunks_per_image, within = chunk % chunks_per_image;
+        const int tile = tile_of_cam[image % n_cams];
+        const int64_t y = within / chunks_per_row, x = (within % chunks_per_row) * 8;
+        return pixels + (size_t)(image / n_cams) * mosaic_frame + ((size_t)(tile / grid_cols) * height + y) * mosaic_pitch +
+               ((size_t)(tile % grid_cols) * width + x) * 3;
+    }
+};
+
+inline void apply_one(uint8_t *dst, const uint8_t *bgr, unsigned mask, int op) {
+    if (op == CAMA_OVERLAY_DRAW_CHUNKS || (op == CAMA_OVERLAY_DRAW && mask == 0xffu)) {
+        memcpy(dst, bgr, 24);
+    } else if (op == CAMA_OVERLAY_BLANK_CHUNKS || (op == CAMA_OVERLAY_BLANK && mask == 0xffu)) {
+        memset(dst, 0, 24);
+    } else {
+        const bool blank = op == CAMA_OVERLAY_BLANK;
+        for (int k = 0; k < 8; ++k) {
+            if ((mask >> k) & 1u) {
+                dst[3 * k] = blank ? 0 : bgr[3 * k];
+                dst[3 * k + 1] = blank ? 0 : bgr[3 * k + 1];
+                dst[3 * k + 2] = blank ? 0 : bgr[3 * k + 2];
             }
         }
     }
-    return CAMA_OK;
 }
 
-// Same, into the 2x3-style camera mosaic the reference builds with np.concatenate before encoding
-// (/root/reference/cama/tools.py:22-25): frame f is one [rows*H, cols*W, 3] image, camera c sits at
-// tile tile_of_cam[c] (row-major).  Writing there directly makes concate_image a no-op.
-extern "C" int cama_overlay_apply_host_mosaic(const cama_overlay_record *records, int64_t n, uint8_t *mosaic, int64_t n_frames,
-                                              int n_cams, int height, int width, int grid_cols, const int32_t *tile_of_cam,
-                                              int op, int n_threads) {
-    CAMA_REQUIRE(n >= 0 && n_frames >= 0 && n_cams > 0 && height > 0 && width > 0 && grid_cols > 0, "bad size");
-    CAMA_REQUIRE(width % 8 == 0, "width must be a multiple of 8");
+}  // namespace
+
+extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int format, const uint8_t *palette_bgr,
+                                       const cama_overlay_target *target, int op, int n_threads) {
+    CAMA_REQUIRE(n >= 0, "negative size");
     CAMA_REQUIRE(op >= CAMA_OVERLAY_DRAW && op <= CAMA_OVERLAY_BLANK_CHUNKS, "bad op");
+    CAMA_REQUIRE(format == CAMA_OVERLAY_BGR || format == CAMA_OVERLAY_PALETTE, "bad format");
     if (n == 0) return CAMA_OK;
-    CAMA_REQUIRE(records && mosaic && tile_of_cam, "NULL buffer");
-    const int grid_rows = (n_cams + grid_cols - 1) / grid_cols;
-    for (int c = 0; c < n_cams; ++c) CAMA_REQUIRE(tile_of_cam[c] >= 0 && tile_of_cam[c] < grid_rows * grid_cols, "tile_of_cam[%d] out of range", c);
-    const int64_t chunks_per_row = width / 8, chunks_per_image = chunks_per_row * height;
-    const int64_t n_chunks = n_frames * n_cams * chunks_per_image;
-    const size_t mosaic_pitch = (size_t)grid_cols * width * 3, mosaic_frame = mosaic_pitch * grid_rows * height;
+    CAMA_REQUIRE(records && target && target->pixels, "NULL buffer");
+    CAMA_REQUIRE(format != CAMA_OVERLAY_PALETTE || palette_bgr, "palette_bgr is NULL");
+    CAMA_REQUIRE(target->n_frames >= 0 && target->n_cams > 0 && target->height > 0 && target->width > 0 && target->width % 8 == 0 &&
+                     target->grid_cols >= 0, "bad target shape");
+    Target t{};
+    t.pixels = target->pixels;
+    t.n_cams = target->n_cams; t.height = target->height; t.width = target->width; t.grid_cols = target->grid_cols;
+    t.chunks_per_row = target->width / 8;
+    t.chunks_per_image = t.chunks_per_row * target->height;
+    t.n_chunks = target->n_frames * target->n_cams * t.chunks_per_image;
+    t.tile_of_cam = target->tile_of_cam;
+    if (t.grid_cols > 0) {
+        CAMA_REQUIRE(t.tile_of_cam, "tile_of_cam is NULL");
+        const int grid_rows = (t.n_cams + t.grid_cols - 1) / t.grid_cols;
+        for (int c = 0; c < t.n_cams; ++c)
+            CAMA_REQUIRE(t.tile_of_cam[c] >= 0 && t.tile_of_cam[c] < grid_rows * t.grid_cols, "tile_of_cam[%d] out of range", c);
+        t.mosaic_pitch = (size_t)t.grid_cols * t.width * 3;
+        t.mosaic_frame = t.mosaic_pitch * grid_rows * t.height;
+    }
     int threads = n_threads > 0 ? n_threads : omp_get_max_threads();
     if (n < 4096) threads = 1;
+    constexpr int64_t kAhead = 24;             // the destination lines are scattered: prefetch them for writing
+    if (format == CAMA_OVERLAY_BGR) {
+        const cama_overlay_record *rec = static_cast<const cama_overlay_record *>(records);
 #pragma omp parallel for num_threads(threads) schedule(static)
-    for (int64_t i = 0; i < n; ++i) {
-        const cama_overlay_record &r = records[i];
-        if ((int64_t)r.chunk >= n_chunks) continue;
-        const int64_t image = r.chunk / chunks_per_image, within = r.chunk % chunks_per_image;
-        const int64_t f = image / n_cams;
-        const int tile = tile_of_cam[image % n_cams];
-        const int64_t y = within / chunks_per_row, x = (within % chunks_per_row) * 8;
-        uint8_t *dst = mosaic + (size_t)f * mosaic_frame + ((size_t)(tile / grid_cols) * height + y) * mosaic_pitch +
-                       ((size_t)(tile % grid_cols) * width + x) * 3;
-        const unsigned mask = r.mask & 0xffu;
-        if (op == CAMA_OVERLAY_DRAW_CHUNKS || (op == CAMA_OVERLAY_DRAW && mask == 0xffu)) {
-            memcpy(dst, r.bgr, 24);
-        } else if (op == CAMA_OVERLAY_BLANK_CHUNKS || (op == CAMA_OVERLAY_BLANK && mask == 0xffu)) {
-            memset(dst, 0, 24);
-        } else {
-            const bool blank = op == CAMA_OVERLAY_BLANK;
-            for (int k = 0; k < 8; ++k) {
-                if ((mask >> k) & 1u) {
-                    dst[3 * k] = blank ? 0 : r.bgr[3 * k];
-                    dst[3 * k + 1] = blank ? 0 : r.bgr[3 * k + 1];
-                    dst[3 * k + 2] = blank ? 0 : r.bgr[3 * k + 2];
-                }
+        for (int64_t i = 0; i < n; ++i) {
+            if (i + kAhead < n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
+            if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
+            apply_one(t.chunk_ptr(rec[i].chunk), rec[i].bgr, rec[i].mask & 0xffu, op);
+        }
+    } else {
+        const cama_overlay_record_palette *rec = static_cast<const cama_overlay_record_palette *>(records);
+        uint32_t pal32[256];                                  // packed B | G << 8 | R << 16, entry 0 (not painted) = black
+        pal32[0] = 0;
+        int used = 1;                                          // entries above the last non-black one are never referenced in practice
+        for (int e = 1; e < 256; ++e) {
+            pal32[e] = (uint32_t)palette_bgr[3 * e] | ((uint32_t)palette_bgr[3 * e + 1] << 8) | ((uint32_t)palette_bgr[3 * e + 2] << 16);
+            if (pal32[e]) used = e + 1;
+        }
+        // two pixels per lookup: pair[a | b << 8] = the 6 bytes of pixel a followed by pixel b
+        static thread_local uint64_t *pair = nullptr;
+        static thread_local int pair_used = 0;                 // entries >= pair_used (either half) are zero = black
+        if (!pair) pair = new uint64_t[65536]();
+        const int fill = used > pair_used ? used : pair_used;  // also overwrites what an earlier, larger palette left behind
+        if (op != CAMA_OVERLAY_BLANK_CHUNKS) {
+            for (int b2 = 0; b2 < 256; ++b2) {                 // every pair with a non-black half (entries >= used are black)
+                const int a_end = b2 < fill ? 256 : fill;
+                for (int a2 = 0; a2 < a_end; ++a2) pair[a2 | b2 << 8] = (uint64_t)pal32[a2] | (uint64_t)pal32[b2] << 24;
             }
+            pair_used = used;
+        }
+        const uint64_t *pair_tab = pair;
+#pragma omp parallel for num_threads(threads) schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            if (i + kAhead < n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
+            if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
+            uint8_t *dst = t.chunk_ptr(rec[i].chunk);
+            if (op == CAMA_OVERLAY_BLANK_CHUNKS) {
+                memset(dst, 0, 24);
+                continue;
+            }
+            const uint8_t *ix = rec[i].index;
+            uint16_t pr[4];
+            memcpy(pr, ix, 8);
+            const uint64_t p01 = pair_tab[pr[0]], p23 = pair_tab[pr[1]], p45 = pair_tab[pr[2]], p67 = pair_tab[pr[3]];
+            const uint64_t w[3] = {p01 | p23 << 48, p23 >> 16 | p45 << 32, p45 >> 32 | p67 << 16};
+            if (op == CAMA_OVERLAY_DRAW_CHUNKS) {              // the 24 bytes, assembled in registers (little endian)
+                memcpy(dst, w, 24);
+                continue;
+            }
+            uint8_t bgr[24];
+            memcpy(bgr, w, 24);
+            unsigned mask = 0;
+            for (int k = 0; k < 8; ++k) mask |= (ix[k] ? 1u : 0u) << k;
+            apply_one(dst, bgr, mask, op);
         }
     }
     return CAMA_OK;

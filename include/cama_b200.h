@@ -178,6 +178,14 @@ typedef struct cama_overlay_record {
     uint8_t bgr[24];
 } cama_overlay_record;
 
+/* Compact form of the same (CAMA_OVERLAY_PALETTE), usable when the instances have at most 255 distinct
+ * colours: one byte per pixel, 0 = not painted, k = palette entry k (`instance_palette` of cama_clip_desc). */
+typedef struct cama_overlay_record_palette {
+    uint32_t chunk;
+    uint8_t index[8];
+} cama_overlay_record_palette;
+enum { CAMA_OVERLAY_BGR = 0, CAMA_OVERLAY_PALETTE = 1 };
+
 typedef struct cama_clip_desc {
     uint32_t struct_bytes;          /* sizeof(cama_clip_desc), ABI guard */
     int32_t mode;                   /* CAMA_CLIP_* */
@@ -205,9 +213,12 @@ typedef struct cama_clip_desc {
      * half-extent {cx,cy,cz,ex,ey,ez} of an axis-aligned box containing them.  A (tile, frame) whose
      * transformed box misses the crop box is skipped as a whole; results are unchanged. */
     const double *tile_bounds;      /* device float64 [ceil(n_vertices / CAMA_TILE_VERTICES), 6] or NULL */
-    cama_overlay_record *overlay_records; /* device [overlay_capacity] or NULL */
+    void *overlay_records;          /* device [overlay_capacity] records of overlay_format, or NULL */
     uint32_t *overlay_count;        /* device [1]: records appended (may exceed the capacity: the excess was dropped) */
     int64_t overlay_capacity;
+    int32_t overlay_format;         /* CAMA_OVERLAY_BGR | CAMA_OVERLAY_PALETTE (needs instance_palette) */
+    int32_t reserved0;
+    const uint8_t *instance_palette; /* device uint8 [n_instances]: palette entry (1..255) of every instance, or NULL */
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -233,22 +244,28 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *desc, const void *
 
 /* ---- host side of the sparse output ------------------------------------------------------------ */
 
-/* Applies `n` overlay records to host frames uint8 [n_frames,n_cams,H,W,3]; records whose chunk is
- * >= n_chunks are ignored.  DRAW is the in-place draw of CameraManager.render_maps
- * (cama/reproject.py:246-257) for pixels whose colour the GPU has already decided: only painted pixels
- * are written.  BLANK sets them to 0,0,0.  The *_CHUNKS variants write all 24 bytes of each chunk: valid
- * when the unpainted pixels of the frames are black anyway (frames without a background), and cheaper.
- * Only moves bytes (n_threads <= 0: all cores). */
-enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS = 2, CAMA_OVERLAY_BLANK_CHUNKS = 3 };
-int cama_overlay_apply_host(const cama_overlay_record *records, int64_t n, uint8_t *frames, int64_t n_chunks,
-                            int op, int n_threads);
+/* Where overlay records are drawn: host frames uint8 [n_frames,n_cams,H,W,3] (grid_cols == 0), or the camera
+ * mosaic that VideoGenerator.concate_image (cama/tools.py:22-25) builds before encoding: uint8
+ * [n_frames, rows*H, grid_cols*W, 3] with rows = ceil(n_cams / grid_cols) and camera c in tile tile_of_cam[c]
+ * (row-major) — drawing there makes concate_image a no-op. */
+typedef struct cama_overlay_target {
+    uint8_t *pixels;
+    int64_t n_frames;
+    int32_t n_cams, height, width;
+    int32_t grid_cols;              /* 0: plain frames */
+    const int32_t *tile_of_cam;     /* host int32 [n_cams], only for the mosaic */
+} cama_overlay_target;
 
-/* Same, into the camera mosaic that VideoGenerator.concate_image (cama/tools.py:22-25) builds before
- * encoding: `mosaic` is uint8 [n_frames, rows*H, grid_cols*W, 3] with rows = ceil(n_cams / grid_cols), and
- * camera c occupies tile tile_of_cam[c] (row-major).  Drawing there makes concate_image a no-op. */
-int cama_overlay_apply_host_mosaic(const cama_overlay_record *records, int64_t n, uint8_t *mosaic, int64_t n_frames,
-                                   int n_cams, int height, int width, int grid_cols, const int32_t *tile_of_cam,
-                                   int op, int n_threads);
+/* Applies `n` overlay records (format CAMA_OVERLAY_BGR: cama_overlay_record; CAMA_OVERLAY_PALETTE:
+ * cama_overlay_record_palette + palette_bgr, host uint8 [256,3], entry 0 unused) to the target; records whose
+ * chunk lies outside it are ignored.  DRAW is the in-place draw of CameraManager.render_maps
+ * (cama/reproject.py:246-257) for pixels whose colour the GPU has already decided: only painted pixels are
+ * written.  BLANK sets them to 0,0,0.  The *_CHUNKS variants write all 24 bytes of each chunk: valid when the
+ * unpainted pixels are black anyway (frames without a background), and cheaper.  Only moves bytes
+ * (n_threads <= 0: all cores). */
+enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS = 2, CAMA_OVERLAY_BLANK_CHUNKS = 3 };
+int cama_overlay_apply_host(const void *records, int64_t n, int format, const uint8_t *palette_bgr,
+                            const cama_overlay_target *target, int op, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -468,22 +468,36 @@ def test_sparse_transfer_equals_dense(rt, config2_clip, clip_root):
 
 
 def test_overlay_records_are_unique_chunks(rt):
-    """Raw C-ABI sparse output: every lit chunk exactly once, masks/colours consistent with the dense frames."""
+    """Raw C-ABI sparse output, both record formats: every lit chunk exactly once, masks/colours/palette
+    entries consistent with the dense frames."""
+    from cama_b200 import _native as N
     g = load_golden("golden_clip_nuscenes_slerp.npz")
     r = renderer_for(g)
     res = r.resident(golden_instances(g))
-    records, n = r.render_overlay(res, to_dev(g["world2chassis"].reshape(-1, 16)))
+    assert res.palette is not None and int((res.palette.any(1)).sum()) == 2          # lane grey + crosswalk yellow
+    dense = g["frames"].reshape(-1, 8, 3)
+    lit_chunks = set(np.flatnonzero(dense.reshape(len(dense), -1).any(1)).tolist())
+    w2c = to_dev(g["world2chassis"].reshape(-1, 16))
+    # 32-byte BGR records
+    records, n, fmt = r.render_overlay(res, w2c, fmt=N.OVERLAY_BGR)
+    assert fmt == N.OVERLAY_BGR and tuple(records.shape[1:]) == (8,)
     rec = records[:n].cpu().numpy().view(np.uint8).reshape(n, 32)
     chunk = rec[:, :4].copy().view("<u4")[:, 0]
     mask = rec[:, 4:8].copy().view("<u4")[:, 0]
     assert len(np.unique(chunk)) == n and mask.max() <= 0xFF and mask.min() >= 1
-    dense = g["frames"].reshape(-1, 8, 3)
-    lit_chunks = np.flatnonzero(dense.reshape(len(dense), -1).any(1))
-    assert set(lit_chunks) <= set(chunk.tolist())              # (a chunk painted pure black would be a record but not lit)
+    assert lit_chunks <= set(chunk.tolist())                   # (a chunk painted pure black would be a record but not lit)
     bits = (mask[:, None] >> np.arange(8)) & 1
     bgr = rec[:, 8:].reshape(n, 8, 3)
     assert np.array_equal(bgr * bits[:, :, None], dense[chunk] * bits[:, :, None])
     assert not (bgr * (1 - bits)[:, :, None]).any() and not (dense[chunk] * (1 - bits)[:, :, None]).any()
+    # 12-byte palette records (the default when the instances have <= 255 colours)
+    records, n2, fmt = r.render_overlay(res, w2c)
+    assert fmt == N.OVERLAY_PALETTE and n2 == n and tuple(records.shape[1:]) == (3,)
+    rec = records[:n2].cpu().numpy().view(np.uint8).reshape(n2, 12)
+    chunk2 = rec[:, :4].copy().view("<u4")[:, 0]
+    index = rec[:, 4:]
+    assert sorted(chunk2.tolist()) == sorted(chunk.tolist())
+    assert np.array_equal(res.palette[index], dense[chunk2]) and index.max() <= 2
 
 
 def test_device_densify_matches_host_and_oracle(rt):

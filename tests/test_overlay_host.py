@@ -2,86 +2,98 @@
 import ctypes
 
 import numpy as np
+import pytest
 
 from cama_b200 import _native as N
+from cama_b200.tools import MOSAIC_ROWS, concate_image
 
 REC = np.dtype([("chunk", "<u4"), ("mask", "<u4"), ("bgr", "u1", (24,))])
+REC_PAL = np.dtype([("chunk", "<u4"), ("index", "u1", (8,))])
 
 
-def apply(records, frames, erase=0, threads=0):
-    assert REC.itemsize == N.OVERLAY_RECORD_BYTES
-    N.check(N.lib().cama_overlay_apply_host(records.ctypes.data, len(records), frames.ctypes.data, frames.size // 24, erase, threads))
+def apply(records, frames, op=0, threads=0, fmt=N.OVERLAY_BGR, palette=None, tiles=None, shape=None):
+    assert REC.itemsize == N.OVERLAY_RECORD_BYTES[N.OVERLAY_BGR] and REC_PAL.itemsize == N.OVERLAY_RECORD_BYTES[N.OVERLAY_PALETTE]
+    F, C, H, W = shape if shape is not None else frames.shape[:4]
+    target = N.OverlayTarget(frames.ctypes.data, F, C, H, W, 0 if tiles is None else 3, None if tiles is None else tiles.ctypes.data)
+    return N.lib().cama_overlay_apply_host(records.ctypes.data if records is not None else None, len(records) if records is not None else 5,
+                                           fmt, None if palette is None else palette.ctypes.data, ctypes.byref(target), op, threads)
 
 
-def reference(records, frames, erase=0):
+def reference(records, frames, op=0, palette=None):
     flat = frames.reshape(-1, 8, 3)
-    for r in records:  # noqa
+    for r in records:
         if r["chunk"] >= len(flat):
             continue
+        if palette is None:
+            mask, bgr = int(r["mask"]), r["bgr"].reshape(8, 3)
+        else:
+            mask = sum(1 << k for k in range(8) if r["index"][k])
+            bgr = np.where(r["index"][:, None] > 0, palette[r["index"]], 0)
         for k in range(8):
-            if (r["mask"] >> k) & 1:
-                flat[r["chunk"], k] = 0 if erase else r["bgr"].reshape(8, 3)[k]
+            whole = op in (N.OVERLAY_DRAW_CHUNKS, N.OVERLAY_BLANK_CHUNKS)
+            if whole or (mask >> k) & 1:
+                flat[r["chunk"], k] = 0 if op in (N.OVERLAY_BLANK, N.OVERLAY_BLANK_CHUNKS) else bgr[k]
 
 
-def test_apply_matches_numpy_and_erases():
+def make_records(rng, n_chunks, n, fmt):
+    recs = np.zeros(n, REC if fmt == N.OVERLAY_BGR else REC_PAL)
+    recs["chunk"] = rng.permutation(n_chunks)[:n]                  # every lit chunk appears once, as the GPU emits them
+    if fmt == N.OVERLAY_BGR:
+        recs["mask"] = rng.integers(0, 256, n)
+        recs["mask"][:10] = 0xFF
+        recs["bgr"] = rng.integers(0, 256, (n, 24))
+        recs["bgr"] *= ((recs["mask"][:, None] >> (np.arange(24) // 3)) & 1).astype(np.uint8)     # unpainted pixels carry zeros
+    else:
+        recs["index"] = rng.integers(0, 4, (n, 8)) * (rng.random((n, 8)) < 0.6)
+        recs["index"][:10] = 2
+    return recs
+
+
+@pytest.mark.parametrize("fmt", [N.OVERLAY_BGR, N.OVERLAY_PALETTE])
+def test_apply_matches_numpy(fmt):
     rng = np.random.default_rng(0)
-    frames = rng.integers(0, 256, size=(2, 3, 16, 64, 3), dtype=np.uint8)
-    n_chunks = frames.size // 24
-    recs = np.zeros(9000, REC)                                     # > 4096: the threaded path
     frames = rng.integers(0, 256, size=(4, 6, 64, 128, 3), dtype=np.uint8)
     n_chunks = frames.size // 24
-    recs["chunk"] = rng.permutation(n_chunks)[:9000]               # every lit chunk appears once, as the GPU emits them
-    recs["mask"] = rng.integers(0, 256, len(recs))
-    recs["mask"][:10] = 0xFF
-    recs["bgr"] = rng.integers(0, 256, (len(recs), 24))
-    extra = np.zeros(1, REC)
-    extra["chunk"], extra["mask"], extra["bgr"] = n_chunks + 5, 0xFF, 7
-    recs = np.concatenate([recs, extra])                           # out of range: ignored
-    want = frames.copy()
-    reference(recs, want)
-    got = frames.copy()
-    apply(recs, got)
-    assert np.array_equal(got, want)
-    single = frames.copy()
-    apply(recs[:100], single, threads=1)
-    want1 = frames.copy()
-    reference(recs[:100], want1)
-    assert np.array_equal(single, want1)
-    # erase: painted pixels -> 0, everything else untouched
-    reference(recs, want, erase=1)
-    apply(recs, got, erase=1)
-    assert np.array_equal(got, want)
-    # whole-chunk variants: 24 bytes per record regardless of the mask
-    blank = np.zeros_like(frames)
-    apply(recs[:-1], blank, erase=N.OVERLAY_DRAW_CHUNKS)
-    assert np.array_equal(blank.reshape(-1, 24)[recs["chunk"][:-1]], recs["bgr"][:-1])
-    apply(recs[:-1], blank, erase=N.OVERLAY_BLANK_CHUNKS)
-    assert not blank.any()
-    assert N.lib().cama_overlay_apply_host(recs.ctypes.data, 5, got.ctypes.data, n_chunks, 7, 0) == N.CAMA_E_INVALID
-    assert N.lib().cama_overlay_apply_host(None, 5, got.ctypes.data, n_chunks, 0, 0) == N.CAMA_E_INVALID
-    N.check(N.lib().cama_overlay_apply_host(None, 0, None, 0, 0, 0))
+    palette = np.zeros((256, 3), np.uint8)
+    palette[1:4] = [[211, 211, 211], [0, 215, 255], [9, 8, 7]]
+    pal = palette if fmt == N.OVERLAY_PALETTE else None
+    recs = make_records(rng, n_chunks, 9000, fmt)                   # > 4096: the threaded path
+    extra = np.zeros(1, recs.dtype)
+    extra["chunk"] = n_chunks + 5
+    recs = np.concatenate([recs, extra])                            # out of range: ignored
+    for op in (N.OVERLAY_DRAW, N.OVERLAY_BLANK, N.OVERLAY_DRAW_CHUNKS, N.OVERLAY_BLANK_CHUNKS):
+        want, got = frames.copy(), frames.copy()
+        reference(recs, want, op, pal)
+        N.check(apply(recs, got, op, fmt=fmt, palette=pal))
+        assert np.array_equal(got, want), op
+        single = frames.copy()
+        N.check(apply(recs[:100], single, op, threads=1, fmt=fmt, palette=pal))
+        want1 = frames.copy()
+        reference(recs[:100], want1, op, pal)
+        assert np.array_equal(single, want1), op
+    assert apply(recs, frames, 7, fmt=fmt, palette=pal) == N.CAMA_E_INVALID
+    assert apply(None, frames, 0, fmt=fmt, palette=pal) == N.CAMA_E_INVALID
+    if fmt == N.OVERLAY_PALETTE:
+        assert apply(recs, frames, 0, fmt=fmt, palette=None) == N.CAMA_E_INVALID
+    N.check(apply(recs[:0], frames, 0, fmt=fmt, palette=pal))
 
 
 def test_mosaic_layout_matches_concate_image():
     """Drawing into the 2x3 mosaic == drawing into [F,C,H,W,3] frames and np.concatenate (reference cama/tools.py:22-25)."""
-    from cama_b200.tools import MOSAIC_ROWS, concate_image
     rng = np.random.default_rng(4)
     F, C, H, W = 3, 6, 16, 32
     names = ["camera_rear", "camera_front_left", "camera_front", "camera_front_right", "camera_rear_left", "camera_rear_right"]   # any camera_list order
     order = [n for row in MOSAIC_ROWS for n in row]
     tiles = np.array([order.index(n) for n in names], np.int32)
-    n_chunks = F * C * H * W // 8
-    recs = np.zeros(600, REC)
-    recs["chunk"] = rng.permutation(n_chunks)[:600]
-    recs["mask"] = rng.integers(1, 256, 600)
-    recs["bgr"] = rng.integers(0, 256, (600, 24))
+    recs = make_records(rng, F * C * H * W // 8, 600, N.OVERLAY_BGR)
     frames = rng.integers(0, 256, size=(F, C, H, W, 3), dtype=np.uint8)
     mosaic = np.stack([concate_image({n: frames[f, c] for c, n in enumerate(names)}) for f in range(F)])
     assert mosaic.shape == (F, 2 * H, 3 * W, 3)
     for op in (N.OVERLAY_DRAW, N.OVERLAY_BLANK, N.OVERLAY_DRAW_CHUNKS, N.OVERLAY_BLANK_CHUNKS):
-        apply(recs, frames, erase=op)
-        N.check(N.lib().cama_overlay_apply_host_mosaic(recs.ctypes.data, len(recs), mosaic.ctypes.data, F, C, H, W, 3, tiles.ctypes.data, op, 0))
+        N.check(apply(recs, frames, op))
+        N.check(apply(recs, mosaic, op, tiles=tiles, shape=(F, C, H, W)))
         want = np.stack([concate_image({n: frames[f, c] for c, n in enumerate(names)}) for f in range(F)])
         assert np.array_equal(mosaic, want), op
-    bad = tiles.copy(); bad[0] = 9
-    assert N.lib().cama_overlay_apply_host_mosaic(recs.ctypes.data, len(recs), mosaic.ctypes.data, F, C, H, W, 3, bad.ctypes.data, 0, 0) == N.CAMA_E_INVALID
+    bad = tiles.copy()
+    bad[0] = 9
+    assert apply(recs, mosaic, 0, tiles=bad, shape=(F, C, H, W)) == N.CAMA_E_INVALID

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Where the milliseconds of Reproject.__call__ (sparse transfer) go, on the GPU box."""
-import os, sys, tempfile, time
+import ctypes, os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from cama_b200 import synth, _native as N
@@ -18,14 +18,16 @@ reps = 20
 for _ in range(reps):
     t0 = time.perf_counter(); idx, w2c = rp.frame_poses("nuscenes"); tick("frame_poses (host pose seek + inverse)", t0)
     t0 = time.perf_counter(); w2c_dev = torch.from_numpy(w2c).to(rp.rt.device); tick("H2D poses", t0)
-    t0 = time.perf_counter(); records, n = rp.renderer.render_overlay(rp.resident("nuscenes"), w2c_dev); tick("render_overlay (GPU + stats read)", t0)
-    cur = rp._ov_host[0]
+    res = rp.resident("nuscenes")
+    t0 = time.perf_counter(); records, n, fmt = rp.renderer.render_overlay(res, w2c_dev); tick("render_overlay (GPU + stats read)", t0)
+    cur, pal = rp._ov_host[0], res.palette
     t0 = time.perf_counter(); cur[:n].copy_(records[:n], non_blocking=True); tick("D2H records", t0)
-    frames = rp._host_frames; n_chunks = frames.size // 24
-    t0 = time.perf_counter(); N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, frames.ctypes.data, n_chunks, 3, 0)); tick("host erase", t0)
-    t0 = time.perf_counter(); N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, frames.ctypes.data, n_chunks, 2, 0)); tick("host draw", t0)
+    frames = rp._host_frames
+    target = N.OverlayTarget(frames.ctypes.data, frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3], 0, None)
+    t0 = time.perf_counter(); N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, fmt, None if pal is None else pal.ctypes.data, ctypes.byref(target), 3, 0)); tick("host erase", t0)
+    t0 = time.perf_counter(); N.check(N.lib().cama_overlay_apply_host(cur.data_ptr(), n, fmt, None if pal is None else pal.ctypes.data, ctypes.byref(target), 2, 0)); tick("host draw", t0)
 t0 = time.perf_counter()
 for _ in range(reps): rp("nuscenes")
 tick("whole call", t0)
 for k, v in T.items(): print(f"{k:45s} {1e3 * v / reps:8.3f} ms")
-print("records", n, "cores", os.cpu_count())
+print("records", n, "bytes each", cur.shape[1] * 4, "cores", os.cpu_count())
