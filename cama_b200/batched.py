@@ -197,8 +197,12 @@ class ClipRenderer:
         N.check(N.lib().cama_remap_bilinear(rt.ctx, rt.ptr(raw), n, hs, ws, rt.ptr(map_x), rt.ptr(map_y), n_maps, rt.ptr(out), h, w, rt.stream()))
         return out
 
-    def render_overlay(self, res, w2c_dev, mode="auto", fmt=None):
+    def render_overlay(self, res, w2c_dev, mode="auto", fmt=None, while_running=None):
         """Sparse output of one clip: the lit 8-pixel chunks instead of dense frames.
+
+        while_running  optional host callable, run once after the launches are enqueued and before the
+                       counters are read back: host work that overlaps the GPU's (Reproject blanks the previous
+                       overlay there)
 
         fmt  N.OVERLAY_PALETTE (12-byte records, needs <= 255 distinct instance colours), N.OVERLAY_BGR (32-byte
              records) or None = palette when possible
@@ -223,8 +227,13 @@ class ClipRenderer:
             N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
             ws = rt.scratch("clip", need.value)
             if n_frames == 0:
+                if while_running is not None:
+                    while_running()
                 return records, 0, fmt
             N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
+            if while_running is not None:
+                while_running()
+                while_running = None
             stats = N.ClipStats()
             code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
             self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
@@ -265,6 +274,7 @@ class Reproject:
         self._ov_prev = None          # ... and the records painted into them (blanked before the next paint)
         self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
         self._ov_flip = 0
+        self._ov_events = []
         self.last_transfer = None
 
     def resident(self, dataset):
@@ -345,22 +355,14 @@ class Reproject:
         shape = (len(idx), C, H, W, 3) if tiles is None else (len(idx), 2 * H, 3 * W, 3)
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(rt.device)
         res = self.resident(dataset)
-        records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode)
-        words = int(records.shape[1])
-        # records -> pinned host memory
-        cur = self._ov_host[self._ov_flip]
-        if cur is None or cur.shape[0] < max(n, 1) or cur.shape[1] != words:
-            cur = torch.empty((max(int(n * 1.25), 4096), words), dtype=torch.int32, pin_memory=True)
-            self._ov_host[self._ov_flip] = cur
-        if n:
-            cur[:n].copy_(records[:n], non_blocking=True)        # in flight while the host blanks the previous overlay
 
-        def apply(rec, count, rec_fmt, palette, op):
+        def apply(rec_ptr, count, rec_fmt, palette, op):
             target = N.OverlayTarget(frames.ctypes.data, len(idx), C, H, W, 0 if tiles is None else 3,
                                      None if tiles is None else tiles.ctypes.data)
-            N.check(N.lib().cama_overlay_apply_host(rec.data_ptr(), count, rec_fmt, None if palette is None else palette.ctypes.data,
+            N.check(N.lib().cama_overlay_apply_host(rec_ptr, count, rec_fmt, None if palette is None else palette.ctypes.data,
                                                     ctypes.byref(target), op, 0))
 
+        blank_previous = None
         if backgrounds is not None:
             frames = backgrounds
             assert isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.shape == shape and frames.flags.c_contiguous \
@@ -370,13 +372,35 @@ class Reproject:
             if frames is None or frames.shape != shape:
                 frames = self._host_frames = np.zeros(shape, dtype=np.uint8)
                 self._ov_prev = None
-            if self._ov_prev is not None:                    # blank what the previous call painted into this buffer
+            if self._ov_prev is not None:                    # blank what the previous call painted into this buffer ...
                 prev, n_prev, prev_fmt, prev_palette = self._ov_prev
-                apply(prev, n_prev, prev_fmt, prev_palette, N.OVERLAY_BLANK_CHUNKS)
+                self._ov_prev = None
+                blank_previous = lambda: apply(prev.data_ptr(), n_prev, prev_fmt, prev_palette, N.OVERLAY_BLANK_CHUNKS)
+        # ... while the GPU renders this one
+        records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode, while_running=blank_previous)
+        words = int(records.shape[1])
+        # records -> pinned host memory in a few slices (records are independent: unique chunks, any order), each drawn
+        # into the host frames while the next one is still crossing PCIe
+        cur = self._ov_host[self._ov_flip]
+        if cur is None or cur.shape[0] < max(n, 1) or cur.shape[1] != words:
+            cur = torch.empty((max(int(n * 1.25), 4096), words), dtype=torch.int32, pin_memory=True)
+            self._ov_host[self._ov_flip] = cur
+        cuts = [0, n] if n < (1 << 16) else [0, n // 8, (3 * n) // 8, n]
+        events = self._ov_events
+        while len(events) < len(cuts) - 1:
+            events.append(torch.cuda.Event())
+        for k in range(len(cuts) - 1):
+            if cuts[k + 1] > cuts[k]:
+                cur[cuts[k]:cuts[k + 1]].copy_(records[cuts[k]:cuts[k + 1]], non_blocking=True)
+            events[k].record(torch.cuda.current_stream(rt.device))
+        if backgrounds is None:
             self._ov_prev = (cur, n, fmt, res.palette)
             self._ov_flip ^= 1
-        rt.synchronize()
-        apply(cur, n, fmt, res.palette, N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS)   # blank frames: unpainted pixels are black anyway
+        draw = N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS   # blank frames: unpainted pixels are black anyway
+        for k in range(len(cuts) - 1):
+            events[k].synchronize()
+            if cuts[k + 1] > cuts[k]:
+                apply(cur.data_ptr() + cuts[k] * words * 4, cuts[k + 1] - cuts[k], fmt, res.palette, draw)
         self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES[fmt], "records": n,
                               "format": "palette" if fmt == N.OVERLAY_PALETTE else "bgr"}
         return idx, frames

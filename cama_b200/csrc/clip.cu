@@ -26,6 +26,14 @@ namespace cama {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// Programmatic dependent launch: the kernels of a clip are launched with programmatic stream
+// serialisation, so a kernel's CTAs may become resident (and run the prologue that does not depend on
+// earlier kernels) while the previous kernel drains.  pdl_wait() blocks until the previous grid has
+// completed and its writes are visible (a no-op when the launch did not carry the attribute);
+// pdl_trigger() lets the next kernel of the stream start launching once every CTA of this one has called it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct CamBlock {                      // by-value kernel parameter (constant bank)
     double E[CAMA_MAX_CAMERAS][12];    // chassis -> camera, rows 0..2 of the 4x4
     double K[CAMA_MAX_CAMERAS][9];
@@ -64,6 +72,8 @@ __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double 
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
                             unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();                                    // (the previous clip's raster still reads the counters cleared here)
+    pdl_trigger();
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
     if (i < stats_words) stats[i] = 0u;
     if (i == 0 && overlay_count) *overlay_count = 0u;
@@ -246,6 +256,8 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
                                                            unsigned long long *__restrict__ worklist, unsigned *__restrict__ n_live) {
     const long long unit = (long long)blockIdx.x * 256 + threadIdx.x;
     unsigned mask = 0;
+    pdl_wait();
+    pdl_trigger();
     if (unit < units) {
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
@@ -281,6 +293,8 @@ __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const Cli
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
     if (BINNED && (tid & 31) == 0) stage.count = 0;
     __syncwarp();
+    pdl_wait();
+    pdl_trigger();
     const long long n_work = a.worklist ? (long long)*a.n_live : units;
     for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
         long long unit = w;
@@ -379,7 +393,9 @@ struct ClipStatsDev {
 };
 
 // single CTA: start[b] = exclusive scan of hist, start[nb] = total; pool overflow check.
-// 4096 buckets per round: one 16-byte load per thread, a warp scan, a scan of the 32 warp totals.
+// 8192 buckets per round (config 2 has 8160: one round): two 16-byte loads per thread, a warp scan, a
+// scan of the 32 warp totals.
+constexpr int kScanPerThread = 8;
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, int nb,
                                                            const unsigned *__restrict__ pool_count, int n_frames, long long pool_cap,
                                                            ClipStatsDev *__restrict__ stats, unsigned *__restrict__ lists /* [4][nb] */,
@@ -390,24 +406,49 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
     unsigned carry = 0;                                            // same value in every thread
     if (tid < 4) s_cursor[tid] = 0;
     __syncthreads();
-    for (int base = 0; base < nb; base += 4096) {
-        const int idx = base + 4 * tid;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (idx + 3 < nb) v = *reinterpret_cast<const uint4 *>(hist + idx);
-        else {
-            if (idx < nb) v.x = hist[idx];
-            if (idx + 1 < nb) v.y = hist[idx + 1];
-            if (idx + 2 < nb) v.z = hist[idx + 2];
+    pdl_wait();
+    pdl_trigger();
+    for (int base = 0; base < nb; base += 1024 * kScanPerThread) {
+        const int idx = base + kScanPerThread * tid;
+        unsigned vals[kScanPerThread];
+        if (idx + kScanPerThread <= nb) {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(hist + idx), v1 = *reinterpret_cast<const uint4 *>(hist + idx + 4);
+            vals[0] = v0.x; vals[1] = v0.y; vals[2] = v0.z; vals[3] = v0.w;
+            vals[4] = v1.x; vals[5] = v1.y; vals[6] = v1.z; vals[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < kScanPerThread; ++e) vals[e] = idx + e < nb ? hist[idx + e] : 0u;
         }
-        const unsigned mine = v.x + v.y + v.z + v.w;
-        unsigned inc = mine;
+        unsigned mine = 0;
+#pragma unroll
+        for (int e = 0; e < kScanPerThread; ++e) mine += vals[e];
+        // Work lists for the raster, one per weight class: buckets with >= 2048, >= 256, >= 1 records (claimed
+        // dynamically, heaviest class first) and the empty ones (dealt out statically).  The four per-class
+        // counts of a thread ride in two words, 16 bits each (<= 8 per thread, <= 256 per warp), so the warp
+        // scan of the record counts carries them along.
+        int cls[kScanPerThread];
+        unsigned cnt01 = 0, cnt23 = 0;                             // class counts, 16 bits each
+#pragma unroll
+        for (int e = 0; e < kScanPerThread; ++e) {
+            cls[e] = idx + e < nb ? (vals[e] == 0u ? 3 : vals[e] >= 2048u ? 0 : vals[e] >= 256u ? 1 : 2) : -1;
+            cnt01 += cls[e] == 0 ? 1u : cls[e] == 1 ? 0x10000u : 0u;
+            cnt23 += cls[e] == 2 ? 1u : cls[e] == 3 ? 0x10000u : 0u;
+        }
+        unsigned inc = mine, inc01 = cnt01, inc23 = cnt23;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(kFull, inc, d);
-            if (lane >= d) inc += t;
+            const unsigned t = __shfl_up_sync(kFull, inc, d), t01 = __shfl_up_sync(kFull, inc01, d), t23 = __shfl_up_sync(kFull, inc23, d);
+            if (lane >= d) { inc += t; inc01 += t01; inc23 += t23; }
         }
         __syncthreads();                                           // warp_sum of the previous round is consumed
         if (lane == 31) warp_sum[warp] = inc;
+        unsigned slot[4] = {0u, 0u, 0u, 0u};                       // one shared-memory atomic per warp and class
+        if (lane == 31) {
+            if (inc01 & 0xffffu) slot[0] = atomicAdd(&s_cursor[0], inc01 & 0xffffu);
+            if (inc01 >> 16) slot[1] = atomicAdd(&s_cursor[1], inc01 >> 16);
+            if (inc23 & 0xffffu) slot[2] = atomicAdd(&s_cursor[2], inc23 & 0xffffu);
+            if (inc23 >> 16) slot[3] = atomicAdd(&s_cursor[3], inc23 >> 16);
+        }
         __syncthreads();
         unsigned w = warp_sum[lane], wi = w;
 #pragma unroll
@@ -418,41 +459,27 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
         const unsigned warps_before = __shfl_sync(kFull, wi - w, warp);       // exclusive prefix of this warp's total
         const unsigned round_total = __shfl_sync(kFull, wi, 31);
         unsigned before = carry + warps_before + inc - mine;
-        if (idx < nb) start[idx] = before;
-        before += v.x; if (idx + 1 < nb) start[idx + 1] = before;
-        before += v.y; if (idx + 2 < nb) start[idx + 2] = before;
-        before += v.z; if (idx + 3 < nb) start[idx + 3] = before;
-        carry += round_total;
-        // Work lists for the raster, one per weight class: buckets with >= 2048, >= 256, >= 1 records (claimed
-        // dynamically, heaviest class first) and the empty ones (dealt out statically).  One shared-memory
-        // atomic per warp, class and element.
-        const unsigned vals[4] = {v.x, v.y, v.z, v.w};
-        int cls[4];
+        if (idx + kScanPerThread <= nb) {
+            uint4 o0, o1;
+            o0.x = before; before += vals[0]; o0.y = before; before += vals[1]; o0.z = before; before += vals[2]; o0.w = before; before += vals[3];
+            o1.x = before; before += vals[4]; o1.y = before; before += vals[5]; o1.z = before; before += vals[6]; o1.w = before;
+            *reinterpret_cast<uint4 *>(start + idx) = o0;
+            *reinterpret_cast<uint4 *>(start + idx + 4) = o1;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) cls[e] = idx + e < nb ? (vals[e] == 0u ? 3 : vals[e] >= 2048u ? 0 : vals[e] >= 256u ? 1 : 2) : -1;
-        unsigned mine_j[4], incl[4], slot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                              // per class: how many of my four, warp prefix, one atomic per warp
-            mine_j[j] = (cls[0] == j) + (cls[1] == j) + (cls[2] == j) + (cls[3] == j);
-            incl[j] = mine_j[j];
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned t = __shfl_up_sync(kFull, incl[j], d);
-                if (lane >= d) incl[j] += t;
+            for (int e = 0; e < kScanPerThread; ++e) {
+                if (idx + e < nb) start[idx + e] = before;
+                before += vals[e];
             }
         }
+        carry += round_total;
+        const unsigned ex01 = inc01 - cnt01, ex23 = inc23 - cnt23;            // exclusive prefixes inside the warp
+        slot[0] = __shfl_sync(kFull, slot[0], 31) + (ex01 & 0xffffu);
+        slot[1] = __shfl_sync(kFull, slot[1], 31) + (ex01 >> 16);
+        slot[2] = __shfl_sync(kFull, slot[2], 31) + (ex23 & 0xffffu);
+        slot[3] = __shfl_sync(kFull, slot[3], 31) + (ex23 >> 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            slot[j] = 0;
-            if (lane == 31 && incl[j]) slot[j] = atomicAdd(&s_cursor[j], incl[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) slot[j] = __shfl_sync(kFull, slot[j], 31) + incl[j] - mine_j[j];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < kScanPerThread; ++e) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (cls[e] == j) lists[(size_t)j * nb + slot[j]++] = (unsigned)(idx + e);
@@ -476,6 +503,8 @@ constexpr int kScatterPerThread = 4;
 __global__ void __launch_bounds__(256) record_scatter_kernel(const uint2 *__restrict__ pool, const unsigned *__restrict__ pool_count, long long pool_cap,
                                                             const unsigned *__restrict__ start, unsigned *__restrict__ hist, long long sorted_cap,
                                                             unsigned *__restrict__ sorted) {
+    pdl_wait();
+    pdl_trigger();
     const long long n = min((long long)*pool_count, pool_cap);
     const int lane = threadIdx.x & 31;
     const long long tile = 256 * kScatterPerThread;
@@ -781,19 +810,40 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     }
     if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
     __syncthreads();
+    pdl_wait();                                  // everything above overlapped the tail of the scatter kernel
+    pdl_trigger();
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
 
+    // Hit masks: a thread ORs the plane-row bit of each of its records into a register per strip (predicated,
+    // no indexing) and the warp publishes them once per bucket (publish_hits: one REDUX + at most one atomic
+    // per strip).  Per-record shared-memory atomicOr on the few hit words serialised ~20-fold (every lane of a
+    // warp hits the same handful of words).  Only the rare records within 2 px of a strip edge still use one.
+    constexpr int kMaxStrips = 8;                  // width <= 2048
+    unsigned hacc[kMaxStrips];
+#pragma unroll
+    for (int k = 0; k < kMaxStrips; ++k) hacc[k] = 0u;
     auto scatter = [&](unsigned rec) {
         // (the validity checks only matter after a capacity overflow, when the pool holds stale records)
         const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
         if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
             smem_max_u16(plane, row * (unsigned)W + x, ord1);
             const unsigned bit = 1u << row, s = x / kStripPx, off = x % kStripPx;
-            atomicOr(&hits[s], bit);
+#pragma unroll
+            for (int k = 0; k < kMaxStrips; ++k) hacc[k] |= s == (unsigned)k ? bit : 0u;
             if (off < 2u && s > 0u) atomicOr(&hits[s - 1], bit);
             if (off >= kStripPx - 2u && s + 1u < (unsigned)n_strips) atomicOr(&hits[s + 1], bit);
-            atomicOr(&hits[n_strips], bit);
         }
+    };
+    auto publish_hits = [&] {                      // warp-collective; hits[n_strips] = OR over the strips
+        unsigned any = 0u;
+#pragma unroll
+        for (int k = 0; k < kMaxStrips; ++k) {
+            const unsigned v = __reduce_or_sync(kFull, hacc[k]);
+            hacc[k] = 0u;
+            if (v != 0u && lane == k) atomicOr(&hits[k], v);
+            any |= v;
+        }
+        if (any != 0u && lane == kMaxStrips) atomicOr(&hits[n_strips], any);
     };
     auto fetch = [&](long long begin, long long end, unsigned (&rec)[4]) {
 #pragma unroll
@@ -878,6 +928,7 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
 #pragma unroll
                 for (int q = 0; q < 4; ++q) scatter(rec[q]);
             }
+            publish_hits();
             sync_compute();
             // 2. cells: dilation + colour + store
             const unsigned hit_any = hits[n_strips];
@@ -959,6 +1010,28 @@ using namespace cama;
 
 namespace {
 
+// Kernel launch with (optionally) programmatic stream serialisation, see pdl_wait().  CAMA_NO_PDL=1
+// in the environment turns the attribute off (plain stream order), for A/B measurements.
+bool pdl_enabled() {
+    static const bool on = getenv("CAMA_NO_PDL") == nullptr;
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 struct ClipPlan {
     int mode;
     int band_rows, n_bands, x_bits;
@@ -976,17 +1049,15 @@ struct ClipPlan {
 constexpr int kRasterCtasPerSm = 4;
 constexpr int kDefaultBandRows = 16;
 template <bool BINNED>
-void launch_geometry(bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
+cudaError_t launch_geometry(bool pdl, bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
     static const bool generic_only = getenv("CAMA_GEO_GENERIC") != nullptr;     // experiment knob
-    if (f32 && !debug && a.n_cams == 6 && !generic_only) {          // the production shape: six cameras, float32 vertices
-        clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6><<<grid, kGeoThreads, 0, s>>>(a, cams);
-    } else if (f32) {
-        if (debug) clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
-        else clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
-    } else {
-        if (debug) clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
-        else clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0><<<grid, kGeoThreads, 0, s>>>(a, cams);
-    }
+    if (f32 && !debug && a.n_cams == 6 && !generic_only)            // the production shape: six cameras, float32 vertices
+        return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6>, grid, kGeoThreads, 0, s, a, cams);
+    if (f32)
+        return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0>, grid, kGeoThreads, 0, s, a, cams)
+                     : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0>, grid, kGeoThreads, 0, s, a, cams);
+    return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0>, grid, kGeoThreads, 0, s, a, cams)
+                 : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0>, grid, kGeoThreads, 0, s, a, cams);
 }
 
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
@@ -1138,11 +1209,13 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         const bool binned = p.mode == CAMA_CLIP_BINNED;
         const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
         const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
-        prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
-                                                               d->instance_bgr, d->n_instances, lut,
-                                                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : nullptr, zero_words,
-                                                               reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                                                               d->overlay_records ? d->overlay_count : nullptr, d->instance_palette);
+        // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
+        CAMA_CUDA_TRY(launch_k(binned && pdl_enabled() && !prof, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
+                               d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
+                               d->instance_bgr, d->n_instances, lut,
+                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : (unsigned *)nullptr, zero_words,
+                               reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
+                               d->overlay_records ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
@@ -1157,7 +1230,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
         CAMA_CUDA_TRY(mark(1));
         if (units > 0) {
-            launch_geometry<false>(f32, debug, geo_grid, s, a, cams);
+            CAMA_CUDA_TRY(launch_geometry<false>(false, f32, debug, geo_grid, s, a, cams));
             CAMA_LAUNCHED(ctx);
         }
         CAMA_CUDA_TRY(mark(2));
@@ -1169,7 +1242,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         return CAMA_OK;
     }
 
-    // BINNED
+    // BINNED (phase events between the kernels would serialise them anyway: no PDL while profiling)
+    const bool pdl = pdl_enabled() && !prof;
     a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.pool_cap = (long long)d->n_frames * p.cap;
     a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
     a.pool_count = reinterpret_cast<unsigned *>(ws + p.off_counter) + 1;      // word 0 of the counter block is spare
@@ -1183,24 +1257,25 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
             unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
             unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
-            geometry_cull_kernel<<<(unsigned)((units + 255) / 256), 256, 0, s>>>(d->tile_bounds, a.w2c64, units, (d->n_frames + kGeoFrames - 1) / kGeoFrames,
-                                                                                d->n_frames, cams, worklist, n_live);
+            CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
+                                   (d->n_frames + kGeoFrames - 1) / kGeoFrames, d->n_frames, cams, worklist, n_live));
             CAMA_LAUNCHED(ctx);
             a.worklist = worklist;
             a.n_live = n_live;
         }
-        launch_geometry<true>(f32, debug, geo_grid, s, a, cams);
+        CAMA_CUDA_TRY(launch_geometry<true>(pdl, f32, debug, geo_grid, s, a, cams));
         CAMA_LAUNCHED(ctx);
     }
     CAMA_CUDA_TRY(mark(2));
     unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
     unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
-    bucket_scan_kernel<<<1, 1024, 0, s>>>(a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats, lists, list_counts);
+    CAMA_CUDA_TRY(launch_k(pdl, bucket_scan_kernel, 1, 1024, 0, s, a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats, lists,
+                           list_counts));
     CAMA_LAUNCHED(ctx);
     {   // one record per thread when the pool is full; CTAs past the records appended exit at once
         const long long tile = 256 * kScatterPerThread;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, 1 << 20));
-        record_scatter_kernel<<<grid, 256, 0, s>>>(a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted);
+        CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
     }
     CAMA_LAUNCHED(ctx);
     CAMA_CUDA_TRY(mark(3));
@@ -1217,17 +1292,17 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
         if (d->overlay_format == CAMA_OVERLAY_PALETTE) {
             CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-            binned_raster_kernel<3><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+            CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<3>, raster_grid, kRasterBlock, p.raster_smem, s, r));
         } else {
             CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-            binned_raster_kernel<2><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+            CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<2>, raster_grid, kRasterBlock, p.raster_smem, s, r));
         }
     } else if (d->background) {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        binned_raster_kernel<1><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+        CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<1>, raster_grid, kRasterBlock, p.raster_smem, s, r));
     } else {
         CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        binned_raster_kernel<0><<<raster_grid, kRasterBlock, p.raster_smem, s>>>(r);
+        CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<0>, raster_grid, kRasterBlock, p.raster_smem, s, r));
     }
     CAMA_LAUNCHED(ctx);
     CAMA_CUDA_TRY(mark(4));
@@ -1241,8 +1316,11 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     if (rc != CAMA_OK) return rc;
     DeviceGuard guard(ctx->device);
     ClipStatsDev h{};
+    unsigned n_overlay = 0;
+    const bool sparse = d->overlay_records && d->overlay_count;
     CAMA_CUDA_TRY(cudaMemcpyAsync(&h, static_cast<const unsigned char *>(workspace) + p.off_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (sparse) CAMA_CUDA_TRY(cudaMemcpyAsync(&n_overlay, d->overlay_count, sizeof(n_overlay), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));      // one round trip for both counters
     out->records_total = (int64_t)h.records_total;
     out->records_max_per_frame = (int64_t)h.records_max_per_frame;
     out->record_capacity = p.cap;
@@ -1250,13 +1328,7 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->mode = p.mode;
     out->band_rows = p.band_rows;
     out->n_bands = p.n_bands;
-    out->overlay_records = 0;
-    if (d->overlay_records && d->overlay_count) {
-        unsigned n = 0;
-        CAMA_CUDA_TRY(cudaMemcpyAsync(&n, d->overlay_count, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        out->overlay_records = n;
-    }
+    out->overlay_records = sparse ? n_overlay : 0;
     if (h.overflow)
         return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", h.records_max_per_frame, p.cap);
     return CAMA_OK;
