@@ -48,7 +48,7 @@ class ClipDesc(Structure):
         ("record_capacity", c_int64),
         ("tile_bounds", c_void_p),
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
-        ("overlay_format", c_int32), ("reserved0", c_int32), ("instance_palette", c_void_p),
+        ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
     ]
 
 

@@ -96,6 +96,7 @@ class ClipRenderer:
         self.n_cams = self.chassis2cam.shape[0]
         self.height, self.width = int(height), int(width)
         self.crop_box = [float(v) for v in crop_box]
+        self.pipeline_frames = 0      # cama_clip_desc.pipeline_frames: 0 = library default, < 0 = off, n = groups of n frames
         self.capacity = {}            # (resident id, n_frames) -> records per frame that were enough
         self.overlay_capacity = {}    # (resident id, n_frames) -> overlay records that were enough
         self.last_stats = None
@@ -124,6 +125,7 @@ class ClipRenderer:
         d.visible_counts = debug["visible_counts"].data_ptr() if debug else None
         d.vu_dense = debug["vu_dense"].data_ptr() if debug and debug.get("vu_dense") is not None else None
         d.record_capacity = int(capacity)
+        d.pipeline_frames = int(self.pipeline_frames)
         d.tile_bounds = res.tile_bounds.data_ptr() if getattr(res, "tile_bounds", None) is not None else None
         if overlay is not None:
             records, count, fmt = overlay

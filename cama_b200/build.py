@@ -58,8 +58,14 @@ def is_stale():
         return fh.read().strip() != source_digest()
 
 
-def build(verbose=False, extra_flags=()):
+def build(verbose=False, extra_flags=(), out=None):
+    """out=<path>: build a variant there (with extra -D flags) and leave the product library alone."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if out is not None:
+        res = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", out, *sources()], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return out
     cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", LIB_PATH, *sources()]
     if verbose:
         print(" ".join(cmd))
@@ -74,7 +80,13 @@ def build(verbose=False, extra_flags=()):
 
 
 def ensure_built():
-    """Build if missing or stale and a compiler is available; never silently fall back."""
+    """Build if missing or stale and a compiler is available; never silently fall back.
+    CAMA_B200_LIB=<path> loads that build of the library instead (A/B experiments with compile-time variants)."""
+    override = os.environ.get("CAMA_B200_LIB")
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError(f"CAMA_B200_LIB={override} does not exist")
+        return override
     if is_stale():
         if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
             build()

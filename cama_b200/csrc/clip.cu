@@ -106,6 +106,9 @@ __device__ __forceinline__ bool load_vertex(const ClipArgs &a, long long n, doub
 //  * K row 2 == (0,0,1) makes q_z == p_z bit-for-bit, so p_z <= 0 rejects before x,y are formed;
 //  * q_x < -q_z or q_x > (W+1) q_z (same for y) puts u (v) outside [0,W) by a whole pixel, far
 //    beyond what the rounding of the division could undo.
+__device__ __forceinline__ bool camera_in_front(const CamBlock &cams, int c, double cx, double cy, double cz) {
+    return !cams.k_row2_is_001[c] || affine_row(cams.E[c] + 8, cx, cy, cz) > 0.0;
+}
 __device__ __forceinline__ bool camera_candidate(const CamBlock &cams, int c, double cx, double cy, double cz, int width, int height,
                                                  double &qx, double &qy, double &qz) {
     const double *E = cams.E[c];
@@ -151,8 +154,20 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
 // counts are fire-and-forget reductions, and no block-level barrier is involved.  (A version that
 // reserved a pool slot and a bucket rank with returning atomics per warp spent a quarter of its
 // time waiting for them; one that staged per CTA spent a third of it in the per-frame barrier.)
+#ifndef CAMA_PIPE_FRAMES_DEFAULT
+#define CAMA_PIPE_FRAMES_DEFAULT 80
+#endif
+#ifndef CAMA_GEO_MINB
+#define CAMA_GEO_MINB 4                    // resident CTAs per SM the geometry kernel is compiled for
+#endif
+#ifndef CAMA_GEO_STAGE_FLUSH
+#define CAMA_GEO_STAGE_FLUSH 128
+#endif
+#ifndef CAMA_GEO_PZ_FIRST
+#define CAMA_GEO_PZ_FIRST 0
+#endif
 constexpr int kGeoThreads = 256;
-constexpr int kStageFlush = 128;                                       // a warp flushes once this many records are staged ...
+constexpr int kStageFlush = CAMA_GEO_STAGE_FLUSH;                                       // a warp flushes once this many records are staged ...
 constexpr int kStageCap = kStageFlush + 32 * 2 * CAMA_MAX_CAMERAS;     // ... so one more frame (<= 2 records per vertex and camera) always fits
 
 struct GeoStage {                          // one per warp
@@ -281,7 +296,7 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
 // NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls and every matrix entry
 // becomes a constant-bank operand of its DFMA instead of an indexed load (0 = any count up to 8).
 template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
-__global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
+__global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT[kGeoFrames][12];
     __shared__ int s_frame_live[kGeoFrames];
     __shared__ GeoStage stages[kGeoThreads / 32];
@@ -332,11 +347,27 @@ __global__ void __launch_bounds__(kGeoThreads, 4) clip_geometry_kernel(const Cli
             if (__any_sync(kFull, alive)) {
                 if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
                 const int n_cams = NCAMS ? NCAMS : a.n_cams;
+#if CAMA_GEO_PZ_FIRST
+                // which cameras have the point in front of them: the depth rows of all cameras first, as independent
+                // dependency chains (one camera after the other, every chain's latency is exposed before the warp vote)
+                unsigned front = 0u;
+#pragma unroll
+                for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c)
+                    if (NCAMS || c < n_cams) front |= (alive && camera_in_front(cams, c, cx, cy, cz)) ? 1u << c : 0u;
+                const unsigned warp_front = __reduce_or_sync(kFull, front);
+#endif
 #pragma unroll
                 for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
                     if (!NCAMS && c >= n_cams) break;
+#if CAMA_GEO_PZ_FIRST
+                    if (!((warp_front >> c) & 1u)) continue;
+#endif
                     double qx = 0.0, qy = 0.0, qz = 1.0;
+#if CAMA_GEO_PZ_FIRST
+                    const bool cand = ((front >> c) & 1u) && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
+#else
                     const bool cand = alive && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
+#endif
                     if (!__any_sync(kFull, cand)) continue;
                     int vi = 0, ui = 0;
                     double v = 0.0, u = 0.0;
@@ -581,6 +612,7 @@ struct RasterArgs {
     int x_bits;                            // record = ord1 : 16 | plane row : 16 - x_bits | x : x_bits
     int n_strips;
     int debug;                             // CAMA_RASTER_DEBUG experiments: 2 = no colour lookup
+    int image_base;                        // sparse output: index of the first (frame, camera) image of this launch inside the clip
     long long sorted_cap;
     const unsigned *start;                 // [n_items+1]
     const unsigned *sorted;
@@ -918,10 +950,11 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
             const int rows_out = min(a.band_rows, a.height - y_first);
             uint8_t *out_base = a.frames + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes;
             const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
-            const unsigned chunk_base = (unsigned)((((size_t)(item0 / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
+            const unsigned chunk_base = (unsigned)((((size_t)(a.image_base + item0 / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
             // 1. centres of this bucket -> plane (max ordinal per pixel) + hit masks
 #pragma unroll
             for (int q = 0; q < 4; ++q) scatter(pre[q]);
+            // (16-byte fetches of four consecutive records per thread and a software-pipelined loop were both measured slower)
             for (long long base = lo + 4 * kRasterThreads; base < hi; base += 4 * kRasterThreads) {
                 unsigned rec[4];
                 fetch(base, hi, rec);
@@ -1017,6 +1050,17 @@ bool pdl_enabled() {
     return on;
 }
 
+// Frames per group of the frame-group pipeline; CAMA_PIPE_FRAMES=<n> overrides (0 = off).  A multiple of the
+// geometry kernel's 8-frame work unit.
+int pipe_group_frames() {
+    static const int frames = [] {
+        const char *env = getenv("CAMA_PIPE_FRAMES");
+        int f = env ? atoi(env) : CAMA_PIPE_FRAMES_DEFAULT;
+        return f <= 0 ? 0 : (f + 7) / 8 * 8;
+    }();
+    return frames;
+}
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
@@ -1044,6 +1088,10 @@ struct ClipPlan {
     size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists;
     long long geo_units;
     size_t total;
+    // frame-group pipeline (BINNED): the clip is rendered as `groups` sub-clips of `group_frames` frames, each with
+    // its own workspace slice of `group_stride` bytes (laid out by the plan of a `group_frames`-frame clip)
+    int groups, group_frames;
+    size_t group_stride;
 };
 
 constexpr int kRasterCtasPerSm = 4;
@@ -1063,7 +1111,7 @@ cudaError_t launch_geometry(bool pdl, bool f32, bool debug, unsigned grid, cudaS
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
 constexpr size_t kRasterStageSmem = kHitBytes;   // + the plane + kZeroRows image rows
 
-int make_plan(const cama_clip_desc *d, ClipPlan &p) {
+int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     CAMA_REQUIRE(d, "desc is NULL");
     CAMA_REQUIRE(d->struct_bytes == sizeof(cama_clip_desc), "cama_clip_desc size mismatch: caller %u, library %zu", d->struct_bytes, sizeof(cama_clip_desc));
     CAMA_REQUIRE(d->n_frames >= 0 && d->n_cams > 0 && d->n_instances >= 0 && d->n_vertices >= 0, "negative size");
@@ -1135,6 +1183,168 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p) {
         p.off_sorted = take(sizeof(unsigned) * (size_t)d->n_frames * cap);
     }
     p.total = std::max<size_t>(off, 256);
+    p.groups = 1;
+    p.group_frames = d->n_frames;
+    p.group_stride = 0;
+    // Frame groups: the geometry of group g+1 runs while group g is sorted and rastered (three stream lanes, see
+    // cama_clip_render).  Not with the per-instance debug outputs (their consumers want one pass), not for small clips.
+    if (allow_groups && mode == CAMA_CLIP_BINNED && !d->crop_counts && !d->visible_counts && !d->vu_dense) {
+        int want = d->pipeline_frames > 0 ? (d->pipeline_frames + 7) / 8 * 8 : d->pipeline_frames < 0 ? 0 : pipe_group_frames();
+        if (want > 0 && d->n_frames > want) {
+            cama_clip_desc sub = *d;
+            sub.n_frames = want;
+            ClipPlan q;
+            const int rc = make_plan(&sub, q, false);
+            if (rc != CAMA_OK) return rc;
+            p.group_frames = want;
+            p.groups = (d->n_frames + want - 1) / want;
+            p.group_stride = align_up(q.total, 256);
+            p.total = std::max(p.total, p.group_stride * (size_t)p.groups);     // (the un-grouped layout is used while phase profiling is on)
+        }
+    }
+    return CAMA_OK;
+}
+
+// Streams one pass (a whole clip, or one frame group) is issued on, and the events that order them
+// (nullptr: the three lanes are one stream).
+struct Lanes {
+    cudaStream_t geo, sort, raster;
+    cudaEvent_t geo_done, sort_done;
+};
+
+// Enqueues one pass over the frames of `d` with the workspace slice `ws` laid out by `p`.  image_base: index of the
+// pass's first (frame, camera) image inside the clip (sparse output); first: this pass clears the clip-wide counters.
+int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsigned char *ws, const CamBlock &cams, const Lanes &lanes,
+                cudaEvent_t *prof, int image_base, bool first) {
+    cudaStream_t s = lanes.geo;
+    auto mark = [&](int i) { return prof ? cudaEventRecord(prof[i], s) : cudaSuccess; };
+    CAMA_CUDA_TRY(mark(0));
+    ClipArgs a{};
+    a.n_frames = d->n_frames; a.n_cams = d->n_cams; a.n_instances = d->n_instances;
+    a.height = d->height; a.width = d->width; a.n_vertices = d->n_vertices;
+    a.vertices = d->vertices; a.vertex_instance = d->vertex_instance;
+    a.w2c64 = reinterpret_cast<const double *>(ws + p.off_w2c64);
+    a.crop_counts = d->crop_counts; a.visible_counts = d->visible_counts; a.vu_dense = d->vu_dense;
+    a.tile_bounds = d->tile_bounds;
+    unsigned *lut = reinterpret_cast<unsigned *>(ws + p.off_lut);
+    ClipStatsDev *stats = reinterpret_cast<ClipStatsDev *>(ws + p.off_stats);
+    const bool binned = p.mode == CAMA_CLIP_BINNED;
+    const bool pdl = binned && pdl_enabled() && !prof;
+
+    if (d->vu_dense)
+        CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
+    {
+        const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
+        const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
+        // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
+        CAMA_CUDA_TRY(launch_k(pdl, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
+                               d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
+                               d->instance_bgr, d->n_instances, lut,
+                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : (unsigned *)nullptr, zero_words,
+                               reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
+                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
+        CAMA_LAUNCHED(ctx);
+    }
+    const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
+    const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
+    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 16));
+    const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
+    const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;
+
+    if (p.mode == CAMA_CLIP_PLANE) {
+        a.plane = reinterpret_cast<unsigned *>(ws + p.off_plane);
+        const size_t px = (size_t)d->n_frames * d->n_cams * d->height * d->width;
+        CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
+        CAMA_CUDA_TRY(mark(1));
+        if (units > 0) {
+            CAMA_CUDA_TRY(launch_geometry<false>(false, f32, debug, geo_grid, s, a, cams));
+            CAMA_LAUNCHED(ctx);
+        }
+        CAMA_CUDA_TRY(mark(2));
+        CAMA_CUDA_TRY(mark(3));
+        plane_raster_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(a.plane, lut, d->background, d->frames, d->height, d->width,
+                                                                        (long long)d->n_frames * d->n_cams);
+        CAMA_LAUNCHED(ctx);
+        CAMA_CUDA_TRY(mark(4));
+        return CAMA_OK;
+    }
+
+    // BINNED (the workspace slice may be laid out for more frames than this pass has: the last frame group)
+    const int n_buckets = d->n_frames * d->n_cams * p.n_bands;
+    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.pool_cap = (long long)d->n_frames * p.cap;
+    a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
+    a.pool_count = reinterpret_cast<unsigned *>(ws + p.off_counter) + 1;      // word 0 of the counter block is spare
+    a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
+    a.pool = reinterpret_cast<uint2 *>(ws + p.off_pool);
+    unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
+    unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
+    CAMA_CUDA_TRY(mark(1));
+    if (units > 0) {
+        // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
+        if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
+            unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
+            unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
+            CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
+                                   (d->n_frames + kGeoFrames - 1) / kGeoFrames, d->n_frames, cams, worklist, n_live));
+            CAMA_LAUNCHED(ctx);
+            a.worklist = worklist;
+            a.n_live = n_live;
+        }
+        CAMA_CUDA_TRY(launch_geometry<true>(pdl, f32, debug, geo_grid, s, a, cams));
+        CAMA_LAUNCHED(ctx);
+    }
+    CAMA_CUDA_TRY(mark(2));
+    const bool lanes_split = lanes.geo_done != nullptr;
+    if (lanes_split) {
+        CAMA_CUDA_TRY(cudaEventRecord(lanes.geo_done, s));
+        CAMA_CUDA_TRY(cudaStreamWaitEvent(lanes.sort, lanes.geo_done, 0));
+    }
+    s = lanes.sort;
+    unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
+    unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
+    CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, bucket_scan_kernel, 1, 1024, 0, s, a.hist, start, n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats,
+                           lists, list_counts));
+    CAMA_LAUNCHED(ctx);
+    {   // grid-stride over the records appended; sized for the pool, capped at a few CTAs per SM slot
+        const long long tile = 256 * kScatterPerThread;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, (long long)ctx->sm_count * 16));
+        CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
+    }
+    CAMA_LAUNCHED(ctx);
+    if (lanes_split) {
+        CAMA_CUDA_TRY(cudaEventRecord(lanes.sort_done, s));
+        CAMA_CUDA_TRY(cudaStreamWaitEvent(lanes.raster, lanes.sort_done, 0));
+    }
+    s = lanes.raster;
+    CAMA_CUDA_TRY(mark(3));
+    RasterArgs r{};
+    r.n_items = n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
+    r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
+    r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.image_base = image_base;
+    if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
+    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    r.lists = lists; r.list_counts = list_counts;
+    r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
+    const unsigned raster_grid = (unsigned)std::min<long long>(n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
+    const bool rpdl = pdl && !lanes_split;
+    if (d->overlay_records) {
+        r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
+        if (d->overlay_format == CAMA_OVERLAY_PALETTE) {
+            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+            CAMA_CUDA_TRY(launch_k(rpdl, binned_raster_kernel<3>, raster_grid, kRasterBlock, p.raster_smem, s, r));
+        } else {
+            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+            CAMA_CUDA_TRY(launch_k(rpdl, binned_raster_kernel<2>, raster_grid, kRasterBlock, p.raster_smem, s, r));
+        }
+    } else if (d->background) {
+        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+        CAMA_CUDA_TRY(launch_k(rpdl, binned_raster_kernel<1>, raster_grid, kRasterBlock, p.raster_smem, s, r));
+    } else {
+        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
+        CAMA_CUDA_TRY(launch_k(rpdl, binned_raster_kernel<0>, raster_grid, kRasterBlock, p.raster_smem, s, r));
+    }
+    CAMA_LAUNCHED(ctx);
+    CAMA_CUDA_TRY(mark(4));
     return CAMA_OK;
 }
 
@@ -1181,8 +1391,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     // phase events of this call, when profiling is on (cama_ctx_profile_enable)
     cudaEvent_t *prof = nullptr;
     if (ctx->prof_calls < ctx->prof_capacity) prof = ctx->prof_events.data() + (size_t)(ctx->prof_calls++) * (CAMA_CLIP_PHASES + 1);
-    auto mark = [&](int i) { return prof ? cudaEventRecord(prof[i], s) : cudaSuccess; };
-    CAMA_CUDA_TRY(mark(0));
 
     CamBlock cams;
     for (int c = 0; c < CAMA_MAX_CAMERAS; ++c) {
@@ -1193,144 +1401,100 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     }
     for (int i = 0; i < 6; ++i) cams.box[i] = d->crop_box[i];
 
-    ClipArgs a{};
-    a.n_frames = d->n_frames; a.n_cams = d->n_cams; a.n_instances = d->n_instances;
-    a.height = d->height; a.width = d->width; a.n_vertices = d->n_vertices;
-    a.vertices = d->vertices; a.vertex_instance = d->vertex_instance;
-    a.w2c64 = reinterpret_cast<const double *>(ws + p.off_w2c64);
-    a.crop_counts = d->crop_counts; a.visible_counts = d->visible_counts; a.vu_dense = d->vu_dense;
-    a.tile_bounds = d->tile_bounds;
-    unsigned *lut = reinterpret_cast<unsigned *>(ws + p.off_lut);
-    ClipStatsDev *stats = reinterpret_cast<ClipStatsDev *>(ws + p.off_stats);
+    ctx->last_render_grouped = p.groups > 1 && !prof;
+    if (p.groups <= 1 || prof) {                       // one pass, one stream (phase events would serialise the lanes anyway)
+        ClipPlan whole = p;
+        if (p.groups > 1) {
+            rc = make_plan(d, whole, false);
+            if (rc != CAMA_OK) return rc;
+        }
+        Lanes lanes{s, s, s, nullptr, nullptr};
+        return render_pass(ctx, d, whole, ws, cams, lanes, prof, 0, true);
+    }
 
-    if (d->vu_dense)
-        CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
+    // Frame-group pipeline.  Lane 0 = the caller's stream: prep + geometry of every group, back to back; lane 1:
+    // scan + scatter of a group once its geometry is done; lane 2: its raster once it is sorted.  The geometry
+    // (FP64 issue-bound, no memory traffic) of group g+1 thus runs under the raster (store-bound) of group g.
+    if (!ctx->pipe_streams[0]) {
+        int lo = 0, hi = 0;
+        CAMA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        static const int raster_prio = getenv("CAMA_PIPE_RASTER_PRIO") ? atoi(getenv("CAMA_PIPE_RASTER_PRIO")) : 0;
+        CAMA_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->pipe_streams[0], cudaStreamNonBlocking, raster_prio ? hi : lo));
+        CAMA_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->pipe_streams[1], cudaStreamNonBlocking, raster_prio ? hi : lo));
+    }
+    while (ctx->pipe_events.size() < (size_t)(2 * p.groups + 1)) {
+        cudaEvent_t e;
+        CAMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    cudaStream_t s_sort = ctx->pipe_streams[0], s_raster = ctx->pipe_streams[1];
+    // (the side lanes only ever start after an event recorded on the caller's stream, i.e. after everything enqueued there before)
+    cudaEvent_t e_join = ctx->pipe_events[2 * p.groups];
+    const size_t image_bytes = (size_t)d->height * d->width * 3;
+    ClipPlan q;                                                // every slice has the layout of a full group
     {
-        const bool binned = p.mode == CAMA_CLIP_BINNED;
-        const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
-        const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
-        // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
-        CAMA_CUDA_TRY(launch_k(binned && pdl_enabled() && !prof, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
-                               d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
-                               d->instance_bgr, d->n_instances, lut,
-                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : (unsigned *)nullptr, zero_words,
-                               reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                               d->overlay_records ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
-        CAMA_LAUNCHED(ctx);
+        cama_clip_desc full = *d;
+        full.n_frames = p.group_frames;
+        rc = make_plan(&full, q, false);
+        if (rc != CAMA_OK) return rc;
+        if (q.total > p.group_stride) return fail(CAMA_E_WORKSPACE, "internal: group plan larger than its slice");
     }
-    const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
-    const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
-    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 16));
-    const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
-    const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;
-
-    if (p.mode == CAMA_CLIP_PLANE) {
-        a.plane = reinterpret_cast<unsigned *>(ws + p.off_plane);
-        const size_t px = (size_t)d->n_frames * d->n_cams * d->height * d->width;
-        CAMA_CUDA_TRY(cudaMemsetAsync(a.plane, 0, sizeof(unsigned) * px, s));
-        CAMA_CUDA_TRY(mark(1));
-        if (units > 0) {
-            CAMA_CUDA_TRY(launch_geometry<false>(false, f32, debug, geo_grid, s, a, cams));
-            CAMA_LAUNCHED(ctx);
-        }
-        CAMA_CUDA_TRY(mark(2));
-        CAMA_CUDA_TRY(mark(3));
-        plane_raster_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(a.plane, lut, d->background, d->frames, d->height, d->width,
-                                                                        (long long)d->n_frames * d->n_cams);
-        CAMA_LAUNCHED(ctx);
-        CAMA_CUDA_TRY(mark(4));
-        return CAMA_OK;
+    for (int g = 0; g < p.groups; ++g) {
+        const int f0 = g * p.group_frames;
+        cama_clip_desc sub = *d;
+        sub.n_frames = std::min(p.group_frames, d->n_frames - f0);
+        sub.world2chassis = d->world2chassis + (size_t)f0 * 16;
+        if (d->frames) sub.frames = d->frames + (size_t)f0 * d->n_cams * image_bytes;
+        if (d->background) sub.background = d->background + (size_t)f0 * d->n_cams * image_bytes;
+        Lanes lanes{s, s_sort, s_raster, ctx->pipe_events[2 * g], ctx->pipe_events[2 * g + 1]};
+        rc = render_pass(ctx, &sub, q, ws + (size_t)g * p.group_stride, cams, lanes, nullptr, f0 * d->n_cams, g == 0);
+        if (rc != CAMA_OK) return rc;
     }
-
-    // BINNED (phase events between the kernels would serialise them anyway: no PDL while profiling)
-    const bool pdl = pdl_enabled() && !prof;
-    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.pool_cap = (long long)d->n_frames * p.cap;
-    a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
-    a.pool_count = reinterpret_cast<unsigned *>(ws + p.off_counter) + 1;      // word 0 of the counter block is spare
-    a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
-    a.pool = reinterpret_cast<uint2 *>(ws + p.off_pool);
-    unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
-    unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
-    CAMA_CUDA_TRY(mark(1));
-    if (units > 0) {
-        // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
-        if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
-            unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
-            unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
-            CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
-                                   (d->n_frames + kGeoFrames - 1) / kGeoFrames, d->n_frames, cams, worklist, n_live));
-            CAMA_LAUNCHED(ctx);
-            a.worklist = worklist;
-            a.n_live = n_live;
-        }
-        CAMA_CUDA_TRY(launch_geometry<true>(pdl, f32, debug, geo_grid, s, a, cams));
-        CAMA_LAUNCHED(ctx);
-    }
-    CAMA_CUDA_TRY(mark(2));
-    unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
-    unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
-    CAMA_CUDA_TRY(launch_k(pdl, bucket_scan_kernel, 1, 1024, 0, s, a.hist, start, p.n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats, lists,
-                           list_counts));
-    CAMA_LAUNCHED(ctx);
-    {   // one record per thread when the pool is full; CTAs past the records appended exit at once
-        const long long tile = 256 * kScatterPerThread;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, 1 << 20));
-        CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
-    }
-    CAMA_LAUNCHED(ctx);
-    CAMA_CUDA_TRY(mark(3));
-    RasterArgs r{};
-    r.n_items = p.n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
-    r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
-    r.x_bits = p.x_bits; r.n_strips = p.n_strips;
-    if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
-    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
-    r.lists = lists; r.list_counts = list_counts;
-    r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
-    const unsigned raster_grid = (unsigned)std::min<long long>(p.n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
-    if (d->overlay_records) {
-        r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
-        if (d->overlay_format == CAMA_OVERLAY_PALETTE) {
-            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-            CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<3>, raster_grid, kRasterBlock, p.raster_smem, s, r));
-        } else {
-            CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-            CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<2>, raster_grid, kRasterBlock, p.raster_smem, s, r));
-        }
-    } else if (d->background) {
-        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<1>, raster_grid, kRasterBlock, p.raster_smem, s, r));
-    } else {
-        CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
-        CAMA_CUDA_TRY(launch_k(pdl, binned_raster_kernel<0>, raster_grid, kRasterBlock, p.raster_smem, s, r));
-    }
-    CAMA_LAUNCHED(ctx);
-    CAMA_CUDA_TRY(mark(4));
+    CAMA_CUDA_TRY(cudaEventRecord(e_join, s_raster));          // (the raster lane's last kernel waited for everything on the sort lane)
+    CAMA_CUDA_TRY(cudaStreamWaitEvent(s, e_join, 0));
     return CAMA_OK;
 }
 
 int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *workspace, void *stream, cama_clip_stats *out) {
     CAMA_REQUIRE(ctx && out && workspace, "NULL argument");
     ClipPlan p;
-    const int rc = make_plan(d, p);
+    int rc = make_plan(d, p);
     if (rc != CAMA_OK) return rc;
     DeviceGuard guard(ctx->device);
-    ClipStatsDev h{};
+    const bool grouped = p.groups > 1 && ctx->last_render_grouped;      // (phase-profiled renders are un-grouped)
+    const int n_blocks = grouped ? p.groups : 1;
+    ClipPlan q = p;
+    if (p.groups > 1) {
+        cama_clip_desc sub = *d;
+        if (grouped) sub.n_frames = p.group_frames;
+        rc = make_plan(&sub, q, false);
+        if (rc != CAMA_OK) return rc;
+    }
+    std::vector<ClipStatsDev> h((size_t)n_blocks);
     unsigned n_overlay = 0;
     const bool sparse = d->overlay_records && d->overlay_count;
-    CAMA_CUDA_TRY(cudaMemcpyAsync(&h, static_cast<const unsigned char *>(workspace) + p.off_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    for (int g = 0; g < n_blocks; ++g)
+        CAMA_CUDA_TRY(cudaMemcpyAsync(&h[g], static_cast<const unsigned char *>(workspace) + (size_t)g * p.group_stride + q.off_stats, sizeof(ClipStatsDev),
+                                      cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     if (sparse) CAMA_CUDA_TRY(cudaMemcpyAsync(&n_overlay, d->overlay_count, sizeof(n_overlay), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));      // one round trip for both counters
-    out->records_total = (int64_t)h.records_total;
-    out->records_max_per_frame = (int64_t)h.records_max_per_frame;
+    CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));      // one round trip for all counters
+    unsigned long long total = 0, max_per_frame = 0;
+    unsigned overflow = 0;
+    for (const ClipStatsDev &b : h) {
+        total += b.records_total;
+        max_per_frame = std::max(max_per_frame, b.records_max_per_frame);
+        overflow |= b.overflow;
+    }
+    out->records_total = (int64_t)total;
+    out->records_max_per_frame = (int64_t)max_per_frame;
     out->record_capacity = p.cap;
-    out->overflow = (int32_t)h.overflow;
+    out->overflow = (int32_t)overflow;
     out->mode = p.mode;
     out->band_rows = p.band_rows;
     out->n_bands = p.n_bands;
     out->overlay_records = sparse ? n_overlay : 0;
-    if (h.overflow)
-        return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", h.records_max_per_frame, p.cap);
+    if (overflow)
+        return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", max_per_frame, p.cap);
     return CAMA_OK;
 }
 

@@ -73,4 +73,9 @@ struct cama_ctx {
     std::vector<cudaEvent_t> prof_events;
     int prof_capacity = 0;
     int prof_calls = 0;
+    // frame-group pipeline of cama_clip_render (created on first use): the sort and raster lanes, and the
+    // events that order the lanes (2 per group + 2)
+    cudaStream_t pipe_streams[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> pipe_events;
+    bool last_render_grouped = false;      // workspace layout of the most recent cama_clip_render (read by cama_clip_stats_read)
 };

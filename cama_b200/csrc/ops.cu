@@ -260,7 +260,13 @@ int cama_ctx_create(int device, cama_ctx **out) {
 }
 
 int cama_ctx_destroy(cama_ctx *ctx) {
-    if (ctx) cama_ctx_profile_enable(ctx, 0);
+    if (ctx) {
+        cama_ctx_profile_enable(ctx, 0);
+        DeviceGuard guard(ctx->device);
+        for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+        for (cudaStream_t s : ctx->pipe_streams)
+            if (s) cudaStreamDestroy(s);
+    }
     delete ctx;
     return CAMA_OK;
 }

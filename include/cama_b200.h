@@ -217,7 +217,8 @@ typedef struct cama_clip_desc {
     uint32_t *overlay_count;        /* device [1]: records appended (may exceed the capacity: the excess was dropped) */
     int64_t overlay_capacity;
     int32_t overlay_format;         /* CAMA_OVERLAY_BGR | CAMA_OVERLAY_PALETTE (needs instance_palette) */
-    int32_t reserved0;
+    int32_t pipeline_frames;        /* BINNED: frames per group of the frame-group pipeline (geometry of group g+1 under the raster of
+                                     * group g, useful for clips of hundreds of frames); 0 = library default, < 0 = off */
     const uint8_t *instance_palette; /* device uint8 [n_instances]: palette entry (1..255) of every instance, or NULL */
 } cama_clip_desc;
 

@@ -415,6 +415,36 @@ def test_frame_sharding_is_exact(rt, config2_clip):
     assert bool((again == whole).all())
 
 
+def test_frame_group_pipeline_is_exact(rt, config2_clip):
+    """cama_clip_desc.pipeline_frames: the clip rendered as frame groups on three stream lanes (geometry of group
+    g+1 under the sort and raster of group g) equals the one-pass render bit for bit — dense frames, composite
+    over a background, sparse records (chunk indices carry the group's frame offset) — with a ragged last group,
+    repeated calls on one workspace, and the counters summed over the groups."""
+    from cama_b200.batched import Reproject
+    import torch
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    r = rp.renderer
+    _, w2c = rp.frame_poses("nuscenes")
+    r.pipeline_frames = -1
+    whole = rp.render_device("nuscenes", w2c=w2c).clone()
+    stats_whole = dict(r.last_stats)
+    bg = torch.randint(0, 256, whole.shape, dtype=torch.uint8, device=whole.device)
+    comp_whole = rp.render_device("nuscenes", w2c=w2c, background=bg.clone()).clone()
+    _, sparse_whole = rp("nuscenes")
+    sparse_whole = sparse_whole.copy()
+    for group in (8, 16, 24):                        # 40 frames: 5 groups; 16+16+8; 24+16
+        r.pipeline_frames = group
+        for _ in range(2):
+            got = rp.render_device("nuscenes", w2c=w2c)
+            assert bool((got == whole).all()), group
+        assert r.last_stats["records_total"] == stats_whole["records_total"] and not r.last_stats["overflow"]
+        comp = rp.render_device("nuscenes", w2c=w2c, background=bg.clone())
+        assert bool((comp == comp_whole).all()), group
+        _, sparse = rp("nuscenes")
+        assert np.array_equal(sparse, sparse_whole), group
+    r.pipeline_frames = 0
+
+
 def test_render_sharded_single_process(rt, config2_clip):
     """cama_b200.shard with no process group = the whole clip; the multi-rank path is covered by
     tests/test_shard_gloo.py (CPU) and tools/multi_gpu_check.py (gpurun --gpus N)."""
