@@ -264,79 +264,85 @@ __device__ __forceinline__ bool tile_may_survive(const double *__restrict__ b, c
 }
 
 // Large clips (sites): most (tile, 8-frame chunk) units contain nothing near the vehicle.  One thread
-// per unit evaluates the 8 culling tests and appends the live units {unit index, frame mask} to a
-// work list, so that the geometry kernel only ever starts units with something to do.
+// per (unit, frame) evaluates one culling test (8 lanes per unit, 4 units per warp); the live units
+// {unit index, frame mask} are appended to a work list, one atomic per warp, so that the geometry
+// kernel only ever starts units with something to do.  (One thread per unit, walking its 8 frames,
+// took 56 us on the 120 k units of a site: a chain of dependent loads per thread.)
+static_assert(kGeoFrames == 8, "geometry_cull_kernel packs 8 frames of a unit into 8 lanes");
 __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__restrict__ tile_bounds, const double *__restrict__ w2c64,
                                                            long long units, int n_chunks, int n_frames, const __grid_constant__ CamBlock cams,
                                                            unsigned long long *__restrict__ worklist, unsigned *__restrict__ n_live) {
-    const long long unit = (long long)blockIdx.x * 256 + threadIdx.x;
-    unsigned mask = 0;
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long unit = t >> 3;
+    const int fi = (int)(t & 7);
+    const int lane = threadIdx.x & 31;
     pdl_wait();
     pdl_trigger();
+    bool frame_live = false;
     if (unit < units) {
         const long long tile = unit / n_chunks;
-        const int f0 = (int)(unit % n_chunks) * kGeoFrames;
-        const int nf = min(kGeoFrames, n_frames - f0);
-        for (int fi = 0; fi < nf; ++fi)
-            if (tile_may_survive(tile_bounds + tile * 6, w2c64 + (size_t)(f0 + fi) * 12, cams.box)) mask |= 1u << fi;
+        const int f = (int)(unit % n_chunks) * kGeoFrames + fi;
+        frame_live = f < n_frames && tile_may_survive(tile_bounds + tile * 6, w2c64 + (size_t)f * 12, cams.box);
     }
-    const unsigned live = __ballot_sync(kFull, mask != 0u);
+    const unsigned votes = __ballot_sync(kFull, frame_live);
+    const unsigned mask = (votes >> (lane & ~7)) & 0xffu;            // frame mask of this lane's unit
+    const bool leader = fi == 0 && mask != 0u;
+    const unsigned live = __ballot_sync(kFull, leader);
     if (live == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(live) - 1;
+    const int first = __ffs(live) - 1;
     unsigned base = 0;
-    if (lane == leader) base = atomicAdd(n_live, (unsigned)__popc(live));
-    base = __shfl_sync(kFull, base, leader);
-    if (mask) worklist[base + __popc(live & ((1u << lane) - 1u))] = ((unsigned long long)unit << 8) | mask;
+    if (lane == first) base = atomicAdd(n_live, (unsigned)__popc(live));
+    base = __shfl_sync(kFull, base, first);
+    if (leader) worklist[base + __popc(live & ((1u << lane) - 1u))] = ((unsigned long long)unit << 8) | mask;
 }
 
-// Work unit = (tile of 256 vertices, chunk of 8 frames).  A thread keeps its vertex in registers and
-// walks the chunk's frames; the 8 poses sit in shared memory (broadcast reads).  Lanes hold
-// consecutive vertices, so crop survival — and with it the 6-camera tail — is almost warp-uniform
-// (polylines are spatially coherent).
+// Work unit = (tile of 256 vertices, chunk of 8 frames); each warp of the CTA takes its 32 vertices of
+// the unit through the chunk's frames on its own: the 8 poses sit in the warp's slice of shared memory
+// (broadcast reads), there is no block-level barrier, so a warp whose vertices all fall outside the crop
+// box moves on to the next unit instead of waiting for the warps that have the 6-camera tail to do (on a
+// site, where most warps of a live unit are dead, the per-unit barriers were the largest stall).  A thread
+// keeps its vertex in registers; lanes hold consecutive vertices, so crop survival — and with it the
+// 6-camera tail — is almost warp-uniform (polylines are spatially coherent).
 // NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls and every matrix entry
 // becomes a constant-bank operand of its DFMA instead of an indexed load (0 = any count up to 8).
 template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
 __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
-    __shared__ double sT[kGeoFrames][12];
-    __shared__ int s_frame_live[kGeoFrames];
+    __shared__ double sT_all[kGeoThreads / 32][kGeoFrames][12];
     __shared__ GeoStage stages[kGeoThreads / 32];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     GeoStage &stage = stages[tid >> 5];
+    double (*sT)[12] = sT_all[tid >> 5];
     const long long n_tiles = (a.n_vertices + kGeoThreads - 1) / kGeoThreads;
     const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
     const long long units = n_tiles * n_chunks;
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
-    if (BINNED && (tid & 31) == 0) stage.count = 0;
+    if (BINNED && lane == 0) stage.count = 0;
     __syncwarp();
     pdl_wait();
     pdl_trigger();
     const long long n_work = a.worklist ? (long long)*a.n_live : units;
     for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
         long long unit = w;
-        unsigned live_mask = 0xffu;
+        unsigned frame_mask = 0xffu;
         if (a.worklist) {
             const unsigned long long e = a.worklist[w];
             unit = (long long)(e >> 8);
-            live_mask = (unsigned)(e & 0xffu);
+            frame_mask = (unsigned)(e & 0xffu);
         }
         const long long tile = unit / n_chunks;
         const int f0 = (int)(unit % n_chunks) * kGeoFrames;
         const int nf = min(kGeoFrames, a.n_frames - f0);
-        __syncthreads();
-        if (tid < nf * 12) sT[tid / 12][tid % 12] = a.w2c64[(size_t)f0 * 12 + tid];
-        __syncthreads();
-        if (tid < kGeoFrames) {
-            int live = (live_mask >> tid) & 1u;
-            if (live && !a.worklist && a.tile_bounds && tid < nf) live = tile_may_survive(a.tile_bounds + tile * 6, sT[tid], cams.box) ? 1 : 0;
-            s_frame_live[tid] = live;
-        }
-        __syncthreads();
+        __syncwarp();
+        for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
+        __syncwarp();
+        if (!a.worklist && a.tile_bounds)                      // (with a work list the cull kernel has made the mask)
+            frame_mask = __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
         const long long n = tile * kGeoThreads + tid;
         double vx, vy, vz;
         int ord;
         const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
         for (int fi = 0; fi < nf; ++fi) {
-            if (!s_frame_live[fi]) continue;                   // (uniform over the CTA)
+            if (!((frame_mask >> fi) & 1u)) continue;          // (uniform over the warp)
             const int f = f0 + fi;
             const double *T = sT[fi];
             // reference cama/dataset.py:99-105: world -> chassis, then the crop box
@@ -1284,7 +1290,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
         if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
             unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
             unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
-            CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
+            CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units * kGeoFrames + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
                                    (d->n_frames + kGeoFrames - 1) / kGeoFrames, d->n_frames, cams, worklist, n_live));
             CAMA_LAUNCHED(ctx);
             a.worklist = worklist;

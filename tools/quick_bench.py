@@ -15,6 +15,7 @@ ap.add_argument("--workload", default="config2")
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--tag", default="")
 ap.add_argument("--sparse", action="store_true", help="sparse overlay output instead of dense frames")
+ap.add_argument("--ramp", type=float, default=0.4, help="seconds of untimed clock ramp (0 under ncu)")
 ap.add_argument("--graph", action="store_true", help="capture one step in a CUDA graph and replay it")
 args = ap.parse_args()
 root = tempfile.mkdtemp()
@@ -42,10 +43,10 @@ if args.graph:
 else:
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(50): step()
-    host_us = (time.perf_counter() - t0) / 50 * 1e6          # enqueue cost per step (the queue is not full yet)
+    for _ in range(50 if args.ramp > 0 else 1): step()
+    host_us = (time.perf_counter() - t0) / (50 if args.ramp > 0 else 1) * 1e6          # enqueue cost per step (the queue is not full yet)
     torch.cuda.synchronize()
-t_end = time.perf_counter() + 0.4
+t_end = time.perf_counter() + args.ramp
 while time.perf_counter() < t_end:
     step(); torch.cuda.synchronize()
 for _ in range(5): step()
