@@ -604,11 +604,21 @@ __device__ __forceinline__ void smem_max_u16(unsigned short *plane, unsigned pix
     }
 }
 
+// CAMA_RASTER_DEBUG & 32: every raster CTA logs {start, end (globaltimer ns), active bands processed} here
+// (read with cama_debug_raster_timeline; a tuning aid, not part of the ABI header)
+__device__ unsigned long long g_raster_timeline[3 * 4096];
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr int kRasterThreads = 128;            // compute threads of a raster CTA
 constexpr int kRasterWarps = kRasterThreads / 32;
 constexpr int kRasterBlock = kRasterThreads;
-constexpr int kStripPx = 256;                  // pixels of one warp strip: 8 per lane
-constexpr int kHitBytes = 128;                 // per-strip hit masks (+ one for "any strip"), padded
+constexpr int kSegPx = 64;                     // pixels of one cell: 8 lanes x 8 px, so a warp computes four cells at a time
+constexpr int kMaxSegs = 32;                   // width <= 2048
+constexpr int kHitBytes = 4 * kMaxSegs;        // per-segment hit masks
 constexpr int kZeroRows = 2;                   // image rows of zeros kept in shared memory (source of dark output)
 constexpr int kMaxPlaneRows = 32;              // band_rows + 4: one bit per plane row in a hit mask
 
@@ -616,7 +626,7 @@ struct RasterArgs {
     int n_items;                           // F*C*NB
     int n_bands, band_rows, height, width, n_instances;
     int x_bits;                            // record = ord1 : 16 | plane row : 16 - x_bits | x : x_bits
-    int n_strips;
+    int n_strips;                          // 64-px segments per row
     int debug;                             // CAMA_RASTER_DEBUG experiments: 2 = no colour lookup
     int image_base;                        // sparse output: index of the first (frame, camera) image of this launch inside the clip
     long long sorted_cap;
@@ -628,6 +638,8 @@ struct RasterArgs {
     const unsigned *lists;                 // [4][n_items]: buckets with >= 2048 / >= 256 / >= 1 records (claimed dynamically, in this order) | empty buckets (dealt round-robin)
     const unsigned *list_counts;           // [4]
     unsigned *work_counter;                // claims of active buckets beyond the first three of every CTA
+    unsigned *empty_counter;               // claims of the dynamically dealt empty buckets
+    int dyn_empty_pct, dyn_empty_per_cta;  // empty buckets held back for the CTAs that finish their active ones early: share of all, cap per CTA
     void *ov_records;                      // MODE 2 / 3: sparse output records
     unsigned *ov_count;
     long long ov_cap;
@@ -804,24 +816,29 @@ __device__ __forceinline__ void raster_cell(const unsigned short *plane, const u
     m[2] = max3_u16x2(max3_u16x2(A[0].z, t1.z, f2.z), t3.z, A[4].z);
     m[3] = max3_u16x2(max3_u16x2(A[0].w, t1.w, f2.w), t3.w, A[4].w);
     store_row<MODE>(lut, m, lane_on, out_px, bg_px, ov, chunk);
-    if (two) {
-        m[0] = max3_u16x2(max3_u16x2(A[1].x, t2.x, f3.x), t4.x, A[5].x);
-        m[1] = max3_u16x2(max3_u16x2(A[1].y, t2.y, f3.y), t4.y, A[5].y);
-        m[2] = max3_u16x2(max3_u16x2(A[1].z, t2.z, f3.z), t4.z, A[5].z);
-        m[3] = max3_u16x2(max3_u16x2(A[1].w, t2.w, f3.w), t4.w, A[5].w);
-        store_row<MODE>(lut, m, lane_on, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr, ov, chunk + (unsigned)(W >> 3));
-    }
+    // (`two` differs between the lane groups of a warp only in a band with an odd row count; the sparse modes append
+    // their records warp-collectively, so every lane goes through the second row with its own predicate)
+    m[0] = max3_u16x2(max3_u16x2(A[1].x, t2.x, f3.x), t4.x, A[5].x);
+    m[1] = max3_u16x2(max3_u16x2(A[1].y, t2.y, f3.y), t4.y, A[5].y);
+    m[2] = max3_u16x2(max3_u16x2(A[1].z, t2.z, f3.z), t4.z, A[5].z);
+    m[3] = max3_u16x2(max3_u16x2(A[1].w, t2.w, f3.w), t4.w, A[5].w);
+    store_row<MODE>(lut, m, lane_on && two, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr, ov, chunk + (unsigned)(W >> 3));
 }
 
-// One work item = one (frame, camera, band), items dealt round-robin to the CTAs.  Shared memory:
-// uint16 centre plane [(band_rows+5)][W] | hit masks (bit r of hits[s]: plane row r has a centre
-// within 2 px of strip s; hits[n_strips]: anywhere) | kZeroRows image rows of zeros.
-// Per item: scatter the bucket's records into the plane, then every warp takes (2 rows x 256 px)
-// cells: a cell whose 6-row window has no hit is dark and is bulk-stored from the shared zeros by
-// one lane (MODE 0; rows dark across the width go out as one store), a lit cell is computed and
-// stored from registers.  Bands without a record cost one thread a few bulk stores.
+// One work item = one (frame, camera, band).  Shared memory: uint16 centre plane [(band_rows+5)][W] | hit
+// masks (bit r of hits[g]: plane row r has a centre within 2 px of the 64-px segment g) | kZeroRows image
+// rows of zeros.  Per item: scatter the bucket's records into the plane; then every warp lists the lit
+// cells of the band (cell = 2 output rows x 64 px whose 6-row window has a hit: one ballot per row pair),
+// keeps the ones that fall to it, and computes four of them per pass (8 lanes x 8 px each) straight from the
+// plane, storing from registers; the dark stretches of a row pair go out as bulk stores from the shared
+// zeros, one per run of dark segments (MODE 0).  Only ~6 % of the pixels of a clip are painted: with
+// 256-px cells (one warp strip) 18 % of the cells were lit and computed, with 64-px cells far fewer.
+// Bands without a record cost one thread a few bulk stores.
+#ifndef CAMA_RASTER_MINB
+#define CAMA_RASTER_MINB 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const RasterArgs a) {
+__global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.width;
@@ -850,38 +867,19 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     __syncthreads();
     pdl_wait();                                  // everything above overlapped the tail of the scatter kernel
     pdl_trigger();
+    if ((a.debug & 32) && tid == 0 && blockIdx.x < 4096) g_raster_timeline[3 * blockIdx.x] = global_ns();
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
 
-    // Hit masks: a thread ORs the plane-row bit of each of its records into a register per strip (predicated,
-    // no indexing) and the warp publishes them once per bucket (publish_hits: one REDUX + at most one atomic
-    // per strip).  Per-record shared-memory atomicOr on the few hit words serialised ~20-fold (every lane of a
-    // warp hits the same handful of words).  Only the rare records within 2 px of a strip edge still use one.
-    constexpr int kMaxStrips = 8;                  // width <= 2048
-    unsigned hacc[kMaxStrips];
-#pragma unroll
-    for (int k = 0; k < kMaxStrips; ++k) hacc[k] = 0u;
     auto scatter = [&](unsigned rec) {
         // (the validity checks only matter after a capacity overflow, when the pool holds stale records)
         const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
         if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
             smem_max_u16(plane, row * (unsigned)W + x, ord1);
-            const unsigned bit = 1u << row, s = x / kStripPx, off = x % kStripPx;
-#pragma unroll
-            for (int k = 0; k < kMaxStrips; ++k) hacc[k] |= s == (unsigned)k ? bit : 0u;
-            if (off < 2u && s > 0u) atomicOr(&hits[s - 1], bit);
-            if (off >= kStripPx - 2u && s + 1u < (unsigned)n_strips) atomicOr(&hits[s + 1], bit);
+            const unsigned bit = 1u << row, g = x / kSegPx, off = x % kSegPx;
+            atomicOr(&hits[g], bit);
+            if (off < 2u && g > 0u) atomicOr(&hits[g - 1], bit);
+            if (off >= kSegPx - 2u && g + 1u < (unsigned)n_strips) atomicOr(&hits[g + 1], bit);
         }
-    };
-    auto publish_hits = [&] {                      // warp-collective; hits[n_strips] = OR over the strips
-        unsigned any = 0u;
-#pragma unroll
-        for (int k = 0; k < kMaxStrips; ++k) {
-            const unsigned v = __reduce_or_sync(kFull, hacc[k]);
-            hacc[k] = 0u;
-            if (v != 0u && lane == k) atomicOr(&hits[k], v);
-            any |= v;
-        }
-        if (any != 0u && lane == kMaxStrips) atomicOr(&hits[n_strips], any);
     };
     auto fetch = [&](long long begin, long long end, unsigned (&rec)[4]) {
 #pragma unroll
@@ -897,6 +895,7 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     // records are dealt round-robin; their zeros are issued by thread 0 a few at a time between active
     // buckets, so that the store queue stays fed while the warps compute.
     __shared__ int s_claim[2];
+    __shared__ unsigned short s_cells[kRasterWarps][kMaxPlaneRows / 2 * kMaxSegs / kRasterWarps + 8];    // lit cells of the band that fall to each warp: pair << 8 | segment
     const unsigned G = gridDim.x;
     const unsigned n0 = a.list_counts[0], n1 = a.list_counts[1], n2 = a.list_counts[2], n_emp = a.list_counts[3];
     const unsigned n_act = n0 + n1 + n2;
@@ -914,14 +913,18 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         blo = bhi = 0;
         if (item >= 0) { blo = a.start[item]; bhi = min((long long)a.start[item + 1], a.sorted_cap); }
     };
+    // The last dyn_empty_pct % of the empty list are not dealt: a CTA that has finished its active buckets claims
+    // them two at a time until they are gone, so the CTAs that drew light buckets take store work off the ones
+    // still computing (CTA end times spread 47..73 us around a mean of 60 with every empty dealt statically).
+    // (the held-back pool only has to cover the spread of the CTAs' finishing times: at most dyn_empty_per_cta buckets per CTA)
+    const unsigned n_dyn = MODE == 0 ? min((unsigned)((unsigned long long)n_emp * (unsigned)a.dyn_empty_pct / 100u), G * (unsigned)a.dyn_empty_per_cta) : 0u;
+    const unsigned n_static = n_emp - n_dyn;
     unsigned e_pos = blockIdx.x;                               // (thread 0) next position of this CTA in the empty list
-    const unsigned my_emp = e_pos < n_emp ? (n_emp - e_pos + G - 1u) / G : 0u;
+    const unsigned my_emp = e_pos < n_static ? (n_static - e_pos + G - 1u) / G : 0u;
     const unsigned my_act = max(1u, (n_act + G - 1u) / G);
     const unsigned empties_per_active = (my_emp + my_act - 1u) / my_act;
-    auto issue_empties = [&](unsigned k) {
-        if (MODE != 0 || tid != 0) return;
-        for (; k > 0u && e_pos < n_emp; --k, e_pos += G) {
-            const int item = (int)empty_list[e_pos];
+    auto store_empty = [&](unsigned pos) {
+            const int item = (int)empty_list[pos];
             const int y_first = (item % a.n_bands) * a.band_rows;
             const int rows_out = min(a.band_rows, a.height - y_first);
             uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
@@ -932,7 +935,10 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
                 off += n; left -= n;
             }
             bulk_commit_group();
-        }
+    };
+    auto issue_empties = [&](unsigned k) {
+        if (MODE != 0 || tid != 0) return;
+        for (; k > 0u && e_pos < n_static; --k, e_pos += G) store_empty(e_pos);
     };
 
     unsigned a2 = blockIdx.x + 2u * G;
@@ -942,7 +948,8 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
     bounds(item0, lo, hi);
     bounds(item1, nlo, nhi);
     fetch(lo, hi, pre);
-    for (int it = 0; item0 >= 0; ++it) {
+    int n_done = 0;
+    for (int it = 0; item0 >= 0; ++it, ++n_done) {
         int claim = 0;
         if (tid == 0) claim = (int)(3u * G + atomicAdd(a.work_counter, 1u));     // list position for three iterations from now
         const int item2 = item_at(a2);
@@ -967,55 +974,57 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
 #pragma unroll
                 for (int q = 0; q < 4; ++q) scatter(rec[q]);
             }
-            publish_hits();
             sync_compute();
-            // 2. cells: dilation + colour + store
-            const unsigned hit_any = hits[n_strips];
+            // 2. cells: dilation + colour + store.  Every warp walks the row pairs (lane = segment): a ballot gives the
+            // pair's lit segments, lit cells are numbered in band order, batches of four go to the warps round-robin
+            // and each warp notes its own; the dark runs of pair p are stored by warp p % 4.
             const int n_pairs = (rows_out + 1) >> 1;
-            // cell (pair p, strip s): warps take cells round-robin, the strip rotated by the pair index so
-            // that no warp keeps one strip; indices advance without integer division
-            int p = 0, s = warp, rot = 0;
-            for (;;) {
-                while (s >= n_strips) { s -= n_strips; ++p; if (++rot == n_strips) rot = 0; }
-                if (p >= n_pairs) break;
-                int sr = s + rot;
-                if (sr >= n_strips) sr -= n_strips;
-                const int y = 2 * p;
+            const bool all_cells = MODE == 1 && !inplace;                       // out-of-place composite: every cell is written
+            const unsigned my_hits = lane < n_strips ? hits[lane] : 0u;
+            const unsigned seg_all = n_strips >= 32 ? kFull : (1u << n_strips) - 1u;
+            unsigned short *my_cells = s_cells[warp];
+            unsigned n_lit = 0;                                                  // (warp-uniform)
+            for (int pp = 0; pp < n_pairs; ++pp) {
+                const int y = 2 * pp;
                 const bool two = y + 1 < rows_out;
-                const unsigned window = two ? 0x3fu : 0x1fu;
-                const int xs = sr * kStripPx;
-                uint8_t *out_row = out_base + (size_t)y * row_bytes;
-                const bool lit = ((hits[sr] >> y) & window) != 0u;
-                if (lit || (MODE == 1 && !inplace)) {
-                    const int x0 = xs + lane * 8;
-                    const bool lane_on = x0 < W;
-                    const int xc = min(x0, W - 8);                             // lanes past the edge recompute the last 8 px, store nothing
-                    if (lit)
-                        raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_row + (size_t)x0 * 3,
-                                          MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes,
-                                          ov, chunk_base + (unsigned)((y * W + x0) >> 3));
-                    else if (lane_on) {                                        // out-of-place composite of a dark cell: copy
-                        for (int r = 0; r < (two ? 2 : 1); ++r) {
-                            const uint2 *b = reinterpret_cast<const uint2 *>(bg_base + (size_t)(y + r) * row_bytes + (size_t)x0 * 3);
-                            uint2 *d = reinterpret_cast<uint2 *>(out_row + (size_t)r * row_bytes + (size_t)x0 * 3);
-                            const uint2 b0 = b[0], b1 = b[1], b2 = b[2];
-                            d[0] = b0; d[1] = b1; d[2] = b2;
+                const bool lit = lane < n_strips && (all_cells || ((my_hits >> y) & (two ? 0x3fu : 0x1fu)) != 0u);
+                const unsigned m = __ballot_sync(kFull, lit);
+                if (lit) {
+                    const unsigned idx = n_lit + (unsigned)__popc(m & ((1u << lane) - 1u)), batch = idx >> 2;
+                    if (batch % kRasterWarps == (unsigned)warp) my_cells[((batch / kRasterWarps) << 2) | (idx & 3u)] = (unsigned short)((pp << 8) | lane);
+                }
+                n_lit += (unsigned)__popc(m);
+                if (MODE == 0 && pp % kRasterWarps == warp) {
+                    const unsigned dark = ~m & seg_all;
+                    if (((dark >> lane) & 1u) && (lane == 0 || !((dark >> (lane - 1)) & 1u))) {          // first segment of a dark run
+                        const unsigned after = m & ~((2u << lane) - 1u);                                    // lit segments beyond it
+                        const int x_a = lane * kSegPx, x_b = min((after ? __ffs(after) - 1 : n_strips) * kSegPx, W);
+                        uint8_t *dst = out_base + (size_t)y * row_bytes + (size_t)x_a * 3;
+                        const unsigned bytes = (unsigned)(x_b - x_a) * 3u;
+                        if (two && bytes == row_bytes) {
+                            bulk_store_shared_to_global(dst, zeros, 2u * row_bytes);                        // dark across the width: both rows at once
+                        } else {
+                            bulk_store_shared_to_global(dst, zeros, bytes);
+                            if (two) bulk_store_shared_to_global(dst + row_bytes, zeros, bytes);
                         }
-                    }
-                } else if (MODE == 0 && lane == 0) {
-                    if (((hit_any >> y) & window) == 0u) {                     // dark across the width: whoever has strip 0 writes whole rows
-                        if (sr == 0) {
-                            bulk_store_shared_to_global(out_row, zeros, (two ? 2u : 1u) * row_bytes);
-                            bulk_commit_group();
-                        }
-                    } else {
-                        const unsigned strip_bytes = (unsigned)min(kStripPx, W - xs) * 3u;
-                        bulk_store_shared_to_global(out_row + (size_t)xs * 3, zeros, strip_bytes);
-                        if (two) bulk_store_shared_to_global(out_row + row_bytes + (size_t)xs * 3, zeros, strip_bytes);
                         bulk_commit_group();
                     }
                 }
-                s += kRasterWarps;
+            }
+            __syncwarp();
+            const unsigned n_batches = (n_lit + 3u) >> 2;
+            for (unsigned b = (unsigned)warp; b < n_batches; b += kRasterWarps) {
+                const unsigned k = (b << 2) | (unsigned)(lane >> 3);           // the cell of this lane group, in band order
+                const bool active = k < n_lit;
+                const unsigned cell = active ? my_cells[((b / kRasterWarps) << 2) | (unsigned)(lane >> 3)] : 0u;
+                const int y = 2 * (int)(cell >> 8);
+                const bool two = y + 1 < rows_out;
+                const int x0 = (int)(cell & 0xffu) * kSegPx + (lane & 7) * 8;
+                const bool lane_on = active && x0 < W;
+                const int xc = min(x0, W - 8);                                 // lanes past the edge recompute the last 8 px, store nothing
+                raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_base + (size_t)y * row_bytes + (size_t)x0 * 3,
+                                  MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes,
+                                  ov, chunk_base + (unsigned)((y * W + x0) >> 3));
             }
             sync_compute();
             // 3. restore the all-zero plane (clearing all of it costs fewer instructions than picking the rows hit)
@@ -1025,7 +1034,7 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
 #pragma unroll 4
                 for (int i = tid; i < n16; i += kRasterThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-            if (tid <= n_strips) hits[tid] = 0u;
+            if (tid < kMaxSegs) hits[tid] = 0u;
         }
         // publish the claim (this barrier also orders the clean-up before the next scatter) and advance the pipeline
         if (tid == 0) s_claim[it & 1] = claim;
@@ -1037,6 +1046,19 @@ __global__ void __launch_bounds__(kRasterBlock, 4) binned_raster_kernel(const Ra
         a2 = (unsigned)s_claim[it & 1];
     }
     issue_empties(0xffffffffu);
+    if (MODE == 0 && tid == 0) {
+        unsigned pos = n_static + atomicAdd(a.empty_counter, 2u);
+        while (pos < n_emp) {
+            const unsigned next = n_static + atomicAdd(a.empty_counter, 2u);      // (in flight while this pair is stored)
+            store_empty(pos);
+            if (pos + 1u < n_emp) store_empty(pos + 1u);
+            pos = next;
+        }
+    }
+    if ((a.debug & 32) && tid == 0 && blockIdx.x < 4096) {
+        g_raster_timeline[3 * blockIdx.x + 1] = global_ns();
+        g_raster_timeline[3 * blockIdx.x + 2] = (unsigned long long)n_done;
+    }
     if (MODE == 2 && ov.st->count > 0u) ov_flush<8>(ov);
     if (MODE == 3 && ov.st->count > 0u) ov_flush<3>(ov);
     // the shared zeros must stay valid until the last bulk stores have read them
@@ -1101,6 +1123,8 @@ struct ClipPlan {
 };
 
 constexpr int kRasterCtasPerSm = 4;
+constexpr int kDynEmptyPerCta = 5;
+constexpr int kDynEmptyPct = 60;                 // measured on config 2: 0 % 78.5 us, 40 % 74.4, 60 % 73.4, 80 % 75.5, 100 % 78.6 (CAMA_RASTER_DYN_EMPTY)
 constexpr int kDefaultBandRows = 16;
 template <bool BINNED>
 cudaError_t launch_geometry(bool pdl, bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
@@ -1168,7 +1192,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         p.band_rows = band_rows;
         p.x_bits = x_bits;
         p.n_bands = (H + band_rows - 1) / band_rows;
-        p.n_strips = (W + kStripPx - 1) / kStripPx;
+        p.n_strips = (W + kSegPx - 1) / kSegPx;
 
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
         CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
@@ -1331,7 +1355,13 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     r.lists = lists; r.list_counts = list_counts;
     r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
-    const unsigned raster_grid = (unsigned)std::min<long long>(n_buckets, (long long)ctx->sm_count * kRasterCtasPerSm);
+    r.empty_counter = reinterpret_cast<unsigned *>(ws + p.off_counter) + 3;
+    static const int dyn_empty_pct = getenv("CAMA_RASTER_DYN_EMPTY") ? std::min(100, std::max(0, atoi(getenv("CAMA_RASTER_DYN_EMPTY")))) : kDynEmptyPct;
+    static const int dyn_empty_per_cta = getenv("CAMA_RASTER_DYN_PER_CTA") ? std::max(0, atoi(getenv("CAMA_RASTER_DYN_PER_CTA"))) : kDynEmptyPerCta;
+    r.dyn_empty_pct = dyn_empty_pct;
+    r.dyn_empty_per_cta = dyn_empty_per_cta;
+    static const int raster_ctas = getenv("CAMA_RASTER_CTAS") ? std::max(1, atoi(getenv("CAMA_RASTER_CTAS"))) : kRasterCtasPerSm;      // experiment knob
+    const unsigned raster_grid = (unsigned)std::min<long long>(n_buckets, (long long)ctx->sm_count * raster_ctas);
     const bool rpdl = pdl && !lanes_split;
     if (d->overlay_records) {
         r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
@@ -1501,6 +1531,14 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->overlay_records = sparse ? n_overlay : 0;
     if (overflow)
         return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", max_per_frame, p.cap);
+    return CAMA_OK;
+}
+
+// tuning aid (CAMA_RASTER_DEBUG & 32): copies the per-CTA {start ns, end ns, active bands} log of the last raster launch
+int cama_debug_raster_timeline(unsigned long long *out, int n_ctas) {
+    CAMA_REQUIRE(out && n_ctas > 0 && n_ctas <= 4096, "bad argument");
+    CAMA_CUDA_TRY(cudaDeviceSynchronize());
+    CAMA_CUDA_TRY(cudaMemcpyFromSymbol(out, g_raster_timeline, sizeof(unsigned long long) * 3 * (size_t)n_ctas));
     return CAMA_OK;
 }
 
