@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="CUDA streams the K steps are dealt over (independent clips overlap); 1 = one stream")
     ap.add_argument("--ramp-seconds", type=float, default=0.4, help="untimed clock-ramp loop before the warm-up (0 under ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded cpu_baseline sample")
     return ap.parse_args()
@@ -272,6 +273,35 @@ def run_b200(args):
     def step():
         rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=False)
 
+    # Throughput mode: the K steps are dealt over `lanes` streams, each with its own workspace and output frames,
+    # so that independent clips overlap (geometry of one under the store-bound raster of the other).
+    n_lanes = max(1, args.lanes)
+    lane_streams = [torch.cuda.Stream(device=rt.device) for _ in range(n_lanes)]
+    lane_frames = [frames] + [torch.empty_like(frames) for _ in range(n_lanes - 1)]
+
+    def lane_step(k):
+        lane = k % n_lanes
+        with torch.cuda.stream(lane_streams[lane]):
+            rp.renderer.render(res, w2c_dev, out=lane_frames[lane], mode=args.mode, check=False, lane=lane)
+
+    def timed_lanes(steps):
+        """-> ms for `steps` steps over the lanes, from an event on the main stream before the first launch to one
+        after the last kernel of every lane."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for ls in lane_streams:
+            ls.wait_event(e0)
+        for k in range(steps):
+            lane_step(k)
+        for ls in lane_streams:
+            done = torch.cuda.Event()
+            done.record(ls)
+            stream.wait_event(done)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
     # sizing pass: settles the record-pool capacity (checked, synchronous) and verifies no overflow
     rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=True)
     stats = dict(rp.renderer.last_stats)
@@ -285,22 +315,27 @@ def run_b200(args):
     while time.perf_counter() < t_end:
         step()
         torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for k in range(max(args.warmup, 3) * n_lanes):
+        lane_step(k)
+    torch.cuda.synchronize()
+    for lf in lane_frames[1:]:
+        assert torch.equal(lf, frames), "lanes disagree"
 
-    # ---- device-resident throughput: exactly K steps between two events, nothing else on the stream
+    # ---- device-resident throughput: exactly K steps, nothing else on the streams
     # (the kernels of a step are chained by programmatic dependent launch; events between them would serialise them)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = rt.launches()
-    barrier()
     sampler.load(True)
+    ms_total = timed_lanes(args.steps)
+    launches = rt.launches() - launches0
+    # the same K steps on one stream (what a single clip sees)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     barrier()
-    launches = rt.launches() - launches0
-    ms_total = ev0.elapsed_time(ev1)
+    ms_single = ev0.elapsed_time(ev1)
 
     # ---- the same K steps again with CUDA events recorded on the launching stream around every phase
     # (cama_ctx_profile_*): the per-kernel durations the roofline is computed from
@@ -365,6 +400,7 @@ def run_b200(args):
         return float(t.item())
 
     ms_total = max_over_ranks(ms_total)
+    ms_single = max_over_ranks(ms_single)
     e2e_s = max_over_ranks(e2e_s)
     dense_s = max_over_ranks(dense_s)
     if gather is not None:
@@ -398,7 +434,11 @@ def run_b200(args):
                        "instances": res.n_instances, "raster_mode": {1: "plane", 2: "binned"}[stats["mode"]],
                        "l2": f"no flush needed: every step writes {frame_bytes / 1e6:.0f} MB of frames (> 126 MB L2); "
                              f"the {res.n_vertices * 16 / 1e6:.1f} MB vertex array is L2-resident by nature (re-read for each of the {F} frames)",
-                       "background": "blank (black) frames, as in the reference CPU timing"},
+                       "background": "blank (black) frames, as in the reference CPU timing",
+                       "streams": n_lanes,
+                       "streams_note": f"the K steps are dealt over {n_lanes} CUDA streams with separate workspaces and output frames (independent clips "
+                                       "overlap); single_stream = the same K steps back to back on one stream"},
+            "single_stream": {"value": world * cam_frames / (ms_single / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_single / args.steps},
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "e2e": {"value": world * cam_frames * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(w2c_host.nbytes), "d2h_bytes_per_step": int(transfer["d2h_bytes"]) + 48,

@@ -136,8 +136,12 @@ class ClipRenderer:
             d.instance_palette = res.palette_index.data_ptr() if fmt == N.OVERLAY_PALETTE else None
         return d
 
-    def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False):
+    def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False, lane=0):
         """Enqueue one clip on the current stream.
+
+        lane        which workspace to use: clips enqueued on different torch streams must use different lanes
+                    (the kernels of independent clips then overlap: the geometry of one runs under the raster of
+                    the other)
 
         res         _Resident from :meth:`resident`
         w2c_dev     torch float32 [F,16] (or [F,4,4]) on this device
@@ -166,7 +170,7 @@ class ClipRenderer:
             desc = self._desc(res, w2c_dev, n_frames, out, background, mode, capacity, dbg)
             need = ctypes.c_size_t()
             N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
-            ws = rt.scratch("clip", need.value)
+            ws = rt.scratch("clip" if lane == 0 else f"clip{lane}", need.value)
             N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
             if not check:
                 break
