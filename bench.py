@@ -375,7 +375,7 @@ def run_b200(args):
     assert checksum == checksum_dense, "sparse and dense transfers disagree"
 
     # ---- optional: the all-gather of rendered frames north_star names (N > 1)
-    gather = None
+    gather = gather_sparse_s = None
     if world > 1 and not args.no_allgather:
         full = torch.empty((world * F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
         for _ in range(2):
@@ -389,6 +389,27 @@ def run_b200(args):
         g1.record(stream)
         barrier()
         gather = g0.elapsed_time(g1)
+        # the same exchange, sparse: every rank renders lit-chunk records, the records are all-gathered and each rank
+        # rebuilds all dense frames with cama_overlay_expand (cama_b200/shard.py); same bytes in HBM at the end
+        from cama_b200 import shard
+        r = rp.renderer
+
+        def sparse_step():
+            records, n, fmt = r.render_overlay(res, w2c_dev, mode=args.mode)
+            everyone, counts = shard.gather_records(records, n)
+            for peer in range(world):
+                r.expand_overlay(everyone[peer], counts[peer], fmt, res.palette, F, out=full[peer * F:(peer + 1) * F])
+
+        for _ in range(2):
+            sparse_step()
+        gather_check = bool((full[rank * F:(rank + 1) * F] == frames).all())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sparse_step()
+        barrier()
+        gather_sparse_s = time.perf_counter() - t0
+        assert gather_check, "sparse all-gather: own block differs from the dense render"
 
     clocks = sampler.stop()
 
@@ -405,6 +426,7 @@ def run_b200(args):
     dense_s = max_over_ranks(dense_s)
     if gather is not None:
         gather = max_over_ranks(gather)
+        gather_sparse_s = max_over_ranks(gather_sparse_s)
 
     if rank == 0:
         peaks = {}
@@ -471,7 +493,11 @@ def run_b200(args):
             ms_g = gather / args.steps
             line["allgather"] = {"value": world * cam_frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
                                  "bytes_received_per_gpu": int((world - 1) * frame_bytes),
-                                 "note": "render + NCCL all_gather_into_tensor of the uint8 frames of all ranks"}
+                                 "note": "render + NCCL all_gather_into_tensor of the uint8 frames of all ranks",
+                                 "sparse": {"value": world * cam_frames * args.steps / gather_sparse_s, "unit": UNIT,
+                                            "ms_per_step": 1e3 * gather_sparse_s / args.steps,
+                                            "note": "sparse render + NCCL all-gather of the lit-chunk records + cama_overlay_expand of every rank's "
+                                                    "records into dense frames on every rank (host-timed, includes the record-count read-back)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -259,6 +259,27 @@ class ClipRenderer:
         raise N.CamaError(N.CAMA_E_CAPACITY, "record pools kept overflowing")
 
 
+    def expand_overlay(self, records, n, fmt, palette, n_frames, out=None, zero_first=True):
+        """cama_overlay_expand: overlay records (device) -> dense frames torch uint8 [n_frames,C,H,W,3] on the device.
+
+        records  torch int32 [>= n, 3 or 8] on this device (render_overlay's output, possibly gathered from other ranks)
+        palette  host uint8 [256,3] (``_Resident.palette``) for the palette format
+        """
+        import torch
+        rt = self.rt
+        shape = (int(n_frames), self.n_cams, self.height, self.width, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=rt.device)
+        assert tuple(out.shape) == shape and out.dtype == torch.uint8 and out.is_contiguous()
+        pal_dev = scratch = None
+        if fmt == N.OVERLAY_PALETTE:
+            pal_dev = rt.to_device(np.ascontiguousarray(palette, dtype=np.uint8))
+            scratch = rt.scratch("palette32", 1024)
+        N.check(N.lib().cama_overlay_expand(rt.ctx, rt.ptr(records), int(n), fmt, rt.ptr(pal_dev), rt.ptr(scratch), rt.ptr(out),
+                                            int(n_frames), self.n_cams, self.height, self.width, 1 if zero_first else 0, rt.stream()))
+        return out
+
+
 class Reproject:
     """Batched drop-in for the frame loop: ``Reproject(configs, clip_path)(dataset)``."""
 

@@ -47,6 +47,69 @@ inline void apply_one(uint8_t *dst, const uint8_t *bgr, unsigned mask, int op) {
 
 }  // namespace
 
+// ---- device side: records -> dense frames (the receiving end of a sparse all-gather) --------------------
+// One thread per record: 24 bytes (8 BGR pixels) written as three 8-byte stores at chunk * 24.  The frames are
+// zero-filled first (cudaMemsetAsync), so the result equals the dense render of the same clip on blank frames.
+template <int FORMAT>
+__global__ void __launch_bounds__(256) overlay_expand_kernel(const uint32_t *__restrict__ records, long long n, const uint32_t *__restrict__ palette,
+                                                            uint8_t *__restrict__ frames, long long n_chunks) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[6];
+    uint32_t chunk;
+    if (FORMAT == CAMA_OVERLAY_BGR) {
+        const uint4 a = reinterpret_cast<const uint4 *>(records)[2 * i], b = reinterpret_cast<const uint4 *>(records)[2 * i + 1];
+        chunk = a.x;                                   // a.y = mask: unpainted pixels of a record are 0,0,0 already
+        w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
+    } else {
+        const uint32_t *r = records + 3 * i;
+        chunk = r[0];
+        const uint32_t lo = r[1], hi = r[2];
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c[k] = palette[(lo >> (8 * k)) & 0xffu];
+            c[4 + k] = palette[(hi >> (8 * k)) & 0xffu];
+        }
+        w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
+        w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
+    }
+    if ((long long)chunk >= n_chunks) return;
+    uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk * 24);
+    d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+}
+
+__global__ void palette_pack_kernel(const uint8_t *__restrict__ palette_bgr, uint32_t *__restrict__ packed) {
+    const int e = threadIdx.x;
+    packed[e] = e == 0 ? 0u : (uint32_t)palette_bgr[3 * e] | ((uint32_t)palette_bgr[3 * e + 1] << 8) | ((uint32_t)palette_bgr[3 * e + 2] << 16);
+}
+
+extern "C" int cama_overlay_expand(cama_ctx *ctx, const void *records, int64_t n, int format, const uint8_t *palette_bgr, void *palette_scratch,
+                                   uint8_t *frames, int64_t n_frames, int n_cams, int height, int width, int zero_first, void *stream) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    CAMA_REQUIRE(n >= 0 && n_frames >= 0 && n_cams > 0 && height > 0 && width > 0 && width % 8 == 0, "bad shape");
+    CAMA_REQUIRE(format == CAMA_OVERLAY_BGR || format == CAMA_OVERLAY_PALETTE, "bad format");
+    CAMA_REQUIRE(format != CAMA_OVERLAY_PALETTE || (palette_bgr && palette_scratch), "the palette format needs palette_bgr and palette_scratch (device)");
+    const int64_t n_chunks = n_frames * n_cams * height * (width / 8);
+    if (n_chunks == 0) return CAMA_OK;
+    CAMA_REQUIRE(frames && ((uintptr_t)frames & 7) == 0, "frames must be 8-byte aligned");
+    CAMA_REQUIRE(n == 0 || (records && ((uintptr_t)records & (format == CAMA_OVERLAY_BGR ? 15 : 3)) == 0), "records must be 16-byte (BGR) / 4-byte (palette) aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) CAMA_CUDA_TRY(cudaMemsetAsync(frames, 0, (size_t)n_chunks * 24, s));
+    if (n == 0) return CAMA_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (format == CAMA_OVERLAY_PALETTE) {
+        palette_pack_kernel<<<1, 256, 0, s>>>(palette_bgr, static_cast<uint32_t *>(palette_scratch));
+        CAMA_LAUNCHED(ctx);
+        overlay_expand_kernel<CAMA_OVERLAY_PALETTE><<<grid, 256, 0, s>>>(static_cast<const uint32_t *>(records), n, static_cast<const uint32_t *>(palette_scratch), frames, n_chunks);
+    } else {
+        overlay_expand_kernel<CAMA_OVERLAY_BGR><<<grid, 256, 0, s>>>(static_cast<const uint32_t *>(records), n, nullptr, frames, n_chunks);
+    }
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
 extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int format, const uint8_t *palette_bgr,
                                        const cama_overlay_target *target, int op, int n_threads) {
     CAMA_REQUIRE(n >= 0, "negative size");

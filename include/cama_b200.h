@@ -268,6 +268,18 @@ enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS =
 int cama_overlay_apply_host(const void *records, int64_t n, int format, const uint8_t *palette_bgr,
                             const cama_overlay_target *target, int op, int n_threads);
 
+/* ---- device side of the sparse output: records -> dense frames ---------------------------------- */
+
+/* Expands `n` overlay records (device) into dense frames uint8 [n_frames,n_cams,H,W,3] (device): the frames are
+ * zero-filled first when zero_first != 0, then every record's 8 pixels are written.  With the records of
+ * cama_clip_render's sparse output this reproduces its dense output on blank frames byte for byte.  It is the
+ * receiving end of a sparse all-gather (cama_b200/shard.py): ranks exchange the lit chunks (~4 % of the dense
+ * bytes) instead of the uint8 frames north_star's all-gather moves, and rebuild the frames at HBM speed.
+ * palette_bgr: device uint8 [256,3] (CAMA_OVERLAY_PALETTE only); palette_scratch: device, 1 KiB. */
+int cama_overlay_expand(cama_ctx *ctx, const void *records, int64_t n, int format, const uint8_t *palette_bgr,
+                        void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams, int height, int width,
+                        int zero_first, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -445,6 +445,31 @@ def test_frame_group_pipeline_is_exact(rt, config2_clip):
     r.pipeline_frames = 0
 
 
+def test_overlay_expand_equals_dense(rt, config2_clip):
+    """cama_overlay_expand (the receiving end of the sparse all-gather): the records of the sparse output, expanded
+    on the device, are the dense render byte for byte — both record formats, whole clip and a block of frames
+    expanded into the middle of a larger tensor (what every rank does with its peers' records)."""
+    from cama_b200 import _native as N
+    from cama_b200.batched import Reproject
+    import torch
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    r, res = rp.renderer, rp.resident("nuscenes")
+    _, w2c = rp.frame_poses("nuscenes")
+    dense = rp.render_device("nuscenes", w2c=w2c).clone()
+    w2c_dev = torch.from_numpy(w2c).to(rp.rt.device)
+    for fmt in (N.OVERLAY_PALETTE, N.OVERLAY_BGR):
+        records, n, got_fmt = r.render_overlay(res, w2c_dev, fmt=fmt)
+        assert got_fmt == fmt and n > 0
+        out = torch.full(dense.shape, 7, dtype=torch.uint8, device=dense.device)
+        r.expand_overlay(records, n, fmt, res.palette, dense.shape[0], out=out)
+        assert bool((out == dense).all()), fmt
+    # a block of frames (13..26) rendered on its own and expanded into its place
+    records, n, fmt = r.render_overlay(res, w2c_dev[13:26].contiguous())
+    big = torch.zeros_like(dense)
+    r.expand_overlay(records[:n].clone(), n, fmt, res.palette, 13, out=big[13:26])
+    assert bool((big[13:26] == dense[13:26]).all()) and int(big[:13].sum()) == 0 and int(big[26:].sum()) == 0
+
+
 def test_render_sharded_single_process(rt, config2_clip):
     """cama_b200.shard with no process group = the whole clip; the multi-rank path is covered by
     tests/test_shard_gloo.py (CPU) and tools/multi_gpu_check.py (gpurun --gpus N)."""

@@ -65,3 +65,38 @@ def test_gather_frames_gloo(world, n_frames):
             p.join(120)
             assert p.exitcode == 0
         assert dict(results) == {r: True for r in range(world)}
+
+
+def _records_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for words in (3, 8):
+            counts = [5 + 3 * r for r in range(world)]                  # ragged: every rank has another count
+            mine = torch.arange(counts[rank] * words, dtype=torch.int32).reshape(-1, words) + 1000 * rank
+            padded = torch.cat([mine, torch.full((4, words), -1, dtype=torch.int32)])     # capacity > count, like the device buffer
+            got, got_counts = shard.gather_records(padded, counts[rank])
+            ok = ok and got_counts == counts and tuple(got.shape) == (world, max(counts), words)
+            for r in range(world):
+                want = torch.arange(counts[r] * words, dtype=torch.int32).reshape(-1, words) + 1000 * r
+                ok = ok and bool((got[r, :counts[r]] == want).all())
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_records_gloo(world):
+    """The sparse all-gather's collective part: ragged record lists of every rank arrive intact on every rank."""
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        results = manager.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_records_worker, args=(r, world, port, results)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(results) == {r: True for r in range(world)}

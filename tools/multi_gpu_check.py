@@ -30,6 +30,8 @@ def main():
         idx, gathered = shard.render_sharded(rp, "nuscenes", gather=True)
         whole = rp.render_device("nuscenes")
         ok = len(idx) == 37 and bool((gathered == whole).all())
+        idx_s, gathered_s = shard.render_sharded(rp, "nuscenes", gather="sparse")      # records over NCCL + cama_overlay_expand
+        ok = ok and idx_s == idx and bool((gathered_s == whole).all())
         lo, hi = shard.frame_block(37, rank, world)
         idx_local, block = shard.render_sharded(rp, "nuscenes", gather=False)
         ok = ok and idx_local == idx[lo:hi] and bool((block == whole[lo:hi]).all())
