@@ -15,6 +15,7 @@ colours, camera matrices — are uploaded once per dataset and stay resident.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -302,6 +303,13 @@ class Reproject:
         self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
         self._ov_flip = 0
         self._ov_events = []
+        # threads of the host draw: this process's share of the cores (torchrun sets OMP_NUM_THREADS=1, which would
+        # make the draw serial; with N ranks on a box every rank takes 1/N of the cores)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        self.host_threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self.last_transfer = None
 
     def resident(self, dataset):
@@ -387,7 +395,7 @@ class Reproject:
             target = N.OverlayTarget(frames.ctypes.data, len(idx), C, H, W, 0 if tiles is None else 3,
                                      None if tiles is None else tiles.ctypes.data)
             N.check(N.lib().cama_overlay_apply_host(rec_ptr, count, rec_fmt, None if palette is None else palette.ctypes.data,
-                                                    ctypes.byref(target), op, 0))
+                                                    ctypes.byref(target), op, self.host_threads))
 
         blank_previous = None
         if backgrounds is not None:
