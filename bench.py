@@ -11,9 +11,11 @@ its own such clip (the scenes of a site, seeds 0..N-1), i.e. weak scaling, no da
 `allgather` additionally reports the NCCL all-gather of the rendered frames north_star asks for.
 
 One JSON line on rank 0:
-  value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM
+  value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM; the K steps are dealt
+               over --lanes CUDA streams (default 2: independent clips overlap); single_stream = one stream
   e2e          same metric through Reproject.__call__: host pose lookup + float32 inverse, H2D of
-               the poses from pinned memory, render, D2H of every frame into pinned host memory
+               the poses, render, lit-chunk records back over PCIe and drawn into the host frames
+               (e2e.dense: every frame byte copied back instead)
   roofline     the raster kernel (writes every frame byte once) against the measured HBM peak
   cpu_baseline the NumPy/OpenCV oracle (= the reference's loop) on this box's host cores
 `--impl reference` times that CPU path alone and prints the same line shape.
