@@ -57,6 +57,10 @@ class OverlayTarget(Structure):
                 ("grid_cols", c_int32), ("tile_of_cam", c_void_p)]
 
 
+class VoxelGrid(Structure):
+    _fields_ = [("origin", c_double * 3), ("voxel", c_double * 3), ("dims", c_int32 * 3), ("reserved", c_int32)]
+
+
 class ClipStats(Structure):
     _fields_ = [
         ("records_total", c_int64), ("records_max_per_frame", c_int64), ("record_capacity", c_int64),
@@ -94,6 +98,7 @@ SIGNATURES = {
     "cama_clip_render": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_size_t, c_void_p]),
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),
     "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(OverlayTarget), c_int, c_int]),
+    "cama_lidar_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cama_overlay_expand": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

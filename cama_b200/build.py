@@ -16,7 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcama_b200.so")
 STAMP_PATH = LIB_PATH + ".stamp"
-SOURCES = ["ops.cu", "clip.cu", "overlay.cu", "densify.cu", "remap.cu"]
+SOURCES = ["ops.cu", "clip.cu", "overlay.cu", "densify.cu", "remap.cu", "lidar.cu"]
 HEADERS = ["common.cuh", "geom.cuh", os.path.join("..", "..", "include", "cama_b200.h")]
 
 NVCC_FLAGS = [

@@ -314,3 +314,38 @@ def write_background_jpegs(clip_path: str, n_frames: int, cameras=None, seed=0):
                             np.full_like(xx, int(rng.integers(0, 255)))], axis=-1).astype(np.uint8)
             img[::50, :, :] = 255
             cv2.imwrite(os.path.join(clip_path, cam, f"{attribute['sync'][cam][idx]}.jpg"), img)
+
+
+def lidar_to_chassis():
+    """lidar_top mounted 1.84 m above the chassis origin, 0.94 m ahead, yawed -90 deg (nuScenes-like)."""
+    T = np.eye(4)
+    T[:3, :3] = _rot_z(-np.pi / 2)
+    T[:3, 3] = [0.94, 0.0, 1.84]
+    return T
+
+
+def write_lidar_sweeps(clip_path: str, n_sweeps: int = 40, n_points: int = 35000, seed: int = 0, ragged: bool = False):
+    """BASELINE.json configs[4] / SURVEY 8d config 5: ``n_sweeps`` sweeps of ``n_points`` points, x,y ~ U(-50,50),
+    z ~ N(0,1), rows (x y z intensity ring time) float64 — written as ``lidar_top/<ms>.bin`` the way
+    dataset/nuscenes2clip.py:550-554 writes them, with the calibration and timestamp entries
+    DatasetReader needs.  Sweep stamps = the clip's frame stamps (the first ``n_sweeps`` of them)."""
+    with open(os.path.join(clip_path, "attribute.json")) as fh:
+        attribute = json.load(fh)
+    stamps = list(attribute["sync"][CAMERA_LIST[0]])[:n_sweeps]
+    assert len(stamps) == n_sweeps, "the clip has fewer frame stamps than sweeps asked for"
+    attribute["calibration"]["lidar_top_2_chassis"] = lidar_to_chassis().tolist()
+    attribute["sync"]["lidar_top"] = stamps
+    attribute["unsync"]["lidar_top"] = stamps
+    with open(os.path.join(clip_path, "attribute.json"), "w") as fh:
+        json.dump(attribute, fh)
+    folder = os.path.join(clip_path, "lidar_top")
+    os.makedirs(folder, exist_ok=True)
+    rng = np.random.default_rng(seed + 777)
+    for k, ms in enumerate(stamps):
+        n = n_points if not ragged else int(n_points * (0.25 + 1.5 * rng.random())) * (k % 5 != 3)
+        pts = np.zeros((n, 6), dtype=np.float64)
+        pts[:, 0:2] = rng.uniform(-50.0, 50.0, size=(n, 2))
+        pts[:, 2] = rng.standard_normal(n)
+        pts[:, 3] = rng.uniform(0.0, 255.0, size=n)
+        pts.tofile(os.path.join(folder, f"{ms}.bin"))
+    return stamps

@@ -280,6 +280,32 @@ int cama_overlay_expand(cama_ctx *ctx, const void *records, int64_t n, int forma
                         void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams, int height, int width,
                         int zero_first, void *stream);
 
+/* ---- LiDAR aggregation (BASELINE.json configs[4]) -------------------------------- */
+
+/* Axis-aligned voxel grid: voxel (ix,iy,iz) covers origin + [i, i+1) * voxel on every axis; counts are stored
+ * uint32 [nz, ny, nx]. */
+typedef struct cama_voxel_grid {
+    double origin[3];               /* world coordinates of the grid's minimum corner */
+    double voxel[3];                /* edge lengths, > 0 */
+    int32_t dims[3];                /* nx, ny, nz */
+    int32_t reserved;
+} cama_voxel_grid;
+
+/* For every sweep s and every point row i in [sweep_offsets[s], sweep_offsets[s+1]):
+ *   world = (transforms[s] @ [x y z 1])[:3]   — MapManager.transform_3d_instance_maps, cama/reproject.py:108-116,
+ *           with transforms[s] = chassis2world(t_s) @ lidar2chassis (PoseTransformer.seek_by_timestamp,
+ *           cama/pose_transformer.py:589-652; DatasetReader.get_extrinsic, cama/dataset_reader.py:222-248)
+ *   counts[floor((world - origin) / voxel)] += 1 when the voxel index is inside the grid.
+ * points: device float64 rows of `row_doubles` values, x y z first (DatasetReader.yield_lidar,
+ * cama/dataset_reader.py:45-51: 6 per row); sweep_offsets: device int64 [n_sweeps+1]; transforms: device float64
+ * [n_sweeps,16] row-major 4x4; counts: device uint32 [nz,ny,nx], accumulated into (caller zero-fills); n_inside:
+ * optional device uint64 [1], incremented by the number of points counted.  The voxel accumulation is not in the
+ * reference snapshot (camav2 branch, README.md:17-20): this definition is the library's own, restated by
+ * oracle/lidar_oracle.py — parity unpinned. */
+int cama_lidar_accumulate(cama_ctx *ctx, const double *points, int row_doubles, const int64_t *sweep_offsets,
+                          int n_sweeps, const double *transforms, const cama_voxel_grid *grid, uint32_t *counts,
+                          uint64_t *n_inside, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

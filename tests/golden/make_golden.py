@@ -9,6 +9,11 @@ What is recorded (all produced by reference code, never by this repo's code):
 
 * golden_known_answers.npz   survey section 8(c) known-answer facts
 * golden_pose.npz            pose_transformer outputs on seeded inputs
+* golden_lidar.npz           the reference-side inputs of the LiDAR aggregation: sweeps read by the
+                             reference's DatasetReader.yield_lidar from a synth clip, lidar->chassis from its
+                             get_extrinsic, chassis->world from its ClipManager trajectory + seek_by_timestamp, and
+                             the world points from its MapManager.transform_3d_instance_maps.  (The voxel
+                             accumulation itself does not exist in the reference: parity unpinned for that step.)
 * golden_clip_<dataset>_<variant>.npz
       full per-frame outputs of ClipManager.yield_frame / project_all_camera /
       CameraManager.render_maps on synth.tiny_spec clips (exact-hit and slerp pose variants)
@@ -276,8 +281,33 @@ def pose_golden(out_path):
     print(out_path)
 
 
+def lidar_golden(out_path, root):
+    """Everything the reference computes on the way to a LiDAR aggregation (pose offset 25 ms: slerp branch)."""
+    from cama.dataset_reader import DatasetReader  # reference
+    spec = synth.tiny_spec(n_frames=5, pose_time_offset_ms=25, name="tiny_lidar")
+    clip = synth.write_clip(spec, root)
+    synth.write_lidar_sweeps(clip, n_sweeps=4, n_points=300, seed=3, ragged=True)
+    dr = DatasetReader(clip)
+    lidar2chassis = dr.get_extrinsic("lidar_top", "chassis")
+    cm = ClipManager(synth.CAMA_CONFIGS, clip)
+    pt = cm.get_pt_nuscenes(dr)
+    mm = MapManager()
+    out = {"lidar2chassis": np.asarray(lidar2chassis, dtype=np.float64)}
+    stamps, sizes, pts_all, world_all, mats = [], [], [], [], []
+    for stamp, cloud in dr.yield_lidar():
+        chassis2world = pt.seek_by_timestamp(float(stamp), t_max_diff=0.5, interpolate=True)
+        T = chassis2world @ lidar2chassis
+        world = mm.transform_3d_instance_maps([{"class": "lidar", "points": cloud[:, :3]}], T)[0]["points"] if len(cloud) else np.zeros((0, 3))
+        stamps.append(stamp); sizes.append(len(cloud)); pts_all.append(cloud); world_all.append(np.ascontiguousarray(world)); mats.append(T)
+    out.update(stamps=np.array(stamps), sizes=np.array(sizes, np.int64), points=np.concatenate(pts_all, 0), world=np.concatenate(world_all, 0),
+               transforms=np.stack(mats), inputs_digest=np.array(digest(np.concatenate(pts_all, 0))))
+    np.savez_compressed(out_path, **out)
+    print(out_path)
+
+
 def main():
     with tempfile.TemporaryDirectory() as root:
+        lidar_golden(os.path.join(HERE, "golden_lidar.npz"), root)
         known_answers(os.path.join(HERE, "golden_known_answers.npz"), root)
         pose_golden(os.path.join(HERE, "golden_pose.npz"))
         for variant, off in (("exact", 0), ("slerp", 25)):

@@ -4,7 +4,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 
 Every rank renders its frame block of the same synthetic config-2 clip, the blocks are all-gathered
-over NCCL, and every rank checks the gathered clip bit for bit against its own single-GPU render.
+over NCCL (dense frames, and sparse records + device expand), and every rank checks the gathered clip bit for bit
+against its own single-GPU render; then the LiDAR sweeps of a clip are sharded and the all-reduced voxel counts
+are checked against the single-GPU aggregation.
 """
 import os
 import sys
@@ -35,6 +37,14 @@ def main():
         lo, hi = shard.frame_block(37, rank, world)
         idx_local, block = shard.render_sharded(rp, "nuscenes", gather=False)
         ok = ok and idx_local == idx[lo:hi] and bool((block == whole[lo:hi]).all())
+        # LiDAR aggregation (configs[4]): sweeps sharded across the ranks, voxel counts summed with one all-reduce
+        from cama_b200.lidar import LidarAggregator, allreduce_counts
+        synth.write_lidar_sweeps(clip, n_sweeps=37, n_points=3000, seed=5, ragged=True)      # (every rank has its own copy of the clip)
+        agg = LidarAggregator(device=local)
+        whole_counts, whole_inside, _ = agg.aggregate_clip(rp.cm)
+        mine, _, _ = agg.aggregate_clip(rp.cm, rank=rank, world_size=world)
+        total = allreduce_counts(mine)
+        ok = ok and whole_inside > 0 and bool((total == whole_counts).all())
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
