@@ -472,6 +472,7 @@ def run_b200(args):
                             "cama_overlay_apply_host blanks the previous overlay and draws the new one into the host frames "
                             "[F,C,540,960,3]",
                     "transfer": "sparse", "overlay_records": int(transfer["records"]), "checksum": checksum,
+                    "host_draw_threads": int(rp.host_threads), "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,
                               "d2h_bytes_per_step": int(frame_bytes), "d2h_gbs": frame_bytes * dense_steps / dense_s / 1e9,
                               "note": "same call with transfer='dense': all frame bytes rendered in HBM and copied back (PCIe-bound)"}},
