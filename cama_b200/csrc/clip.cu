@@ -39,6 +39,8 @@ struct CamBlock {                      // by-value kernel parameter (constant ba
     double K[CAMA_MAX_CAMERAS][9];
     double box[6];
     int k_row2_is_001[CAMA_MAX_CAMERAS];
+    double wlim, hlim;                 // (double)(width + 1), (double)(height + 1): bounds of the frustum pre-test
+    int all_pinhole;                   // every K is exactly [[fx,0,cx],[0,fy,cy],[0,0,1]]
 };
 
 struct ClipArgs {
@@ -106,22 +108,32 @@ __device__ __forceinline__ bool load_vertex(const ClipArgs &a, long long n, doub
 //  * K row 2 == (0,0,1) makes q_z == p_z bit-for-bit, so p_z <= 0 rejects before x,y are formed;
 //  * q_x < -q_z or q_x > (W+1) q_z (same for y) puts u (v) outside [0,W) by a whole pixel, far
 //    beyond what the rounding of the division could undo.
-__device__ __forceinline__ bool camera_in_front(const CamBlock &cams, int c, double cx, double cy, double cz) {
-    return !cams.k_row2_is_001[c] || affine_row(cams.E[c] + 8, cx, cy, cz) > 0.0;
-}
+// PINHOLE: K is exactly [[fx,0,cx],[0,fy,cy],[0,0,1]] (what CameraManager builds, cama/reproject.py:180-182).  The
+// products with the zero entries add an exact zero in NumPy's accumulation (a0*b0, then one fma per further term)
+// and the one with the 1 returns p_z, so q = (fma(cx,pz,fx*px), fma(cy,pz,fy*py), pz) bit for bit for finite
+// camera coordinates — 4 FP64 operations instead of 9.  (A non-finite p_x or p_y makes q_x or q_y non-finite here
+// and NaN there: the point is masked either way.)
+template <bool PINHOLE>
 __device__ __forceinline__ bool camera_candidate(const CamBlock &cams, int c, double cx, double cy, double cz, int width, int height,
                                                  double &qx, double &qy, double &qz) {
     const double *E = cams.E[c];
     const double *K = cams.K[c];
     const double pz = affine_row(E + 8, cx, cy, cz);
-    if (cams.k_row2_is_001[c] && !(pz > 0.0)) return false;
+    if ((PINHOLE || cams.k_row2_is_001[c]) && !(pz > 0.0)) return false;
     const double px = affine_row(E, cx, cy, cz);
     const double py = affine_row(E + 4, cx, cy, cz);
-    qz = linear_row(K + 6, px, py, pz);
-    if (!((qz > 0.0) & (qz <= DBL_MAX))) return false;
-    qx = linear_row(K, px, py, pz);
-    qy = linear_row(K + 3, px, py, pz);
-    return !((qx < -qz) | (qx > (double)(width + 1) * qz) | (qy < -qz) | (qy > (double)(height + 1) * qz));
+    if (PINHOLE) {
+        qz = pz;
+        if (!(qz <= DBL_MAX)) return false;
+        qx = __fma_rn(K[2], pz, __dmul_rn(K[0], px));
+        qy = __fma_rn(K[5], pz, __dmul_rn(K[4], py));
+    } else {
+        qz = linear_row(K + 6, px, py, pz);
+        if (!((qz > 0.0) & (qz <= DBL_MAX))) return false;
+        qx = linear_row(K, px, py, pz);
+        qy = linear_row(K + 3, px, py, pz);
+    }
+    return !((qx < -qz) | (qx > cams.wlim * qz) | (qy < -qz) | (qy > cams.hlim * qz));
 }
 
 // Pixel of a candidate: trunc(fl(q_x / q_z)), trunc(fl(q_y / q_z)) and the in-image test of the reference,
@@ -162,9 +174,6 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
 #endif
 #ifndef CAMA_GEO_STAGE_FLUSH
 #define CAMA_GEO_STAGE_FLUSH 128
-#endif
-#ifndef CAMA_GEO_PZ_FIRST
-#define CAMA_GEO_PZ_FIRST 0
 #endif
 constexpr int kGeoThreads = 256;
 constexpr int kStageFlush = CAMA_GEO_STAGE_FLUSH;                                       // a warp flushes once this many records are staged ...
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
 // 6-camera tail — is almost warp-uniform (polylines are spatially coherent).
 // NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls and every matrix entry
 // becomes a constant-bank operand of its DFMA instead of an indexed load (0 = any count up to 8).
-template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS>
+template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS, bool PINHOLE>
 __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT_all[kGeoThreads / 32][kGeoFrames][12];
     __shared__ GeoStage stages[kGeoThreads / 32];
@@ -353,27 +362,11 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
             if (__any_sync(kFull, alive)) {
                 if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
                 const int n_cams = NCAMS ? NCAMS : a.n_cams;
-#if CAMA_GEO_PZ_FIRST
-                // which cameras have the point in front of them: the depth rows of all cameras first, as independent
-                // dependency chains (one camera after the other, every chain's latency is exposed before the warp vote)
-                unsigned front = 0u;
-#pragma unroll
-                for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c)
-                    if (NCAMS || c < n_cams) front |= (alive && camera_in_front(cams, c, cx, cy, cz)) ? 1u << c : 0u;
-                const unsigned warp_front = __reduce_or_sync(kFull, front);
-#endif
 #pragma unroll
                 for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
                     if (!NCAMS && c >= n_cams) break;
-#if CAMA_GEO_PZ_FIRST
-                    if (!((warp_front >> c) & 1u)) continue;
-#endif
                     double qx = 0.0, qy = 0.0, qz = 1.0;
-#if CAMA_GEO_PZ_FIRST
-                    const bool cand = ((front >> c) & 1u) && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
-#else
-                    const bool cand = alive && camera_candidate(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
-#endif
+                    const bool cand = alive && camera_candidate<PINHOLE>(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
                     if (!__any_sync(kFull, cand)) continue;
                     int vi = 0, ui = 0;
                     double v = 0.0, u = 0.0;
@@ -1129,13 +1122,15 @@ constexpr int kDefaultBandRows = 16;
 template <bool BINNED>
 cudaError_t launch_geometry(bool pdl, bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
     static const bool generic_only = getenv("CAMA_GEO_GENERIC") != nullptr;     // experiment knob
-    if (f32 && !debug && a.n_cams == 6 && !generic_only)            // the production shape: six cameras, float32 vertices
-        return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6>, grid, kGeoThreads, 0, s, a, cams);
+    if (f32 && !debug && a.n_cams == 6 && !generic_only) {          // the production shape: six cameras, float32 vertices
+        if (cams.all_pinhole) return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6, true>, grid, kGeoThreads, 0, s, a, cams);
+        return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6, false>, grid, kGeoThreads, 0, s, a, cams);
+    }
     if (f32)
-        return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0>, grid, kGeoThreads, 0, s, a, cams)
-                     : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0>, grid, kGeoThreads, 0, s, a, cams);
-    return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0>, grid, kGeoThreads, 0, s, a, cams)
-                 : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0>, grid, kGeoThreads, 0, s, a, cams);
+        return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0, false>, grid, kGeoThreads, 0, s, a, cams)
+                     : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0, false>, grid, kGeoThreads, 0, s, a, cams);
+    return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0, false>, grid, kGeoThreads, 0, s, a, cams)
+                 : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0, false>, grid, kGeoThreads, 0, s, a, cams);
 }
 
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
@@ -1436,6 +1431,13 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         cams.k_row2_is_001[c] = live && cams.K[c][6] == 0.0 && cams.K[c][7] == 0.0 && cams.K[c][8] == 1.0;
     }
     for (int i = 0; i < 6; ++i) cams.box[i] = d->crop_box[i];
+    cams.wlim = (double)(d->width + 1);
+    cams.hlim = (double)(d->height + 1);
+    cams.all_pinhole = 1;
+    for (int c = 0; c < d->n_cams; ++c) {
+        const double *K = cams.K[c];
+        if (!(cams.k_row2_is_001[c] && K[1] == 0.0 && K[3] == 0.0)) cams.all_pinhole = 0;
+    }
 
     ctx->last_render_grouped = p.groups > 1 && !prof;
     if (p.groups <= 1 || prof) {                       // one pass, one stream (phase events would serialise the lanes anyway)
