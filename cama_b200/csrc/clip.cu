@@ -107,7 +107,8 @@ __device__ __forceinline__ bool load_vertex(const ClipArgs &a, long long n, doub
 // is certain to discard; the early exits only skip work whose result the mask would discard anyway:
 //  * K row 2 == (0,0,1) makes q_z == p_z bit-for-bit, so p_z <= 0 rejects before x,y are formed;
 //  * q_x < -q_z or q_x > (W+1) q_z (same for y) puts u (v) outside [0,W) by a whole pixel, far
-//    beyond what the rounding of the division could undo.
+//    beyond what the rounding of the division could undo (NaN coordinates may or may not pass: the
+//    pixel test that follows masks them).
 // PINHOLE: K is exactly [[fx,0,cx],[0,fy,cy],[0,0,1]] (what CameraManager builds, cama/reproject.py:180-182).  The
 // products with the zero entries add an exact zero in NumPy's accumulation (a0*b0, then one fma per further term)
 // and the one with the 1 returns p_z, so q = (fma(cx,pz,fx*px), fma(cy,pz,fy*py), pz) bit for bit for finite
@@ -133,7 +134,13 @@ __device__ __forceinline__ bool camera_candidate(const CamBlock &cams, int c, do
         qx = linear_row(K, px, py, pz);
         qy = linear_row(K + 3, px, py, pz);
     }
-    return !((qx < -qz) | (qx > cams.wlim * qz) | (qy < -qz) | (qy > cams.hlim * qz));
+    // q_x + q_z < 0, q_y + q_z < 0, (W+1) q_z - q_x < 0 or (H+1) q_z - q_y < 0: one operation each, the four sign bits
+    // ORed (the comparison form compiled to a NaN-aware min/max sequence of 16 instructions).  The sum of two doubles
+    // has the sign of the exact sum, the fused product-difference that of the exact value; a visible point has
+    // q_x >= 0 and q_x < W q_z (1 + 2^-52) < (W+1) q_z, so none of the four is negative for it.
+    const double lo_x = __dadd_rn(qx, qz), lo_y = __dadd_rn(qy, qz);
+    const double hi_x = __fma_rn(cams.wlim, qz, -qx), hi_y = __fma_rn(cams.hlim, qz, -qy);
+    return (__double2hiint(lo_x) | __double2hiint(lo_y) | __double2hiint(hi_x) | __double2hiint(hi_y)) >= 0;
 }
 
 // Pixel of a candidate: trunc(fl(q_x / q_z)), trunc(fl(q_y / q_z)) and the in-image test of the reference,
