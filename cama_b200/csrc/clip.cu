@@ -120,12 +120,15 @@ __device__ __forceinline__ bool camera_candidate(const CamBlock &cams, int c, do
     const double *E = cams.E[c];
     const double *K = cams.K[c];
     const double pz = affine_row(E + 8, cx, cy, cz);
-    if ((PINHOLE || cams.k_row2_is_001[c]) && !(pz > 0.0)) return false;
+    if (PINHOLE) {                              // q_z == p_z: 0 < p_z <= DBL_MAX decided before x and y are formed
+        if (!((pz > 0.0) & ((unsigned)__double2hiint(pz) < 0x7ff00000u))) return false;
+    } else if (cams.k_row2_is_001[c] && !(pz > 0.0)) {
+        return false;
+    }
     const double px = affine_row(E, cx, cy, cz);
     const double py = affine_row(E + 4, cx, cy, cz);
     if (PINHOLE) {
         qz = pz;
-        if (!(qz <= DBL_MAX)) return false;
         qx = __fma_rn(K[2], pz, __dmul_rn(K[0], px));
         qy = __fma_rn(K[5], pz, __dmul_rn(K[4], py));
     } else {
@@ -369,10 +372,10 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
             if (__any_sync(kFull, alive)) {
                 if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
                 const int n_cams = NCAMS ? NCAMS : a.n_cams;
+                double qx = 0.0, qy = 0.0, qz = 1.0;            // (lanes that are no candidate keep whatever the last camera left: masked)
 #pragma unroll
                 for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
                     if (!NCAMS && c >= n_cams) break;
-                    double qx = 0.0, qy = 0.0, qz = 1.0;
                     const bool cand = alive && camera_candidate<PINHOLE>(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
                     if (!__any_sync(kFull, cand)) continue;
                     int vi = 0, ui = 0;
