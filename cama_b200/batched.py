@@ -412,7 +412,11 @@ class Reproject:
                 self._ov_prev = None
                 blank_previous = lambda: apply(prev.data_ptr(), n_prev, prev_fmt, prev_palette, N.OVERLAY_BLANK_CHUNKS)
         # ... while the GPU renders this one
-        records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode, while_running=blank_previous)
+        try:
+            records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode, while_running=blank_previous)
+        except Exception:
+            self._host_frames = None                         # (the reused buffer may be half blanked: start from zeros next time)
+            raise
         words = int(records.shape[1])
         # records -> pinned host memory in a few slices (records are independent: unique chunks, any order), each drawn
         # into the host frames while the next one is still crossing PCIe
