@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
     __syncthreads();
     pdl_wait();
     pdl_trigger();
+    const unsigned long long pool_total = tid == 0 ? (unsigned long long)*pool_count : 0ull;      // (in flight with the counts)
     for (int base = 0; base < nb; base += 1024 * kScanPerThread) {
         const int idx = base + kScanPerThread * tid;
         unsigned vals[kScanPerThread];
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
     if (tid < 4) list_counts[tid] = s_cursor[tid];
     if (tid == 0) {
         start[nb] = carry;
-        const unsigned long long total = *pool_count;
+        const unsigned long long total = pool_total;
         stats->records_total = total;
         stats->records_max_per_frame = n_frames > 0 ? (total + n_frames - 1) / n_frames : 0;    // mean per frame: what a rerun must provision
         stats->overflow = total > (unsigned long long)pool_cap ? 1u : 0u;
@@ -539,7 +540,13 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
 // pool (arrival order) -> sorted (bucket order).  A record's place inside its bucket is taken from
 // the bucket's count, counted down; runs of equal buckets (records of one warp) share one atomic.
 // Four independent records per thread keep four load -> atomic -> store chains in flight.
-constexpr int kScatterPerThread = 4;
+#ifndef CAMA_SCATTER_PER_THREAD
+#define CAMA_SCATTER_PER_THREAD 4
+#endif
+#ifndef CAMA_SCATTER_CTAS_PER_SM
+#define CAMA_SCATTER_CTAS_PER_SM 16
+#endif
+constexpr int kScatterPerThread = CAMA_SCATTER_PER_THREAD;
 __global__ void __launch_bounds__(256) record_scatter_kernel(const uint2 *__restrict__ pool, const unsigned *__restrict__ pool_count, long long pool_cap,
                                                             const unsigned *__restrict__ start, unsigned *__restrict__ hist, long long sorted_cap,
                                                             unsigned *__restrict__ sorted) {
@@ -1342,7 +1349,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     CAMA_LAUNCHED(ctx);
     {   // grid-stride over the records appended; sized for the pool, capped at a few CTAs per SM slot
         const long long tile = 256 * kScatterPerThread;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, (long long)ctx->sm_count * 16));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, (long long)ctx->sm_count * CAMA_SCATTER_CTAS_PER_SM));
         CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
     }
     CAMA_LAUNCHED(ctx);
