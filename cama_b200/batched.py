@@ -303,6 +303,7 @@ class Reproject:
         self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
         self._ov_flip = 0
         self._ov_events = []
+        self._pose_stage = None
         # threads of the host draw: this process's share of the cores (torchrun sets OMP_NUM_THREADS=1, which would
         # make the draw serial; with N ranks on a box every rank takes 1/N of the cores)
         try:
@@ -324,6 +325,26 @@ class Reproject:
         idx = [i for i, _ in poses]
         w2c = np.stack([m for _, m in poses]).reshape(-1, 16) if poses else np.zeros((0, 16), np.float32)
         return idx, np.ascontiguousarray(w2c, dtype=np.float32)
+
+    def _poses_to_device(self, w2c):
+        """Host float32 [F',16] -> device, through a reused pinned staging buffer (one asynchronous copy on the
+        current stream; a pageable source costs a staging copy and a synchronisation per call)."""
+        import torch
+        w2c = np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)
+        n = int(w2c.shape[0])
+        if n == 0:
+            return torch.empty((0, 16), dtype=torch.float32, device=self.rt.device)
+        stage = self._pose_stage
+        if stage is None or stage[0].shape[0] < n:
+            cap = max(n, 64)
+            stage = self._pose_stage = (torch.empty((cap, 16), dtype=torch.float32, pin_memory=True),
+                                        torch.empty((cap, 16), dtype=torch.float32, device=self.rt.device), torch.cuda.Event())
+        pinned, dev, done = stage
+        done.synchronize()                                       # (the previous call's copy has long finished)
+        pinned[:n].numpy()[...] = w2c
+        dev[:n].copy_(pinned[:n], non_blocking=True)
+        done.record(torch.cuda.current_stream(self.rt.device))
+        return dev[:n]
 
     def undistort_maps_device(self):
         """Per-camera cv2.initUndistortRectifyMap maps on the device: (map_x, map_y) float32 [C,H,W]."""
@@ -388,7 +409,7 @@ class Reproject:
         rt = self.rt
         H, W, C = self.renderer.height, self.renderer.width, self.renderer.n_cams
         shape = (len(idx), C, H, W, 3) if tiles is None else (len(idx), 2 * H, 3 * W, 3)
-        w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(rt.device)
+        w2c_dev = self._poses_to_device(w2c)
         res = self.resident(dataset)
 
         def apply(rec_ptr, count, rec_fmt, palette, op):
