@@ -467,10 +467,10 @@ def run_b200(args):
             "e2e": {"value": world * cam_frames * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(w2c_host.nbytes), "d2h_bytes_per_step": int(transfer["d2h_bytes"]) + 48,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-                    "call": "cama_b200.batched.Reproject.__call__(dataset): host pose seek + float32 inverse, H2D of the poses, "
-                            "cama_clip_render (sparse output), D2H of the lit 8-pixel chunk records into pinned memory, "
-                            "cama_overlay_apply_host blanks the previous overlay and draws the new one into the host frames "
-                            "[F,C,540,960,3]",
+                    "call": "cama_b200.batched.Reproject.__call__(dataset): host pose seek + float32 inverse, H2D of the poses from pinned "
+                            "memory, cama_clip_render (sparse output), D2H of the lit 8-pixel chunk records into pinned memory in slices, "
+                            "cama_overlay_apply_host blanks the previous overlay (helper thread, during the former) and draws the new one "
+                            "into the host frames [F,C,540,960,3]",
                     "transfer": "sparse", "overlay_records": int(transfer["records"]), "checksum": checksum,
                     "host_draw_threads": int(rp.host_threads), "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,

@@ -304,6 +304,9 @@ class Reproject:
         self._ov_flip = 0
         self._ov_events = []
         self._pose_stage = None
+        self._helper_pool = None
+        self._host_tiles = None       # mosaic tile table the reused host buffer was drawn with (None: plain frames)
+        self._pose_views = {}
         # threads of the host draw: this process's share of the cores (torchrun sets OMP_NUM_THREADS=1, which would
         # make the draw serial; with N ranks on a box every rank takes 1/N of the cores)
         try:
@@ -321,10 +324,8 @@ class Reproject:
 
     def frame_poses(self, dataset):
         """-> (image_idx list, float32 [F',16] world->chassis), host side."""
-        poses = self.cm.frame_poses(dataset)
-        idx = [i for i, _ in poses]
-        w2c = np.stack([m for _, m in poses]).reshape(-1, 16) if poses else np.zeros((0, 16), np.float32)
-        return idx, np.ascontiguousarray(w2c, dtype=np.float32)
+        idx, w2c = self.cm.frame_pose_arrays(dataset)
+        return list(idx), np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)
 
     def _poses_to_device(self, w2c):
         """Host float32 [F',16] -> device, through a reused pinned staging buffer (one asynchronous copy on the
@@ -340,11 +341,14 @@ class Reproject:
             stage = self._pose_stage = (torch.empty((cap, 16), dtype=torch.float32, pin_memory=True),
                                         torch.empty((cap, 16), dtype=torch.float32, device=self.rt.device), torch.cuda.Event())
         pinned, dev, done = stage
+        views = self._pose_views.get(n)
+        if views is None or views[0] is not pinned:
+            views = self._pose_views[n] = (pinned, pinned[:n].numpy(), pinned[:n], dev[:n])
         done.synchronize()                                       # (the previous call's copy has long finished)
-        pinned[:n].numpy()[...] = w2c
-        dev[:n].copy_(pinned[:n], non_blocking=True)
-        done.record(torch.cuda.current_stream(self.rt.device))
-        return dev[:n]
+        views[1][...] = w2c
+        views[3].copy_(views[2], non_blocking=True)
+        done.record()
+        return views[3]
 
     def undistort_maps_device(self):
         """Per-camera cv2.initUndistortRectifyMap maps on the device: (map_x, map_y) float32 [C,H,W]."""
@@ -396,6 +400,40 @@ class Reproject:
         consumer of ``render_device`` gets).  Both give identical bytes.
         """
         import torch
+        # The previous overlay of the reused host buffer is blanked by a helper thread (the native routine runs its
+        # own OpenMP team and holds no Python lock) while this thread looks the poses up, uploads them and the GPU
+        # renders; the draw waits for it.
+        blank_job = None
+        if backgrounds is None and transfer != "dense" and self._ov_prev is not None and self._host_frames is not None:
+            prev, n_prev, prev_fmt, prev_palette = self._ov_prev
+            self._ov_prev = None
+            blank_job = self._helper().submit(self._apply_records, self._host_frames, self._host_tiles, prev.data_ptr(), n_prev, prev_fmt,
+                                              prev_palette, N.OVERLAY_BLANK_CHUNKS)
+        try:
+            return self._call_sparse(dataset, backgrounds, mode, transfer, layout, blank_job)
+        except Exception:
+            if blank_job is not None:
+                blank_job.exception()                        # (wait for it; its own error, if any, is secondary)
+            self._host_frames = None                         # the reused buffer may be half drawn: start from zeros next time
+            self._ov_prev = None
+            raise
+
+    def _helper(self):
+        if self._helper_pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._helper_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cama-b200-host")
+        return self._helper_pool
+
+    def _apply_records(self, frames, tiles, rec_ptr, count, rec_fmt, palette, op):
+        """cama_overlay_apply_host on host frames [F,C,H,W,3] (tiles None) or the mosaic [F,2H,3W,3]."""
+        H, W, C = self.renderer.height, self.renderer.width, self.renderer.n_cams
+        target = N.OverlayTarget(frames.ctypes.data, int(frames.shape[0]), C, H, W, 0 if tiles is None else 3,
+                                 None if tiles is None else tiles.ctypes.data)
+        N.check(N.lib().cama_overlay_apply_host(rec_ptr, count, rec_fmt, None if palette is None else palette.ctypes.data,
+                                                ctypes.byref(target), op, self.host_threads))
+
+    def _call_sparse(self, dataset, backgrounds, mode, transfer, layout, blank_job):
+        import torch
         idx, w2c = self.frame_poses(dataset)
         tiles = None
         if layout == "mosaic":
@@ -405,39 +443,28 @@ class Reproject:
         elif layout != "frames":
             raise ValueError(f"unknown layout {layout!r}")
         if transfer == "dense" or _MODES.get(mode, mode) == N.CLIP_PLANE or not self._sparse_ok():
+            if blank_job is not None:
+                blank_job.result()
             return idx, self._call_dense(dataset, w2c, backgrounds, mode)
         rt = self.rt
         H, W, C = self.renderer.height, self.renderer.width, self.renderer.n_cams
         shape = (len(idx), C, H, W, 3) if tiles is None else (len(idx), 2 * H, 3 * W, 3)
         w2c_dev = self._poses_to_device(w2c)
         res = self.resident(dataset)
-
-        def apply(rec_ptr, count, rec_fmt, palette, op):
-            target = N.OverlayTarget(frames.ctypes.data, len(idx), C, H, W, 0 if tiles is None else 3,
-                                     None if tiles is None else tiles.ctypes.data)
-            N.check(N.lib().cama_overlay_apply_host(rec_ptr, count, rec_fmt, None if palette is None else palette.ctypes.data,
-                                                    ctypes.byref(target), op, self.host_threads))
-
-        blank_previous = None
         if backgrounds is not None:
             frames = backgrounds
             assert isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.shape == shape and frames.flags.c_contiguous \
                 and frames.flags.writeable, "backgrounds must be a writeable C-contiguous uint8 array [F',C,H,W,3] (or [F',2H,3W,3] for the mosaic)"
         else:
             frames = self._host_frames
-            if frames is None or frames.shape != shape:
+            same_tiles = (tiles is None) == (self._host_tiles is None) and (tiles is None or np.array_equal(tiles, self._host_tiles))
+            if frames is None or frames.shape != shape or not same_tiles:
+                if blank_job is not None:
+                    blank_job.result()
+                    blank_job = None
                 frames = self._host_frames = np.zeros(shape, dtype=np.uint8)
-                self._ov_prev = None
-            if self._ov_prev is not None:                    # blank what the previous call painted into this buffer ...
-                prev, n_prev, prev_fmt, prev_palette = self._ov_prev
-                self._ov_prev = None
-                blank_previous = lambda: apply(prev.data_ptr(), n_prev, prev_fmt, prev_palette, N.OVERLAY_BLANK_CHUNKS)
-        # ... while the GPU renders this one
-        try:
-            records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode, while_running=blank_previous)
-        except Exception:
-            self._host_frames = None                         # (the reused buffer may be half blanked: start from zeros next time)
-            raise
+                self._host_tiles = tiles
+        records, n, fmt = self.renderer.render_overlay(res, w2c_dev, mode=mode)
         words = int(records.shape[1])
         # records -> pinned host memory in a few slices (records are independent: unique chunks, any order), each drawn
         # into the host frames while the next one is still crossing PCIe
@@ -452,15 +479,17 @@ class Reproject:
         for k in range(len(cuts) - 1):
             if cuts[k + 1] > cuts[k]:
                 cur[cuts[k]:cuts[k + 1]].copy_(records[cuts[k]:cuts[k + 1]], non_blocking=True)
-            events[k].record(torch.cuda.current_stream(rt.device))
-        if backgrounds is None:
-            self._ov_prev = (cur, n, fmt, res.palette)
-            self._ov_flip ^= 1
+            events[k].record()
+        if blank_job is not None:
+            blank_job.result()                               # the buffer is black again
         draw = N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS   # blank frames: unpainted pixels are black anyway
         for k in range(len(cuts) - 1):
             events[k].synchronize()
             if cuts[k + 1] > cuts[k]:
-                apply(cur.data_ptr() + cuts[k] * words * 4, cuts[k + 1] - cuts[k], fmt, res.palette, draw)
+                self._apply_records(frames, tiles, cur.data_ptr() + cuts[k] * words * 4, cuts[k + 1] - cuts[k], fmt, res.palette, draw)
+        if backgrounds is None:                              # what the next call has to blank
+            self._ov_prev = (cur, n, fmt, res.palette)
+            self._ov_flip ^= 1
         self.last_transfer = {"mode": "sparse", "d2h_bytes": n * N.OVERLAY_RECORD_BYTES[fmt], "records": n,
                               "format": "palette" if fmt == N.OVERLAY_PALETTE else "bgr"}
         return idx, frames

@@ -99,7 +99,12 @@ class ClipManager:
         return cache[dataset]
 
     def frame_poses(self, dataset):
-        """[(image_idx, world2chassis float32 4x4)] for every renderable frame.
+        """[(image_idx, world2chassis float32 4x4)] for every renderable frame (see frame_pose_arrays)."""
+        kept_idx, inverses = self.frame_pose_arrays(dataset)
+        return [(i, inverses[j]) for j, i in enumerate(kept_idx)]
+
+    def frame_pose_arrays(self, dataset):
+        """(image_idx list, world2chassis float32 [F',4,4]) for every renderable frame.
 
         Reference cama/dataset.py:78-99: index 0 is skipped; the pose is sought with
         interpolation and ``t_max_diff=0.5``; a ``RuntimeError`` from the lookup skips the frame;
@@ -108,7 +113,7 @@ class ClipManager:
         pt, stamps = self._trajectory(dataset)
         n = len(stamps)
         if n <= 1:
-            return []
+            return [], np.zeros((0, 4, 4), np.float32)
         # Frames whose stamp coincides with a pose stamp (the usual case: the poses come from the same
         # sync list) take seek_by_timestamp's first branch; resolve all of them with one comparison.
         # The other frames go through the method itself (interpolation / RuntimeError).  The comparison
@@ -136,11 +141,10 @@ class ClipManager:
             kept_idx.append(image_idx)
             kept_pose.append(chassis2world)
         if not kept_idx:
-            return []
+            return [], np.zeros((0, 4, 4), np.float32)
         # one batched LAPACK call: np.linalg.inv loops the same float32 gesv over the stack, so every
         # matrix is bit-identical to inverting it on its own (tests/test_host_golden.py)
-        inverses = np.linalg.inv(np.stack(kept_pose).astype(np.float32))
-        return [(i, inverses[j]) for j, i in enumerate(kept_idx)]
+        return kept_idx, np.linalg.inv(np.stack(kept_pose).astype(np.float32))
 
     # ------------------------------------------------------------------ the per-frame protocol of main.py
     def yield_frame(self, dataset):

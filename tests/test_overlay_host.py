@@ -97,3 +97,35 @@ def test_mosaic_layout_matches_concate_image():
     bad = tiles.copy()
     bad[0] = 9
     assert apply(recs, mosaic, 0, tiles=bad, shape=(F, C, H, W)) == N.CAMA_E_INVALID
+
+
+@pytest.mark.parametrize("n_colours", [1, 2, 15, 16, 40, 255])
+def test_palette_draw_chunks_both_paths(n_colours):
+    """DRAW_CHUNKS with palette records: up to 15 colours take the byte-shuffle path (SSSE3), more take the
+    two-pixels-per-lookup table; both must write exactly palette[index] for all 8 pixels of every record, leave the
+    other chunks alone, ignore chunks outside the target and entries above the palette size in use."""
+    rng = np.random.default_rng(n_colours)
+    frames = rng.integers(0, 256, size=(2, 3, 64, 256, 3), dtype=np.uint8)
+    n_chunks = frames.size // 24
+    palette = np.zeros((256, 3), np.uint8)
+    palette[1:n_colours + 1] = rng.integers(1, 256, (n_colours, 3))
+    recs = np.zeros(6000, REC_PAL)
+    recs["chunk"] = rng.permutation(n_chunks)[:6000]
+    recs["chunk"][-3:] = [n_chunks, n_chunks + 7, 0xFFFFFFFF]           # outside the target: ignored
+    recs["index"] = rng.integers(0, n_colours + 1, (6000, 8))
+    want = frames.copy()
+    flat = want.reshape(-1, 8, 3)
+    inside = recs["chunk"] < n_chunks
+    flat[recs["chunk"][inside]] = palette[recs["index"][inside]]
+    masked = frames.copy()                                              # DRAW: only painted pixels (index != 0) are written
+    mflat = masked.reshape(-1, 8, 3)
+    painted = recs["index"][inside] > 0
+    mflat[recs["chunk"][inside]] = np.where(painted[:, :, None], palette[recs["index"][inside]], mflat[recs["chunk"][inside]])
+    for threads in (1, 0):
+        got = frames.copy()
+        assert apply(recs, got, op=N.OVERLAY_DRAW_CHUNKS, threads=threads, fmt=N.OVERLAY_PALETTE, palette=palette) == 0
+        assert np.array_equal(got, want), (n_colours, threads)
+        got = frames.copy()
+        assert apply(recs, got, op=N.OVERLAY_DRAW, threads=threads, fmt=N.OVERLAY_PALETTE, palette=palette) == 0
+        assert np.array_equal(got, masked), (n_colours, threads)
+
