@@ -328,27 +328,24 @@ class Reproject:
         return list(idx), np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)
 
     def _poses_to_device(self, w2c):
-        """Host float32 [F',16] -> device, through a reused pinned staging buffer (one asynchronous copy on the
-        current stream; a pageable source costs a staging copy and a synchronisation per call)."""
+        """Host float32 [F',16] -> something the kernels can read: a reused **pinned** staging buffer whose host
+        pointer is valid on the device (unified addressing: cudaHostAlloc memory is mapped), so the prep kernel
+        fetches the 2.5 KB of poses over PCIe itself — no copy call, no torch dispatch on the call's critical path.
+        The buffer is rewritten by the next call, which starts after this one's counters have been read back."""
         import torch
         w2c = np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)
         n = int(w2c.shape[0])
         if n == 0:
             return torch.empty((0, 16), dtype=torch.float32, device=self.rt.device)
         stage = self._pose_stage
-        if stage is None or stage[0].shape[0] < n:
-            cap = max(n, 64)
-            stage = self._pose_stage = (torch.empty((cap, 16), dtype=torch.float32, pin_memory=True),
-                                        torch.empty((cap, 16), dtype=torch.float32, device=self.rt.device), torch.cuda.Event())
-        pinned, dev, done = stage
+        if stage is None or stage.shape[0] < n:
+            stage = self._pose_stage = torch.empty((max(n, 64), 16), dtype=torch.float32, pin_memory=True)
+            self._pose_views = {}
         views = self._pose_views.get(n)
-        if views is None or views[0] is not pinned:
-            views = self._pose_views[n] = (pinned, pinned[:n].numpy(), pinned[:n], dev[:n])
-        done.synchronize()                                       # (the previous call's copy has long finished)
-        views[1][...] = w2c
-        views[3].copy_(views[2], non_blocking=True)
-        done.record()
-        return views[3]
+        if views is None:
+            views = self._pose_views[n] = (stage[:n].numpy(), stage[:n])
+        views[0][...] = w2c
+        return views[1]
 
     def undistort_maps_device(self):
         """Per-camera cv2.initUndistortRectifyMap maps on the device: (map_x, map_y) float32 [C,H,W]."""
