@@ -19,10 +19,19 @@
 #include <climits>
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>      // header-only; the ranges cost nothing unless a profiler is attached
+
 #include "common.cuh"
 #include "geom.cuh"
 
 namespace cama {
+
+// NVTX range over a scope: `ncu --nvtx --nvtx-include "cama_clip_render/"` (or any NVTX-aware profiler) can pick a
+// call or one of its phases.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -1276,6 +1285,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     if (d->vu_dense)
         CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
     {
+        NvtxRange nvtx_phase("prep");
         const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
         const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
         // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
@@ -1322,6 +1332,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
+        NvtxRange nvtx_phase("geometry");
         // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
         if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
             unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
@@ -1344,6 +1355,8 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     s = lanes.sort;
     unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
     unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
+    {
+    NvtxRange nvtx_phase("sort");
     CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, bucket_scan_kernel, 1, 1024, 0, s, a.hist, start, n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats,
                            lists, list_counts));
     CAMA_LAUNCHED(ctx);
@@ -1353,12 +1366,14 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
         CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
     }
     CAMA_LAUNCHED(ctx);
+    }
     if (lanes_split) {
         CAMA_CUDA_TRY(cudaEventRecord(lanes.sort_done, s));
         CAMA_CUDA_TRY(cudaStreamWaitEvent(lanes.raster, lanes.sort_done, 0));
     }
     s = lanes.raster;
     CAMA_CUDA_TRY(mark(3));
+    NvtxRange nvtx_raster("raster");
     RasterArgs r{};
     r.n_items = n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
     r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
@@ -1434,6 +1449,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     CAMA_REQUIRE(((uintptr_t)d->frames & 15) == 0 && ((uintptr_t)d->background & 15) == 0 && ((uintptr_t)d->vertices & 15) == 0,
                  "frames/background/vertices must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
+    NvtxRange nvtx_call("cama_clip_render");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     // phase events of this call, when profiling is on (cama_ctx_profile_enable)
