@@ -99,6 +99,7 @@ SIGNATURES = {
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),
     "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(OverlayTarget), c_int, c_int]),
     "cama_lidar_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cama_overlay_fetch_apply": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, POINTER(OverlayTarget), c_int, c_int, c_void_p]),
     "cama_overlay_expand": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

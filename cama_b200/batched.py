@@ -469,21 +469,14 @@ class Reproject:
         if cur is None or cur.shape[0] < max(n, 1) or cur.shape[1] != words:
             cur = torch.empty((max(int(n * 1.25), 4096), words), dtype=torch.int32, pin_memory=True)
             self._ov_host[self._ov_flip] = cur
-        cuts = [0, n] if n < (1 << 16) else [0, n // 8, (3 * n) // 8, n]
-        events = self._ov_events
-        while len(events) < len(cuts) - 1:
-            events.append(torch.cuda.Event())
-        for k in range(len(cuts) - 1):
-            if cuts[k + 1] > cuts[k]:
-                cur[cuts[k]:cuts[k + 1]].copy_(records[cuts[k]:cuts[k + 1]], non_blocking=True)
-            events[k].record()
         if blank_job is not None:
-            blank_job.result()                               # the buffer is black again
+            blank_job.result()                               # the buffer is black again (normally long done by now)
         draw = N.OVERLAY_DRAW if backgrounds is not None else N.OVERLAY_DRAW_CHUNKS   # blank frames: unpainted pixels are black anyway
-        for k in range(len(cuts) - 1):
-            events[k].synchronize()
-            if cuts[k + 1] > cuts[k]:
-                self._apply_records(frames, tiles, cur.data_ptr() + cuts[k] * words * 4, cuts[k + 1] - cuts[k], fmt, res.palette, draw)
+        if n:                                                # slices of records over PCIe, each drawn while the next one flies
+            target = N.OverlayTarget(frames.ctypes.data, int(frames.shape[0]), C, H, W, 0 if tiles is None else 3,
+                                     None if tiles is None else tiles.ctypes.data)
+            N.check(N.lib().cama_overlay_fetch_apply(rt.ctx, records.data_ptr(), n, fmt, None if res.palette is None else res.palette.ctypes.data,
+                                                     cur.data_ptr(), ctypes.byref(target), draw, self.host_threads, rt.stream()))
         if backgrounds is None:                              # what the next call has to blank
             self._ov_prev = (cur, n, fmt, res.palette)
             self._ov_flip ^= 1

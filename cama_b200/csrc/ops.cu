@@ -264,6 +264,7 @@ int cama_ctx_destroy(cama_ctx *ctx) {
         cama_ctx_profile_enable(ctx, 0);
         DeviceGuard guard(ctx->device);
         for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->fetch_events) cudaEventDestroy(e);
         for (cudaStream_t s : ctx->pipe_streams)
             if (s) cudaStreamDestroy(s);
     }

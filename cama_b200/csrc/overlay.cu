@@ -261,3 +261,46 @@ extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int forma
     }
     return CAMA_OK;
 }
+
+// Device records -> host frames in one call: the records are copied to the caller's pinned staging buffer in three
+// slices (1/8, 1/4, 5/8) on `stream`, and each slice is applied to the target while the next one is still crossing
+// PCIe (records are independent: unique chunks, any order).  The same pipeline Reproject.__call__ ran from Python,
+// without the per-slice interpreter and tensor-dispatch overhead.
+extern "C" int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, int64_t n, int format, const uint8_t *palette_bgr,
+                                        void *staging_pinned, const cama_overlay_target *target, int op, int n_threads, void *stream) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    CAMA_REQUIRE(n >= 0, "negative size");
+    CAMA_REQUIRE(format == CAMA_OVERLAY_BGR || format == CAMA_OVERLAY_PALETTE, "bad format");
+    if (n == 0) return CAMA_OK;
+    CAMA_REQUIRE(records_dev && staging_pinned, "NULL buffer");
+    const size_t rb = format == CAMA_OVERLAY_BGR ? sizeof(cama_overlay_record) : sizeof(cama_overlay_record_palette);
+    int64_t cuts[4] = {0, n, n, n};
+    int n_slices = 1;
+    if (n >= (1 << 16)) {
+        cuts[1] = n / 8; cuts[2] = (3 * n) / 8; cuts[3] = n;
+        n_slices = 3;
+    }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    while (ctx->fetch_events.size() < 3) {
+        cudaEvent_t e;
+        CAMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->fetch_events.push_back(e);
+    }
+    const unsigned char *src = static_cast<const unsigned char *>(records_dev);
+    unsigned char *dst = static_cast<unsigned char *>(staging_pinned);
+    for (int k = 0; k < n_slices; ++k) {
+        const int64_t count = cuts[k + 1] - cuts[k];
+        if (count > 0) CAMA_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)cuts[k] * rb, src + (size_t)cuts[k] * rb, (size_t)count * rb, cudaMemcpyDeviceToHost, s));
+        CAMA_CUDA_TRY(cudaEventRecord(ctx->fetch_events[k], s));
+    }
+    for (int k = 0; k < n_slices; ++k) {
+        CAMA_CUDA_TRY(cudaEventSynchronize(ctx->fetch_events[k]));
+        const int64_t count = cuts[k + 1] - cuts[k];
+        if (count > 0) {
+            const int rc = cama_overlay_apply_host(dst + (size_t)cuts[k] * rb, count, format, palette_bgr, target, op, n_threads);
+            if (rc != CAMA_OK) return rc;
+        }
+    }
+    return CAMA_OK;
+}

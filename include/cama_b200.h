@@ -268,6 +268,12 @@ enum { CAMA_OVERLAY_DRAW = 0, CAMA_OVERLAY_BLANK = 1, CAMA_OVERLAY_DRAW_CHUNKS =
 int cama_overlay_apply_host(const void *records, int64_t n, int format, const uint8_t *palette_bgr,
                             const cama_overlay_target *target, int op, int n_threads);
 
+/* The whole return path of the sparse output in one call: `n` records (device) are copied into `staging_pinned`
+ * (pinned host memory, at least n records) in slices on `stream`, and every slice is applied to the target with
+ * cama_overlay_apply_host(op) while the next one is still in flight.  Synchronises with the copies it issued. */
+int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, int64_t n, int format, const uint8_t *palette_bgr,
+                             void *staging_pinned, const cama_overlay_target *target, int op, int n_threads, void *stream);
+
 /* ---- device side of the sparse output: records -> dense frames ---------------------------------- */
 
 /* Expands `n` overlay records (device) into dense frames uint8 [n_frames,n_cams,H,W,3] (device): the frames are
