@@ -302,7 +302,6 @@ class Reproject:
         self._ov_prev = None          # ... and the records painted into them (blanked before the next paint)
         self._ov_host = [None, None]  # pinned record staging, double-buffered because _ov_prev keeps one alive
         self._ov_flip = 0
-        self._ov_events = []
         self._pose_stage = None
         self._helper_pool = None
         self._host_tiles = None       # mosaic tile table the reused host buffer was drawn with (None: plain frames)
