@@ -17,14 +17,14 @@ LIB_DIR = os.path.join(_PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcama_b200.so")
 STAMP_PATH = LIB_PATH + ".stamp"
 SOURCES = ["ops.cu", "clip.cu", "overlay.cu", "densify.cu", "remap.cu", "lidar.cu"]
-HEADERS = ["common.cuh", "geom.cuh", os.path.join("..", "..", "include", "cama_b200.h")]
+HEADERS = ["common.cuh", "geom.cuh", "host_pool.h", os.path.join("..", "..", "include", "cama_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-fmad=false",            # every FMA in the arithmetic contract is written explicitly (csrc/geom.cuh)
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-lgomp",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",      # host loops run on the library's own worker pool (csrc/host_pool.h)
 ]
 
 

@@ -2,8 +2,11 @@
 // produced into host frames (the in-place draw of /root/reference/cama/reproject.py:246-257 for
 // pixels whose colour is already decided), either plain [F,C,H,W,3] frames or the 2x3 camera mosaic of
 // /root/reference/cama/tools.py:22-25.  Pure byte movement, OpenMP over the records.
+#include <algorithm>
 #include <cstring>
-#include <omp.h>
+#include <thread>
+
+#include "host_pool.h"
 #if defined(__x86_64__)
 #include <tmmintrin.h>
 #define CAMA_HAVE_SSSE3 1
@@ -14,6 +17,8 @@
 using namespace cama;
 
 namespace {
+
+constexpr int64_t kHostChunk = 2048;           // records a worker claims at a time (~20 us of drawing)
 
 struct Target {
     uint8_t *pixels;
@@ -86,23 +91,93 @@ __attribute__((target("ssse3"))) inline void expand8_ssse3(const Pal16 &pal, con
     _mm_storel_epi64(reinterpret_cast<__m128i *>(dst + 16), out1);
 }
 
+struct DrawPal16Job {
+    const cama_overlay_record_palette *rec;
+    int64_t n;
+    const Target *t;
+    Pal16 pal;
+};
+template <bool MASKED>
+__attribute__((target("ssse3"))) void draw_pal16_range(void *ctx, int64_t lo, int64_t hi) {
+    const DrawPal16Job &j = *static_cast<const DrawPal16Job *>(ctx);
+    const cama_overlay_record_palette *rec = j.rec;
+    const Target &t = *j.t;
+    constexpr int64_t kAhead = 24;                 // the destination lines are scattered: prefetch them for writing
+    for (int64_t i = lo; i < hi; ++i) {
+        if (i + kAhead < j.n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
+        if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
+        expand8_ssse3<MASKED>(j.pal, rec[i].index, t.chunk_ptr(rec[i].chunk));
+    }
+}
+
 template <bool MASKED>
 __attribute__((target("ssse3"))) void draw_pal16(const cama_overlay_record_palette *rec, int64_t n, const uint8_t *palette_bgr, const Target &t, int threads) {
     alignas(16) uint8_t tb[16] = {0}, tg[16] = {0}, tr[16] = {0};
     for (int e = 1; e < 16; ++e) { tb[e] = palette_bgr[3 * e]; tg[e] = palette_bgr[3 * e + 1]; tr[e] = palette_bgr[3 * e + 2]; }
-    Pal16 pal;
-    pal.b = _mm_load_si128(reinterpret_cast<const __m128i *>(tb));
-    pal.g = _mm_load_si128(reinterpret_cast<const __m128i *>(tg));
-    pal.r = _mm_load_si128(reinterpret_cast<const __m128i *>(tr));
-    constexpr int64_t kAhead = 24;
-#pragma omp parallel for num_threads(threads) schedule(static)
-    for (int64_t i = 0; i < n; ++i) {
-        if (i + kAhead < n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
-        if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
-        expand8_ssse3<MASKED>(pal, rec[i].index, t.chunk_ptr(rec[i].chunk));
-    }
+    DrawPal16Job job{rec, n, &t, {}};
+    job.pal.b = _mm_load_si128(reinterpret_cast<const __m128i *>(tb));
+    job.pal.g = _mm_load_si128(reinterpret_cast<const __m128i *>(tg));
+    job.pal.r = _mm_load_si128(reinterpret_cast<const __m128i *>(tr));
+    HostPool::instance().run(threads, n, kHostChunk, draw_pal16_range<MASKED>, &job);
 }
 #endif
+
+struct BgrJob {
+    const cama_overlay_record *rec;
+    int64_t n;
+    const Target *t;
+    int op;
+};
+void apply_bgr_range(void *ctx, int64_t lo, int64_t hi) {
+    const BgrJob &j = *static_cast<const BgrJob *>(ctx);
+    const cama_overlay_record *rec = j.rec;
+    const Target &t = *j.t;
+    constexpr int64_t kAhead = 24;                 // the destination lines are scattered: prefetch them for writing
+    for (int64_t i = lo; i < hi; ++i) {
+        if (i + kAhead < j.n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
+        if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
+        apply_one(t.chunk_ptr(rec[i].chunk), rec[i].bgr, rec[i].mask & 0xffu, j.op);
+    }
+}
+
+struct PalJob {
+    const cama_overlay_record_palette *rec;
+    int64_t n;
+    const Target *t;
+    int op;
+    const uint64_t *pair_tab;                      // two pixels per lookup: pair[a | b << 8] = the 6 bytes of pixel a followed by pixel b
+};
+void apply_pal_range(void *ctx, int64_t lo, int64_t hi) {
+    const PalJob &j = *static_cast<const PalJob *>(ctx);
+    const cama_overlay_record_palette *rec = j.rec;
+    const Target &t = *j.t;
+    const uint64_t *pair_tab = j.pair_tab;
+    const int op = j.op;
+    constexpr int64_t kAhead = 24;
+    for (int64_t i = lo; i < hi; ++i) {
+        if (i + kAhead < j.n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
+        if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
+        uint8_t *dst = t.chunk_ptr(rec[i].chunk);
+        if (op == CAMA_OVERLAY_BLANK_CHUNKS) {
+            memset(dst, 0, 24);
+            continue;
+        }
+        const uint8_t *ix = rec[i].index;
+        uint16_t pr[4];
+        memcpy(pr, ix, 8);
+        const uint64_t p01 = pair_tab[pr[0]], p23 = pair_tab[pr[1]], p45 = pair_tab[pr[2]], p67 = pair_tab[pr[3]];
+        const uint64_t w[3] = {p01 | p23 << 48, p23 >> 16 | p45 << 32, p45 >> 32 | p67 << 16};
+        if (op == CAMA_OVERLAY_DRAW_CHUNKS) {              // the 24 bytes, assembled in registers (little endian)
+            memcpy(dst, w, 24);
+            continue;
+        }
+        uint8_t bgr[24];
+        memcpy(bgr, w, 24);
+        unsigned mask = 0;
+        for (int k = 0; k < 8; ++k) mask |= (ix[k] ? 1u : 0u) << k;
+        apply_one(dst, bgr, mask, op);
+    }
+}
 
 }  // namespace
 
@@ -194,17 +269,11 @@ extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int forma
         t.mosaic_pitch = (size_t)t.grid_cols * t.width * 3;
         t.mosaic_frame = t.mosaic_pitch * grid_rows * t.height;
     }
-    int threads = n_threads > 0 ? n_threads : omp_get_max_threads();
+    int threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     if (n < 4096) threads = 1;
-    constexpr int64_t kAhead = 24;             // the destination lines are scattered: prefetch them for writing
     if (format == CAMA_OVERLAY_BGR) {
-        const cama_overlay_record *rec = static_cast<const cama_overlay_record *>(records);
-#pragma omp parallel for num_threads(threads) schedule(static)
-        for (int64_t i = 0; i < n; ++i) {
-            if (i + kAhead < n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
-            if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
-            apply_one(t.chunk_ptr(rec[i].chunk), rec[i].bgr, rec[i].mask & 0xffu, op);
-        }
+        BgrJob job{static_cast<const cama_overlay_record *>(records), n, &t, op};
+        HostPool::instance().run(threads, n, kHostChunk, apply_bgr_range, &job);
     } else {
         const cama_overlay_record_palette *rec = static_cast<const cama_overlay_record_palette *>(records);
         uint32_t pal32[256];                                  // packed B | G << 8 | R << 16, entry 0 (not painted) = black
@@ -233,31 +302,8 @@ extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int forma
             }
             pair_used = used;
         }
-        const uint64_t *pair_tab = pair;
-#pragma omp parallel for num_threads(threads) schedule(static)
-        for (int64_t i = 0; i < n; ++i) {
-            if (i + kAhead < n && (int64_t)rec[i + kAhead].chunk < t.n_chunks) __builtin_prefetch(t.chunk_ptr(rec[i + kAhead].chunk), 1, 0);
-            if ((int64_t)rec[i].chunk >= t.n_chunks) continue;
-            uint8_t *dst = t.chunk_ptr(rec[i].chunk);
-            if (op == CAMA_OVERLAY_BLANK_CHUNKS) {
-                memset(dst, 0, 24);
-                continue;
-            }
-            const uint8_t *ix = rec[i].index;
-            uint16_t pr[4];
-            memcpy(pr, ix, 8);
-            const uint64_t p01 = pair_tab[pr[0]], p23 = pair_tab[pr[1]], p45 = pair_tab[pr[2]], p67 = pair_tab[pr[3]];
-            const uint64_t w[3] = {p01 | p23 << 48, p23 >> 16 | p45 << 32, p45 >> 32 | p67 << 16};
-            if (op == CAMA_OVERLAY_DRAW_CHUNKS) {              // the 24 bytes, assembled in registers (little endian)
-                memcpy(dst, w, 24);
-                continue;
-            }
-            uint8_t bgr[24];
-            memcpy(bgr, w, 24);
-            unsigned mask = 0;
-            for (int k = 0; k < 8; ++k) mask |= (ix[k] ? 1u : 0u) << k;
-            apply_one(dst, bgr, mask, op);
-        }
+        PalJob job{rec, n, &t, op, pair};
+        HostPool::instance().run(threads, n, kHostChunk, apply_pal_range, &job);
     }
     return CAMA_OK;
 }
