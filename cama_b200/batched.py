@@ -397,7 +397,7 @@ class Reproject:
         """
         import torch
         # The previous overlay of the reused host buffer is blanked by a helper thread (the native routine runs its
-        # own OpenMP team and holds no Python lock) while this thread looks the poses up, uploads them and the GPU
+        # worker pool and holds no Python lock) while this thread looks the poses up, uploads them and the GPU
         # renders; the draw waits for it.
         blank_job = None
         if backgrounds is None and transfer != "dense" and self._ov_prev is not None and self._host_frames is not None:
