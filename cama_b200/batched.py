@@ -396,7 +396,7 @@ class Reproject:
         consumer of ``render_device`` gets).  Both give identical bytes.
         """
         import torch
-        # The previous overlay of the reused host buffer is blanked by a helper thread (the native routine runs its
+        # The previous overlay of the reused host buffer is blanked by a helper thread (the native routine runs on the library's
         # worker pool and holds no Python lock) while this thread looks the poses up, uploads them and the GPU
         # renders; the draw waits for it.
         blank_job = None

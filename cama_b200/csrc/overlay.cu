@@ -1,7 +1,7 @@
 // libcama_b200: host side of the sparse overlay output — draws the lit 8-pixel chunks the GPU
 // produced into host frames (the in-place draw of /root/reference/cama/reproject.py:246-257 for
 // pixels whose colour is already decided), either plain [F,C,H,W,3] frames or the 2x3 camera mosaic of
-// /root/reference/cama/tools.py:22-25.  Pure byte movement, OpenMP over the records.
+// /root/reference/cama/tools.py:22-25.  Pure byte movement, on the library's worker pool (host_pool.h).
 #include <algorithm>
 #include <cstring>
 #include <thread>
