@@ -129,3 +129,37 @@ def test_palette_draw_chunks_both_paths(n_colours):
         assert apply(recs, got, op=N.OVERLAY_DRAW, threads=threads, fmt=N.OVERLAY_PALETTE, palette=palette) == 0
         assert np.array_equal(got, masked), (n_colours, threads)
 
+
+
+def test_worker_pool_concurrent_callers_and_thread_counts():
+    """The host loops run on the library's own worker pool (csrc/host_pool.h): callers on different Python threads
+    (Reproject's helper thread blanks while the main thread may draw) are serialised region by region, the pool grows
+    with the thread count asked for, and the result never depends on either."""
+    import threading
+    rng = np.random.default_rng(11)
+    shape = (2, 3, 64, 256, 3)
+    n_chunks = int(np.prod(shape)) // 24
+    palette = np.zeros((256, 3), np.uint8)
+    palette[1:4] = [[211, 211, 211], [0, 215, 255], [9, 8, 7]]
+    recs = make_records(rng, n_chunks, 12000, N.OVERLAY_PALETTE)
+    halves = [np.ascontiguousarray(recs[:6000]), np.ascontiguousarray(recs[6000:])]      # disjoint chunks
+    want = np.zeros(shape, np.uint8)
+    reference(recs, want, op=N.OVERLAY_DRAW_CHUNKS, palette=palette)
+    for threads in (2, 3, 8, 0, 5):
+        frames = np.zeros(shape, np.uint8)
+        errors = []
+
+        def work(part):
+            for _ in range(20):
+                if apply(part, frames, op=N.OVERLAY_DRAW_CHUNKS, threads=threads, fmt=N.OVERLAY_PALETTE, palette=palette) != 0:
+                    errors.append(1)
+
+        workers = [threading.Thread(target=work, args=(h,)) for h in halves]
+        for w in workers:
+            w.start()
+        for w in workers:
+            w.join(60)
+        assert not errors and not any(w.is_alive() for w in workers)
+        assert np.array_equal(frames, want), threads
+        assert apply(recs, frames, op=N.OVERLAY_BLANK_CHUNKS, threads=threads, fmt=N.OVERLAY_PALETTE, palette=palette) == 0
+        assert not frames.any()
