@@ -46,6 +46,11 @@ CLASS_RGB = {"Road_teeth": (235, 73, 127), "lane_marking": (211, 211, 211),
              "Stop_Line": (211, 211, 211), "Crosswalk_Line": (255, 215, 0)}
 
 
+def class_colour_arrays():
+    """class -> RGB array, built afresh on every call like BaseManager.get_color_maps (cama/reproject.py:11-17)."""
+    return {k: np.array(v) for k, v in CLASS_RGB.items()}
+
+
 # --------------------------------------------------------------------------- pose algebra
 def inv_rigid(T):
     """[R t; 0 1]^-1 = [R^T, -R^T t]; float64 result.  Reference cama/pose_transformer.py:8-21."""
@@ -234,14 +239,19 @@ def project_instances(instances, K, width, height):
 
 
 def render_instances(image, instances_vu):
-    """In-place painter's loop of radius-2 filled discs, BGR.  Reference cama/reproject.py:246-257."""
+    """In-place painter's loop of radius-2 filled discs, BGR.  Reference cama/reproject.py:246-257.
+
+    The loop has the reference's exact form — rows of the int32 array handed to ``cv2.circle`` as NumPy
+    scalars, the colour tuple built from the class's RGB array per instance — because this function is also
+    what ``bench.py --impl reference`` times: a different spelling of the same loop costs up to 1.8x more
+    per point (tools/port_vs_reference.py keeps the two within 5 % per phase)."""
     import cv2
     for inst in instances_vu:
-        centres = inst["points"].astype(np.int32)
+        points = inst["points"].astype(np.int32)
         cls = inst["class"] if inst["class"] == "lane_marking" else "Crosswalk_Line"
-        bgr = tuple(int(c) for c in CLASS_RGB[cls][::-1])
-        for v, u in centres:
-            cv2.circle(image, (int(u), int(v)), 2, bgr, -1)
+        colour = tuple(class_colour_arrays()[cls][::-1].tolist())
+        for point in points:
+            cv2.circle(image, (point[1], point[0]), 2, colour, -1)
     return image
 
 
@@ -306,6 +316,23 @@ class ClipOracle:
         h, w = OUTPUT_HW
         return {cam: project_instances(transform_instances(chassis_instances, E), K, w, h)
                 for cam, E, K in zip(self.cameras, self.chassis2cam, self.K)}
+
+    def read_resized_image(self, cam, image_idx):
+        """Camera image of a frame, undistort-resized to the output size.  Reference cama/reproject.py:207-215,
+        228-244: cv2.imread, then initUndistortRectifyMap (recomputed on every call, like the reference:
+        d is all zeros in a clip, so the map is a pure affine resample) and a bilinear cv2.remap."""
+        import cv2
+        info = self.attribute["calibration"][cam]
+        stamp = self.attribute["sync"][cam][image_idx]
+        image = cv2.imread(os.path.join(self.clip_path, cam, f"{stamp}.jpg"))
+        h, w = OUTPUT_HW
+        K_origin = np.asarray(info["K"])
+        mapx, mapy = cv2.initUndistortRectifyMap(K_origin, np.asarray(info["d"]), None, self.K[self.cameras.index(cam)], (w, h), cv2.CV_32FC1)
+        return cv2.remap(image, mapx, mapy, interpolation=cv2.INTER_LINEAR)
+
+    def render_vectors(self, per_cam, image_idx):
+        """-> {camera: image}: the frame's camera images with the map drawn in place.  cama/dataset.py:119-126."""
+        return {cam: render_instances(self.read_resized_image(cam, image_idx), per_cam[cam]) for cam in self.cameras}
 
     def render_clip(self, dataset, backgrounds=None):
         """All frames on blank (or given) backgrounds -> (image_idx list, uint8 [F,C,H,W,3])."""

@@ -18,6 +18,14 @@ What is recorded (all produced by reference code, never by this repo's code):
       full per-frame outputs of ClipManager.yield_frame / project_all_camera /
       CameraManager.render_maps on synth.tiny_spec clips (exact-hit and slerp pose variants)
 
+* golden_fullsize.npz        the reference at the sizes BASELINE.json names: per-(frame, camera) SHA-256 of the rendered
+                             frame, visible-point counts and per-frame crop counts for config 2 (all 40 frames x 6
+                             cameras; nuScenes labels with exact and slerp poses, CAMA labels with exact poses) and for
+                             12 sampled frames of the config-3 site (320 frames, 767 k vertices)
+* golden_composited.npz      ClipManager.render_vectors on a 3-frame clip WITH camera JPEGs (cv2.imread ->
+                             initUndistortRectifyMap -> remap -> render_maps in place): SHA-256 per camera-frame, two
+                             full images, and digests of the decoded JPEGs the result was computed from
+
 The synthetic inputs are regenerated at test time from cama_b200.synth (seeded), so the
 fixtures hold outputs plus a digest of the inputs they were computed from.
 """
@@ -305,8 +313,94 @@ def lidar_golden(out_path, root):
     print(out_path)
 
 
+def frame_digests(frames):
+    """uint8 [n, 32]: SHA-256 of each image of `frames` (C-contiguous bytes)."""
+    return np.stack([np.frombuffer(hashlib.sha256(np.ascontiguousarray(f).tobytes()).digest(), np.uint8) for f in frames])
+
+
+def fullsize_case(spec, dataset, root, sample=None):
+    """The unmodified reference loop (main.py:57-59 with blank frames) on a full-size clip ->
+    dict of per-frame / per-camera-frame digests and counts.  sample: positions (in yield order) to keep."""
+    clip = synth.write_clip(spec, root)
+    cm = ClipManager(synth.CAMA_CONFIGS, clip)
+    n_cam = len(cm.cm_list)
+    idx, digests, visible, cropped, lit = [], [], [], [], []
+    for k, (image_idx, instance_map) in enumerate(cm.yield_frame(dataset)):
+        if sample is not None and k not in sample:
+            continue
+        maps_2d = cm.project_all_camera(instance_map)
+        images = [cam.render_maps(np.zeros((cam.height, cam.width, 3), np.uint8), maps_2d[cam.camera_name]) for cam in cm.cm_list]
+        idx.append(image_idx)
+        cropped.append(sum(len(i["points"]) for i in instance_map))
+        visible.append([sum(len(i["points"]) for i in maps_2d[cam.camera_name]) for cam in cm.cm_list])
+        lit.append([int(im.any(-1).sum()) for im in images])
+        digests.append(frame_digests(images))
+    n_vertices = sum(len(i["points"]) for i in cm.instance_maps[dataset])
+    print(spec.name, dataset, "frames", len(idx), "N", n_vertices, "visible", int(np.sum(visible)), "lit", int(np.sum(lit)))
+    return {"frame_idx": np.array(idx, np.int32), "sha256": np.stack(digests).reshape(len(idx), n_cam, 32),
+            "visible": np.array(visible, np.int64), "cropped": np.array(cropped, np.int64), "lit": np.array(lit, np.int64),
+            "n_vertices": np.array(n_vertices, np.int64), "n_instances": np.array(len(cm.instance_maps[dataset]), np.int64)}
+
+
+CONFIG3_SAMPLE = (0, 1, 31, 64, 97, 130, 159, 160, 201, 255, 288, 319)      # positions in yield order (image_idx - 1)
+
+
+def fullsize_golden(out_path, root):
+    out = {}
+    cases = {"config2_nuscenes_exact": (synth.config2_spec(seed=0, name="g_config2_exact"), "nuscenes", None),
+             "config2_nuscenes_slerp": (synth.config2_spec(seed=0, pose_time_offset_ms=25, name="g_config2_slerp"), "nuscenes", None),
+             "config2_cama_exact": (synth.config2_spec(seed=0, name="g_config2_cama"), "cama", None),
+             "config3_nuscenes": (synth.config3_spec(seed=1, name="g_config3"), "nuscenes", set(CONFIG3_SAMPLE))}
+    for key, (spec, dataset, sample) in cases.items():
+        if dataset == "nuscenes":
+            spec.write_cama = False
+        else:
+            spec.write_nuscenes = False
+        for name, value in fullsize_case(spec, dataset, root, sample).items():
+            out[f"{key}.{name}"] = value
+    np.savez_compressed(out_path, **out)
+    print(out_path)
+
+
+def composited_golden(out_path, root):
+    """render_vectors with real camera images (D5: the reference draws in place on the undistort-resized frame)."""
+    import cv2
+    spec = synth.tiny_spec(name="tiny_composited")
+    clip = synth.write_clip(spec, root)
+    synth.write_background_jpegs(clip, spec.n_frames, seed=4)
+    cm = ClipManager(synth.CAMA_CONFIGS, clip)
+    out = {}
+    for dataset in ("nuscenes", "cama"):
+        idx, digests, raw_digests, keep = [], [], [], {}
+        for image_idx, instance_map in cm.yield_frame(dataset):
+            maps_2d = cm.project_all_camera(instance_map)
+            image_dict = cm.render_vectors(maps_2d, image_idx)
+            assert list(image_dict) == synth.CAMERA_LIST
+            images = [image_dict[name] for name in synth.CAMERA_LIST]
+            idx.append(image_idx)
+            digests.append(frame_digests(images))
+            raw_digests.append(frame_digests([cv2.imread(cam.get_image_path(image_idx, True)) for cam in cm.cm_list]))
+            if image_idx == 1:
+                keep = {"image_front": images[1], "image_rear": images[4]}
+        out[f"{dataset}.frame_idx"] = np.array(idx, np.int32)
+        out[f"{dataset}.sha256"] = np.stack(digests)
+        out[f"{dataset}.raw_sha256"] = np.stack(raw_digests)
+        for name, image in keep.items():
+            out[f"{dataset}.{name}"] = image
+        print("composited", dataset, "frames", idx)
+    np.savez_compressed(out_path, **out)
+    print(out_path)
+
+
 def main():
+    if "--fullsize-only" in sys.argv:
+        with tempfile.TemporaryDirectory() as root:
+            fullsize_golden(os.path.join(HERE, "golden_fullsize.npz"), root)
+            composited_golden(os.path.join(HERE, "golden_composited.npz"), root)
+        return
     with tempfile.TemporaryDirectory() as root:
+        fullsize_golden(os.path.join(HERE, "golden_fullsize.npz"), root)
+        composited_golden(os.path.join(HERE, "golden_composited.npz"), root)
         lidar_golden(os.path.join(HERE, "golden_lidar.npz"), root)
         known_answers(os.path.join(HERE, "golden_known_answers.npz"), root)
         pose_golden(os.path.join(HERE, "golden_pose.npz"))
