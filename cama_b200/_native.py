@@ -16,12 +16,16 @@ VERTEX_F32X4, VERTEX_F64X3 = 0, 1
 CLIP_AUTO, CLIP_PLANE, CLIP_BINNED = 0, 1, 2
 MAX_CAMERAS = 8
 TILE_VERTICES = 256
+WARP_VERTICES = 32
+MAX_PEERS = 8
+PEER_HEADER_BYTES = 256
+PEER_HANDLE_BYTES = 64
 OVERLAY_BGR, OVERLAY_PALETTE = 0, 1
 OVERLAY_RECORD_BYTES = {OVERLAY_BGR: 32, OVERLAY_PALETTE: 12}
 OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
 CLIP_PHASES = 4
 PHASE_NAMES = ("prep", "geometry", "sort", "raster")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CamaError(RuntimeError):
@@ -31,7 +35,7 @@ class CamaError(RuntimeError):
 
 
 class CapacityError(CamaError):
-    """The record pool of a clip render overflowed; rerun with stats.records_max_per_frame."""
+    """The record pool of a clip render overflowed; rerun with stats.records_per_frame_needed."""
 
 
 class ClipDesc(Structure):
@@ -46,9 +50,10 @@ class ClipDesc(Structure):
         ("instance_bgr", c_void_p), ("background", c_void_p), ("frames", c_void_p),
         ("crop_counts", c_void_p), ("visible_counts", c_void_p), ("vu_dense", c_void_p),
         ("record_capacity", c_int64),
-        ("tile_bounds", c_void_p),
+        ("tile_bounds", c_void_p), ("warp_bounds", c_void_p),
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
+        ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
     ]
 
 
@@ -63,7 +68,7 @@ class VoxelGrid(Structure):
 
 class ClipStats(Structure):
     _fields_ = [
-        ("records_total", c_int64), ("records_max_per_frame", c_int64), ("record_capacity", c_int64),
+        ("records_total", c_int64), ("records_per_frame_needed", c_int64), ("record_capacity", c_int64),
         ("overflow", c_int32), ("mode", c_int32), ("band_rows", c_int32), ("n_bands", c_int32),
         ("overlay_records", c_int64),
     ]
@@ -100,6 +105,14 @@ SIGNATURES = {
     "cama_overlay_apply_host": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(OverlayTarget), c_int, c_int]),
     "cama_lidar_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cama_overlay_fetch_apply": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, POINTER(OverlayTarget), c_int, c_int, c_void_p]),
+    "cama_peer_slot_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
+    "cama_peer_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p]),
+    "cama_peer_free": (c_int, [c_void_p, c_void_p]),
+    "cama_peer_open": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_void_p)]),
+    "cama_peer_close": (c_int, [c_void_p, c_void_p]),
+    "cama_peer_publish": (c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_void_p), c_int, c_void_p]),
+    "cama_peer_expand": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_uint32, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cama_overlay_expand": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

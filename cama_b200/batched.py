@@ -48,12 +48,13 @@ def pack_vertices(instances):
     return N.VERTEX_F64X3, np.ascontiguousarray(flat), ordinal, bgr
 
 
-def tile_bounds(xyz):
-    """float64 [ceil(n / TILE_VERTICES), 6]: centre and half-extent of the axis-aligned box of every tile of
-    consecutive vertices (``tile_bounds`` of cama_clip_desc).  Non-finite coordinates make a tile uncullable."""
+def tile_bounds(xyz, tile=None):
+    """float64 [ceil(n / tile), 6]: centre and half-extent of the axis-aligned box of every tile of
+    consecutive vertices (``tile_bounds`` / ``warp_bounds`` of cama_clip_desc; tile = TILE_VERTICES by default).
+    Non-finite coordinates make a tile uncullable."""
     xyz = np.asarray(xyz, dtype=np.float64)
     n = xyz.shape[0]
-    starts = np.arange(0, n, N.TILE_VERTICES)
+    starts = np.arange(0, n, tile or N.TILE_VERTICES)
     lo = np.minimum.reduceat(xyz, starts, axis=0)
     hi = np.maximum.reduceat(xyz, starts, axis=0)
     out = np.concatenate([(lo + hi) / 2, (hi - lo) / 2], axis=1)
@@ -74,6 +75,7 @@ class _Resident:
         else:
             self.vertices = rt.to_device(verts)
         self.tile_bounds = rt.to_device(tile_bounds(verts[:, :3])) if self.n_vertices else None
+        self.warp_bounds = rt.to_device(tile_bounds(verts[:, :3], N.WARP_VERTICES)) if self.n_vertices else None
         # palette of the distinct instance colours (compact sparse records): entry 0 = not painted
         colours, index = (np.unique(bgr, axis=0, return_inverse=True) if len(bgr) else (np.zeros((0, 3), np.uint8), np.zeros(0, np.int64)))
         self.palette = None
@@ -128,11 +130,21 @@ class ClipRenderer:
         d.record_capacity = int(capacity)
         d.pipeline_frames = int(self.pipeline_frames)
         d.tile_bounds = res.tile_bounds.data_ptr() if getattr(res, "tile_bounds", None) is not None else None
+        d.warp_bounds = res.warp_bounds.data_ptr() if getattr(res, "warp_bounds", None) is not None else None
         if overlay is not None:
-            records, count, fmt = overlay
-            d.overlay_records = records.data_ptr()
-            d.overlay_count = count.data_ptr()
-            d.overlay_capacity = int(records.shape[0])
+            if isinstance(overlay, dict):            # raw pointers (a mailbox slot of shard.PeerExchange)
+                d.overlay_records, d.overlay_count = overlay["records_ptr"], overlay["count_ptr"]
+                d.overlay_capacity, fmt = int(overlay["capacity"]), overlay["fmt"]
+                mirrors = list(overlay.get("mirrors", ()))
+                d.overlay_n_mirrors = len(mirrors)
+                for m, ptr in enumerate(mirrors):
+                    d.overlay_mirrors[m] = ptr
+                d.overlay_image_base = int(overlay.get("image_base", 0))
+            else:
+                records, count, fmt = overlay
+                d.overlay_records = records.data_ptr()
+                d.overlay_count = count.data_ptr()
+                d.overlay_capacity = int(records.shape[0])
             d.overlay_format = fmt
             d.instance_palette = res.palette_index.data_ptr() if fmt == N.OVERLAY_PALETTE else None
         return d
@@ -165,6 +177,9 @@ class ClipRenderer:
                    "visible_counts": torch.zeros((n_frames, self.n_cams, res.n_instances), dtype=torch.int32, device=rt.device),
                    "vu_dense": torch.empty((n_frames, self.n_cams, res.n_vertices, 2), dtype=torch.float64, device=rt.device)
                    if want_vu else None}
+        if n_frames == 0:                    # nothing to launch (an empty frame block of a sharded clip): no statistics either
+            self.last_stats = None
+            return (out, dbg) if debug else out
         key = (id(res), n_frames)
         capacity = self.capacity.get(key, 0)
         for attempt in range(3):
@@ -179,7 +194,7 @@ class ClipRenderer:
             code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
             self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
             if code == N.CAMA_E_CAPACITY and attempt < 2:
-                capacity = int(stats.records_max_per_frame * 1.1) + 1024
+                capacity = int(stats.records_per_frame_needed * 1.1) + 1024
                 self.capacity[key] = capacity
                 if dbg:
                     dbg["crop_counts"].zero_()
@@ -246,7 +261,7 @@ class ClipRenderer:
             self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
             retry = False
             if code == N.CAMA_E_CAPACITY:
-                capacity = int(stats.records_max_per_frame * 1.1) + 1024
+                capacity = int(stats.records_per_frame_needed * 1.1) + 1024
                 self.capacity[key] = capacity
                 retry = True
             else:
@@ -259,6 +274,26 @@ class ClipRenderer:
                 return records, int(stats.overlay_records), fmt
         raise N.CamaError(N.CAMA_E_CAPACITY, "record pools kept overflowing")
 
+
+    def enqueue_overlay(self, res, w2c_dev, overlay, mode="auto", capacity=None, lane=0):
+        """Asynchronous sparse render: enqueues one clip whose lit-chunk records go to caller-provided storage and
+        returns at once (no counter is read back; the caller checks the count against its capacity later).
+
+        overlay   dict(records_ptr, count_ptr, capacity, fmt[, mirrors, image_base]) — see ``cama_clip_desc``
+        capacity  centre records per frame of the internal pool (default: what earlier checked renders of this
+                  resident / frame count settled on)
+        """
+        n_frames = int(w2c_dev.shape[0])
+        if n_frames == 0:
+            return
+        rt = self.rt
+        if capacity is None:
+            capacity = self.capacity.get((id(res), n_frames), 0)
+        desc = self._desc(res, w2c_dev, n_frames, None, None, mode, capacity, None, overlay=overlay)
+        need = ctypes.c_size_t()
+        N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+        ws = rt.scratch("clip" if lane == 0 else f"clip{lane}", need.value)
+        N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
 
     def expand_overlay(self, records, n, fmt, palette, n_frames, out=None, zero_first=True):
         """cama_overlay_expand: overlay records (device) -> dense frames torch uint8 [n_frames,C,H,W,3] on the device.
@@ -383,8 +418,16 @@ class Reproject:
             return None
         return np.array([order.index(name) for name in self.camera_names], dtype=np.int32)
 
-    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse", layout="frames"):
+    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse", layout="frames", copy=False):
         """-> (image_idx list, uint8 numpy [F',C,H,W,3] in host memory).
+
+        **Ownership of the returned array.**  With ``backgrounds`` the result IS that array (drawn on in place, as the
+        reference draws on the camera images).  Without, the result is a buffer this object owns and REUSES: it stays
+        valid until the next call on the same object, which blanks the pixels painted now and draws the new overlay
+        into the same memory (that is what keeps a call at ~1 ms: no 373 MB allocation, first touch and zero-fill per
+        clip); bytes the caller writes into it are not cleaned up.  A caller that keeps frames across calls — two
+        datasets, the same dataset twice — passes ``copy=True`` and gets a fresh array it owns, like the reference
+        returns fresh images.
 
         ``backgrounds`` (host uint8 array of that shape) are drawn on **in place**, exactly like the
         reference draws on the camera images (cama/reproject.py:246-257), and returned.  Without
@@ -406,7 +449,10 @@ class Reproject:
             blank_job = self._helper().submit(self._apply_records, self._host_frames, self._host_tiles, prev.data_ptr(), n_prev, prev_fmt,
                                               prev_palette, N.OVERLAY_BLANK_CHUNKS)
         try:
-            return self._call_sparse(dataset, backgrounds, mode, transfer, layout, blank_job)
+            idx, frames = self._call_sparse(dataset, backgrounds, mode, transfer, layout, blank_job)
+            if copy and backgrounds is None:
+                frames = frames.copy()
+            return idx, frames
         except Exception:
             if blank_job is not None:
                 blank_job.exception()                        # (wait for it; its own error, if any, is secondary)

@@ -16,7 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcama_b200.so")
 STAMP_PATH = LIB_PATH + ".stamp"
-SOURCES = ["ops.cu", "clip.cu", "overlay.cu", "densify.cu", "remap.cu", "lidar.cu"]
+SOURCES = ["ops.cu", "clip.cu", "overlay.cu", "densify.cu", "remap.cu", "lidar.cu", "peer.cu"]
 HEADERS = ["common.cuh", "geom.cuh", "host_pool.h", os.path.join("..", "..", "include", "cama_b200.h")]
 
 NVCC_FLAGS = [
@@ -92,6 +92,9 @@ def ensure_built():
             build()
         elif not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing and nvcc is not available to build it")
+        else:
+            raise RuntimeError(f"{LIB_PATH} was built from other sources than the ones in {CSRC} (digest mismatch) and nvcc is "
+                               "not available to rebuild it; set CAMA_B200_LIB=<path> to load a specific build on purpose")
     return LIB_PATH
 
 

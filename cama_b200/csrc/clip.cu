@@ -61,6 +61,12 @@ struct ClipArgs {
     const double *tile_bounds;         // [n_tiles,6] centre + half-extent, or nullptr
     const unsigned long long *worklist; // live units {unit << 8 | frame mask} from geometry_cull_kernel, or nullptr (all units)
     const unsigned *n_live;
+    const double *warp_bounds;         // [ceil(n_vertices / 32),6] centre + half-extent of every warp's 32 vertices, or nullptr
+    unsigned *geo_counter;             // [1] dynamic claims of the geometry warps (cleared by prep)
+    const unsigned char *cam_table;    // [tab_ny][tab_nx] cameras that can see a chassis-frame cell (camera_table_build), or nullptr
+    double tab_x0, tab_y0;
+    float tab_inv_sx, tab_inv_sy;
+    int tab_nx, tab_ny;
     int *crop_counts;
     int *visible_counts;
     double *vu_dense;
@@ -75,16 +81,79 @@ struct ClipArgs {
     uint2 *pool;                       // [pool_cap] {bucket, payload} in arrival order
 };
 
+// ------------------------------------------------------------------------------------------------ camera table
+// Which cameras can see a point of the crop box at all?  The box's x-y rectangle is cut into cells (about a metre);
+// for every cell and camera the five linear forms that decide visibility — q_z > 0, q_x >= 0, W q_z - q_x > 0,
+// q_y >= 0, H q_z - q_y > 0 with q = K (E [x y z 1]) (cama/dataset.py:110-115, cama/reproject.py:191-198) — are
+// maximised over the cell (grown by 2 % for the rounding of the cell lookup) x the box's z range; a camera stays in
+// the cell's mask unless one of them is negative by more than a slack ~1e7 times the rounding error of the chain.
+// The geometry warps then only run the cameras in the OR of their lanes' masks (typically 1-2 of 6).  Conservative:
+// a masked-out camera could not have produced a visible point, so results are unchanged; NaN/inf entries never cull.
+struct CamTable {
+    double x0, y0, sx, sy;                 // cell (ix, iy) covers x0 + [ix, ix+1) sx, y0 + [iy, iy+1) sy
+    int nx, ny;
+};
+constexpr int kCamTableMaxDim = 256;
+
+__device__ __forceinline__ double form_max(const double *f, const double *lo, const double *hi, double &scale) {
+    double m = f[3];
+    scale = fabs(f[3]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (f[j] != 0.0) {
+            m += fmax(f[j] * lo[j], f[j] * hi[j]);
+            scale += fabs(f[j]) * fmax(fabs(lo[j]), fabs(hi[j]));
+        }
+    }
+    return m;
+}
+
+// one (cell, camera): may the camera see anything inside the cell?
+__device__ bool camera_sees_cell(const CamBlock &cams, int c, int width, int height, const CamTable &t, int cell) {
+    const int ix = cell % t.nx, iy = cell / t.nx;
+    const double lo[3] = {t.x0 + (ix - 0.02) * t.sx, t.y0 + (iy - 0.02) * t.sy, cams.box[4]};
+    const double hi[3] = {t.x0 + (ix + 1.02) * t.sx, t.y0 + (iy + 1.02) * t.sy, cams.box[5]};
+    const double *E = cams.E[c], *K = cams.K[c];
+    double q[3][4];                                                // q_r = sum_j K[r][j] * (row j of E), as a form over [x y z 1]
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[r][j] = K[3 * r] * E[j] + K[3 * r + 1] * E[4 + j] + K[3 * r + 2] * E[8 + j];
+    bool out = false;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            f[j] = k == 0 ? q[2][j] : k == 1 ? q[0][j] : k == 2 ? (double)width * q[2][j] - q[0][j] : k == 3 ? q[1][j] : (double)height * q[2][j] - q[1][j];
+        double scale;
+        const double m = form_max(f, lo, hi, scale);
+        out = out || (m < -(1e-6 * scale + 1e-9));               // (false for NaN: never culls)
+    }
+    return !out;
+}
+
 // ------------------------------------------------------------------------------------------------ prep
 // (also clears the per-call counters, so that a clip costs kernel launches only: zero_words 32-bit words at `zero`,
 // the statistics block, the sparse-output counter)
 __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
                             const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
-                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette) {
+                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette,
+                            const __grid_constant__ CamBlock cams, int n_cams, int width, int height, const CamTable tab, unsigned char *__restrict__ cam_table) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                    // (the previous clip's raster still reads the counters cleared here)
     pdl_trigger();
+    if (cam_table) {                               // 8 lanes per cell, one camera each; the lane of camera 0 writes the cell's mask
+        static_assert(CAMA_MAX_CAMERAS == 8, "camera table: one byte per cell, 8 lanes per cell");
+        const int n_cells = tab.nx * tab.ny;
+        for (int base = (i & ~31); base < n_cells * 8; base += gridDim.x * blockDim.x) {       // (warp-uniform bounds: the ballot needs every lane)
+            const int k = base + (threadIdx.x & 31), cell = k >> 3, c = k & 7;
+            const bool sees = cell < n_cells && c < n_cams && camera_sees_cell(cams, c, width, height, tab, cell);
+            const unsigned votes = __ballot_sync(kFull, sees);
+            if (c == 0 && cell < n_cells) cam_table[cell] = (unsigned char)((votes >> (threadIdx.x & 24)) & 0xffu);
+        }
+    }
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
     if (i < stats_words) stats[i] = 0u;
     if (i == 0 && overlay_count) *overlay_count = 0u;
@@ -324,77 +393,106 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
     if (leader) worklist[base + __popc(live & ((1u << lane) - 1u))] = ((unsigned long long)unit << 8) | mask;
 }
 
-// Work unit = (tile of 256 vertices, chunk of 8 frames); each warp of the CTA takes its 32 vertices of
-// the unit through the chunk's frames on its own: the 8 poses sit in the warp's slice of shared memory
-// (broadcast reads), there is no block-level barrier, so a warp whose vertices all fall outside the crop
-// box moves on to the next unit instead of waiting for the warps that have the 6-camera tail to do (on a
-// site, where most warps of a live unit are dead, the per-unit barriers were the largest stall).  A thread
-// keeps its vertex in registers; lanes hold consecutive vertices, so crop survival — and with it the
-// 6-camera tail — is almost warp-uniform (polylines are spatially coherent).
-// NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls and every matrix entry
-// becomes a constant-bank operand of its DFMA instead of an indexed load (0 = any count up to 8).
+// Work unit of a WARP = (32 consecutive vertices, chunk of 8 frames).  The kernel is a persistent grid of
+// independent warps: every warp claims its next unit from a global counter (one returning atomic per unit,
+// issued a whole unit ahead of its use), keeps the 8 poses of the unit in its own slice of shared memory, and
+// never meets a block-level barrier — so a warp whose vertices all fall outside the crop box moves on at once,
+// and no CTA slot idles behind its slowest warp (with one 256-vertex unit per CTA the achieved occupancy was a
+// third: the dead warps of a unit had left, the slot had not).  Per unit: the warp's own bounding box
+// (`warp_bounds`) decides which of the 8 frames it has to look at (lane = frame); a thread keeps its vertex in
+// registers; lanes hold consecutive vertices, so crop survival — and with it the camera tail — is almost
+// warp-uniform (polylines are spatially coherent).  Cameras: the table of camera_table_build gives every
+// surviving lane the cameras that can see its cell; the warp runs the OR of them (typically 1-2 of 6).
+// With a work list (sites: geometry_cull_kernel has culled (256-vertex tile, 8 frames) units) entry e covers the
+// eight warp units 8e .. 8e+7.
+// NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls (0 = any count up to 8).
 template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS, bool PINHOLE>
 __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT_all[kGeoThreads / 32][kGeoFrames][12];
     __shared__ GeoStage stages[kGeoThreads / 32];
+    constexpr int kWarps = kGeoThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31;
     GeoStage &stage = stages[tid >> 5];
     double (*sT)[12] = sT_all[tid >> 5];
-    const long long n_tiles = (a.n_vertices + kGeoThreads - 1) / kGeoThreads;
+    const long long n_tiles = (a.n_vertices + 31) / 32;                     // warp tiles
     const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
-    const long long units = n_tiles * n_chunks;
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
     if (BINNED && lane == 0) stage.count = 0;
     __syncwarp();
     pdl_wait();
     pdl_trigger();
-    const long long n_work = a.worklist ? (long long)*a.n_live : units;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-        long long unit = w;
+    const long long n_work = a.worklist ? (long long)*a.n_live * 8 : n_tiles * n_chunks;
+    const long long first_dynamic = (long long)gridDim.x * kWarps;           // units [0, first_dynamic) are dealt statically
+    long long w = (long long)blockIdx.x * kWarps + (tid >> 5);
+    while (w < n_work) {
+        unsigned claim = 0;
+        if (lane == 0) claim = atomicAdd(a.geo_counter, 1u);                // the unit after this one (used at the bottom of the loop)
+        long long tile;
+        int f0;
         unsigned frame_mask = 0xffu;
         if (a.worklist) {
-            const unsigned long long e = a.worklist[w];
-            unit = (long long)(e >> 8);
+            const unsigned long long e = a.worklist[w >> 3];
+            tile = (long long)(e >> 8) / n_chunks * 8 + (w & 7);            // (a 256-vertex tile = 8 warp tiles)
+            f0 = (int)((long long)(e >> 8) % n_chunks) * kGeoFrames;
             frame_mask = (unsigned)(e & 0xffu);
+        } else {
+            tile = w / n_chunks;
+            f0 = (int)(w % n_chunks) * kGeoFrames;
         }
-        const long long tile = unit / n_chunks;
-        const int f0 = (int)(unit % n_chunks) * kGeoFrames;
         const int nf = min(kGeoFrames, a.n_frames - f0);
-        __syncwarp();
-        for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
-        __syncwarp();
-        if (!a.worklist && a.tile_bounds)                      // (with a work list the cull kernel has made the mask)
-            frame_mask = __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
-        const long long n = tile * kGeoThreads + tid;
-        double vx, vy, vz;
-        int ord;
-        const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
-        for (int fi = 0; fi < nf; ++fi) {
-            if (!((frame_mask >> fi) & 1u)) continue;          // (uniform over the warp)
-            const int f = f0 + fi;
-            const double *T = sT[fi];
-            // reference cama/dataset.py:99-105: world -> chassis, then the crop box
-            const double cx = affine_row(T, vx, vy, vz);
-            const double cy = affine_row(T + 4, vx, vy, vz);
-            const double cz = affine_row(T + 8, vx, vy, vz);
-            const bool alive = valid && in_box(cams.box, cx, cy, cz);
-            if (__any_sync(kFull, alive)) {
-                if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
-                const int n_cams = NCAMS ? NCAMS : a.n_cams;
-                double qx = 0.0, qy = 0.0, qz = 1.0;            // (lanes that are no candidate keep whatever the last camera left: masked)
-#pragma unroll
-                for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
-                    if (!NCAMS && c >= n_cams) break;
-                    const bool cand = alive && camera_candidate<PINHOLE>(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
-                    if (!__any_sync(kFull, cand)) continue;
-                    int vi = 0, ui = 0;
-                    double v = 0.0, u = 0.0;
-                    const bool vis = candidate_pixel(cand, qx, qy, qz, a.width, a.height, want_exact, vi, ui, v, u);
-                    if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, stage, f, c, vis, vi, ui, v, u, ord, n);
-                }
-            }
-            if (BINNED && stage.count >= (unsigned)kStageFlush) stage_flush(a, stage);     // (warp-uniform)
+        if (tile < n_tiles) {
+            __syncwarp();
+            for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
+            __syncwarp();
+            if (a.warp_bounds)
+                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.warp_bounds + tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
+            else if (!a.worklist && a.tile_bounds)                            // (with a work list the cull kernel has made the mask)
+                frame_mask = __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + (tile >> 3) * 6, sT[lane & (kGeoFrames - 1)], cams.box));
+            if (nf < kGeoFrames) frame_mask &= (1u << nf) - 1u;
+        } else {
+            frame_mask = 0u;
         }
+        if (frame_mask) {
+            const long long n = tile * 32 + lane;
+            double vx, vy, vz;
+            int ord;
+            const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
+            for (unsigned left = frame_mask; left; left &= left - 1u) {       // (uniform over the warp)
+                const int fi = __ffs(left) - 1;
+                const int f = f0 + fi;
+                const double *T = sT[fi];
+                // reference cama/dataset.py:99-105: world -> chassis, then the crop box
+                const double cx = affine_row(T, vx, vy, vz);
+                const double cy = affine_row(T + 4, vx, vy, vz);
+                const double cz = affine_row(T + 8, vx, vy, vz);
+                const bool alive = valid && in_box(cams.box, cx, cy, cz);
+                if (__any_sync(kFull, alive)) {
+                    if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
+                    const int n_cams = NCAMS ? NCAMS : a.n_cams;
+                    unsigned lane_cams = alive ? 0xffu : 0u;                   // cameras that can see this lane's point at all
+                    if (a.cam_table && alive) {
+                        const int ix = min(max((int)((float)(cx - a.tab_x0) * a.tab_inv_sx), 0), a.tab_nx - 1);
+                        const int iy = min(max((int)((float)(cy - a.tab_y0) * a.tab_inv_sy), 0), a.tab_ny - 1);
+                        lane_cams = __ldg(a.cam_table + iy * a.tab_nx + ix);
+                    }
+                    const unsigned warp_cams = __reduce_or_sync(kFull, lane_cams);
+                    double qx = 0.0, qy = 0.0, qz = 1.0;            // (lanes that are no candidate keep whatever the last camera left: masked)
+#pragma unroll
+                    for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
+                        if (!NCAMS && c >= n_cams) break;
+                        if (!((warp_cams >> c) & 1u)) continue;     // (uniform)
+                        const bool cand = ((lane_cams >> c) & 1u) && camera_candidate<PINHOLE>(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
+                        if (!__any_sync(kFull, cand)) continue;
+                        int vi = 0, ui = 0;
+                        double v = 0.0, u = 0.0;
+                        const bool vis = candidate_pixel(cand, qx, qy, qz, a.width, a.height, want_exact, vi, ui, v, u);
+                        if (!BINNED || DEBUG || __any_sync(kFull, vis)) emit_centre<BINNED, DEBUG>(a, stage, f, c, vis, vi, ui, v, u, ord, n);
+                    }
+                }
+                if (BINNED && stage.count >= (unsigned)kStageFlush) stage_flush(a, stage);     // (warp-uniform)
+            }
+        }
+        w = first_dynamic + (long long)__shfl_sync(kFull, claim, 0);
     }
     if (BINNED && stage.count > 0u) stage_flush(a, stage);
 }
@@ -436,7 +534,7 @@ __global__ void __launch_bounds__(256) plane_raster_kernel(const unsigned *__res
 // ------------------------------------------------------------------------------------------------ BINNED: scan + scatter
 struct ClipStatsDev {
     unsigned long long records_total;
-    unsigned long long records_max_per_frame;
+    unsigned long long records_per_frame_needed;
     unsigned overflow;
     unsigned pad;
 };
@@ -541,7 +639,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__res
         start[nb] = carry;
         const unsigned long long total = pool_total;
         stats->records_total = total;
-        stats->records_max_per_frame = n_frames > 0 ? (total + n_frames - 1) / n_frames : 0;    // mean per frame: what a rerun must provision
+        stats->records_per_frame_needed = n_frames > 0 ? (total + n_frames - 1) / n_frames : 0;    // the pool is shared by the frames of a pass: mean per frame
         stats->overflow = total > (unsigned long long)pool_cap ? 1u : 0u;
     }
 }
@@ -662,6 +760,8 @@ struct RasterArgs {
     void *ov_records;                      // MODE 2 / 3: sparse output records
     unsigned *ov_count;
     long long ov_cap;
+    void *ov_mirrors[CAMA_MAX_PEERS];      // record arrays on peer GPUs that receive every flush too (frame-sharded clips)
+    int ov_n_mirrors;
 };
 
 // Sparse output (MODE 2: 32-byte BGR records, MODE 3: 12-byte palette records): lit 8-pixel chunks are
@@ -679,6 +779,7 @@ struct OvSink {
     unsigned *records;
     unsigned *count;
     long long cap;
+    const RasterArgs *args;                // (mirrors)
 };
 
 template <int RW>
@@ -691,6 +792,12 @@ __device__ __forceinline__ void ov_flush(const OvSink &o) {
     const long long room = o.cap > b ? o.cap - b : 0;                  // records that still fit
     const unsigned n_words = (unsigned)min((long long)n, room) * RW;
     for (unsigned i = lane; i < n_words; i += 32) o.records[b * RW + i] = o.st->words[i];
+    // frame-sharded clips: the same words to the same place in every peer's mailbox (stores over NVLink; the slot's
+    // count and step number follow in cama_peer_publish, after this kernel)
+    for (int m = 0; m < o.args->ov_n_mirrors; ++m) {
+        unsigned *dst = static_cast<unsigned *>(o.args->ov_mirrors[m]) + b * RW;
+        for (unsigned i = lane; i < n_words; i += 32) dst[i] = o.st->words[i];
+    }
     __syncwarp();
     if (lane == 0) o.st->count = 0;
     __syncwarp();
@@ -871,7 +978,7 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
     OvSink ov{};
     if (MODE >= 2) {                                                     // per-warp staging of sparse records, after the zeros
         ov.st = reinterpret_cast<OvStage *>(zeros + zero_bytes) + warp;
-        ov.records = reinterpret_cast<unsigned *>(a.ov_records); ov.count = a.ov_count; ov.cap = a.ov_cap;
+        ov.records = reinterpret_cast<unsigned *>(a.ov_records); ov.count = a.ov_count; ov.cap = a.ov_cap; ov.args = &a;
         if (lane == 0) ov.st->count = 0;
     }
     const bool inplace = MODE == 1 && a.bg == a.frames;
@@ -1132,7 +1239,7 @@ struct ClipPlan {
     size_t raster_smem;
     // workspace offsets
     size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
-    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists;
+    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists, off_camtab;
     long long geo_units;
     size_t total;
     // frame-group pipeline (BINNED): the clip is rendered as `groups` sub-clips of `group_frames` frames, each with
@@ -1207,6 +1314,10 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     p.off_stats = take(sizeof(ClipStatsDev));
     p.geo_units = ((d->n_vertices + kGeoThreads - 1) / kGeoThreads) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
     p.off_worklist = take(sizeof(unsigned long long) * (size_t)std::max<long long>(p.geo_units, 1));
+    p.off_camtab = take((size_t)kCamTableMaxDim * kCamTableMaxDim);
+    p.off_zero = off;                                                      // cleared by prep every call: counters | hist (BINNED)
+    p.off_counter = take(256);
+    p.zero_bytes = off - p.off_zero;
     if (mode == CAMA_CLIP_PLANE) {
         p.off_plane = take(sizeof(unsigned) * (size_t)d->n_frames * d->n_cams * H * W);
     } else {
@@ -1224,9 +1335,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         p.cap = cap;
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         if (d->overlay_records) p.raster_smem += sizeof(OvStage) * kRasterWarps;
-        p.off_zero = off;
-        p.off_counter = take(256);
-        p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));
+        p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));              // (directly after the counter block)
         p.zero_bytes = off - p.off_zero;
         p.off_start = take(sizeof(unsigned) * ((size_t)nb + 1));
         p.off_lists = take(sizeof(unsigned) * 4 * (size_t)nb);             // bucket lists of the raster, one per weight class
@@ -1282,24 +1391,47 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     const bool binned = p.mode == CAMA_CLIP_BINNED;
     const bool pdl = binned && pdl_enabled() && !prof;
 
+    // camera table over the crop box's x-y rectangle (cells of about a metre, at most 256 x 256); none for a degenerate box
+    CamTable tab{};
+    {
+        static const bool no_table = getenv("CAMA_GEO_NO_CAMTABLE") != nullptr;          // experiment knob
+        const double rx = d->crop_box[1] - d->crop_box[0], ry = d->crop_box[3] - d->crop_box[2];
+        if (!no_table && rx > 0.0 && ry > 0.0 && rx <= 1e6 && ry <= 1e6) {                // (false for NaN / infinite boxes)
+            tab.nx = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(rx)));
+            tab.ny = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(ry)));
+            tab.x0 = d->crop_box[0]; tab.y0 = d->crop_box[2];
+            tab.sx = rx / tab.nx; tab.sy = ry / tab.ny;
+            a.cam_table = ws + p.off_camtab;
+            a.tab_x0 = tab.x0; a.tab_y0 = tab.y0;
+            a.tab_inv_sx = (float)(1.0 / tab.sx); a.tab_inv_sy = (float)(1.0 / tab.sy);
+            a.tab_nx = tab.nx; a.tab_ny = tab.ny;
+        }
+    }
+    static const bool no_warp_bounds = getenv("CAMA_GEO_NO_WARPBOUNDS") != nullptr;     // experiment knob
+    a.warp_bounds = no_warp_bounds ? nullptr : d->warp_bounds;
+    a.geo_counter = reinterpret_cast<unsigned *>(ws + p.off_counter) + 8;
     if (d->vu_dense)
         CAMA_CUDA_TRY(cudaMemsetAsync(d->vu_dense, 0xff, sizeof(double) * 2 * (size_t)d->n_frames * d->n_cams * d->n_vertices, s));
     {
         NvtxRange nvtx_phase("prep");
-        const long long zero_words = binned ? (long long)(p.zero_bytes / 4) : 0;
-        const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
+        const long long zero_words = (long long)(p.zero_bytes / 4);
+        const long long n = std::max<long long>(std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20)),
+                                                (long long)tab.nx * tab.ny * 8);
         // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
         CAMA_CUDA_TRY(launch_k(pdl, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
                                d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
                                d->instance_bgr, d->n_instances, lut,
-                               binned ? reinterpret_cast<unsigned *>(ws + p.off_zero) : (unsigned *)nullptr, zero_words,
+                               reinterpret_cast<unsigned *>(ws + p.off_zero), zero_words,
                                reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
+                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette,
+                               cams, d->n_cams, d->width, d->height, tab, tab.nx ? ws + p.off_camtab : (unsigned char *)nullptr));
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
-    const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
-    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * 16));
+    const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);          // (256-vertex tile, 8 frames): what the cull kernel works on
+    const long long warp_units = ((d->n_vertices + 31) / 32) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
+    // persistent grid: every resident warp claims (32-vertex, 8-frame) units until none are left
+    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>((warp_units + 7) / 8, (long long)ctx->sm_count * CAMA_GEO_MINB));
     const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
     const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;
 
@@ -1392,6 +1524,9 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     const bool rpdl = pdl && !lanes_split;
     if (d->overlay_records) {
         r.ov_records = d->overlay_records; r.ov_count = d->overlay_count; r.ov_cap = d->overlay_capacity;
+        r.ov_n_mirrors = d->overlay_n_mirrors;
+        for (int m = 0; m < d->overlay_n_mirrors; ++m) r.ov_mirrors[m] = d->overlay_mirrors[m];
+        r.image_base = image_base + (int)d->overlay_image_base;
         if (d->overlay_format == CAMA_OVERLAY_PALETTE) {
             CAMA_CUDA_TRY(cudaFuncSetAttribute(binned_raster_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.raster_smem));
             CAMA_CUDA_TRY(launch_k(rpdl, binned_raster_kernel<3>, raster_grid, kRasterBlock, p.raster_smem, s, r));
@@ -1441,7 +1576,10 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_REQUIRE(((uintptr_t)d->overlay_records & 15) == 0, "overlay_records must be 16-byte aligned");
         CAMA_REQUIRE(d->overlay_format == CAMA_OVERLAY_BGR || d->overlay_format == CAMA_OVERLAY_PALETTE, "bad overlay_format");
         CAMA_REQUIRE(d->overlay_format != CAMA_OVERLAY_PALETTE || d->n_instances == 0 || d->instance_palette, "the palette overlay format needs instance_palette");
-        CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width / 8 < (1ll << 32), "clip too large for 32-bit chunk indices");
+        CAMA_REQUIRE(d->overlay_image_base >= 0 && ((long long)d->n_frames * d->n_cams + d->overlay_image_base) * d->height * d->width / 8 < (1ll << 32),
+                     "clip too large for 32-bit chunk indices");
+        CAMA_REQUIRE(d->overlay_n_mirrors >= 0 && d->overlay_n_mirrors <= CAMA_MAX_PEERS, "overlay_n_mirrors out of range");
+        for (int m = 0; m < d->overlay_n_mirrors; ++m) CAMA_REQUIRE(d->overlay_mirrors[m] && ((uintptr_t)d->overlay_mirrors[m] & 15) == 0, "overlay_mirrors[%d] is NULL or misaligned", m);
     }
     CAMA_REQUIRE(d->n_vertices == 0 || d->vertices, "vertices is NULL");
     CAMA_REQUIRE(d->n_instances == 0 || d->instance_bgr, "instance_bgr is NULL");
@@ -1531,6 +1669,14 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     ClipPlan p;
     int rc = make_plan(d, p);
     if (rc != CAMA_OK) return rc;
+    if (d->n_frames == 0) {                        // cama_clip_render launched nothing: the workspace holds no statistics of this call
+        *out = cama_clip_stats{};
+        out->record_capacity = p.cap;
+        out->mode = p.mode;
+        out->band_rows = p.band_rows;
+        out->n_bands = p.n_bands;
+        return CAMA_OK;
+    }
     DeviceGuard guard(ctx->device);
     const bool grouped = p.groups > 1 && ctx->last_render_grouped;      // (phase-profiled renders are un-grouped)
     const int n_blocks = grouped ? p.groups : 1;
@@ -1553,11 +1699,11 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     unsigned overflow = 0;
     for (const ClipStatsDev &b : h) {
         total += b.records_total;
-        max_per_frame = std::max(max_per_frame, b.records_max_per_frame);
+        max_per_frame = std::max(max_per_frame, b.records_per_frame_needed);
         overflow |= b.overflow;
     }
     out->records_total = (int64_t)total;
-    out->records_max_per_frame = (int64_t)max_per_frame;
+    out->records_per_frame_needed = (int64_t)max_per_frame;
     out->record_capacity = p.cap;
     out->overflow = (int32_t)overflow;
     out->mode = p.mode;
@@ -1565,7 +1711,7 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->n_bands = p.n_bands;
     out->overlay_records = sparse ? n_overlay : 0;
     if (overflow)
-        return fail(CAMA_E_CAPACITY, "record pool overflow: a frame produced %llu records, capacity %lld", max_per_frame, p.cap);
+        return fail(CAMA_E_CAPACITY, "record pool overflow: %llu records per frame needed, capacity %lld", max_per_frame, p.cap);
     return CAMA_OK;
 }
 

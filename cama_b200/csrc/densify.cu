@@ -143,6 +143,9 @@ int cama_densify_fill(cama_ctx *ctx, const float *raw_xy, const int32_t *raw_pol
     if (total == 0) return CAMA_OK;
     CAMA_REQUIRE(raw_xy && raw_poly && seg_start && out_vertices, "NULL buffer");
     CAMA_REQUIRE(!bev_height || (bev_rows > 0 && bev_cols > 0), "bad height map shape");
+    // both indices are clipped with bev_rows - 1, like the reference (cama/reproject.py:98): a map with fewer columns
+    // than rows would be read past the end of a row (the reference raises IndexError there)
+    CAMA_REQUIRE(!bev_height || bev_cols >= bev_rows, "height map with fewer columns (%d) than rows (%d): the reference's lookup fails on it", bev_cols, bev_rows);
     CAMA_REQUIRE(((uintptr_t)out_vertices & 15) == 0, "out_vertices must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     DensifyArgs a{};

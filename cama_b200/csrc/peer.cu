@@ -1,0 +1,233 @@
+// libcama_b200: a frame-sharded clip assembled on every GPU of one box without a host in the loop.
+//
+// BASELINE.json configs[3] shards the frames of a site over the GPUs (frames are independent units of
+// /root/reference/cama/dataset.py:88-106) and wants every rank to end up with every frame.  Moving the dense uint8
+// frames is NVLink-bound (every rank receives (world-1)/world of 3 GB); only ~6 % of the pixels are painted, so the
+// ranks exchange the LIT 8-PIXEL CHUNKS instead and rebuild the frames locally at HBM speed:
+//
+//   raster (clip.cu, sparse output)   every flush of lit-chunk records goes to the rank's slot of its own mailbox AND,
+//                                      by peer stores over NVLink, to the same slot of every peer's mailbox — the
+//                                      exchange happens tile by tile while the raster computes, there is no separate
+//                                      collective;
+//   cama_peer_publish                  one warp: record count + step number into the slot headers on every GPU
+//                                      (release at system scope, after the records);
+//   cama_peer_expand                   waits (acquire at system scope, with a timeout) until the slots of all ranks
+//                                      carry this step's number, then writes every record's 8 pixels into the
+//                                      zero-filled frames.
+//
+// Mailbox of a rank (device memory allocated here with cudaMalloc, so that cudaIpcGetMemHandle can export it):
+//   [2 parities][world sources] slots of  cama_peer_slot_bytes(capacity, record_bytes)  =  256-byte header | records.
+// A slot is rewritten two steps later; the stream order render(s) -> publish(s) -> expand(s) -> render(s+1) on every
+// rank makes that safe (a rank can only publish step s+2 after its expand of step s+1 has seen every peer's step s+1,
+// which those peers published after finishing their expand of step s).
+#include "common.cuh"
+
+using namespace cama;
+
+namespace {
+
+struct SlotHeader {                    // first 256 bytes of a slot
+    unsigned count;                    // records appended (may exceed the capacity: the excess was dropped)
+    unsigned step;                     // written last, with release semantics
+    unsigned pad[62];
+};
+static_assert(sizeof(SlotHeader) == CAMA_PEER_HEADER_BYTES, "slot header size is part of the ABI");
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct PeerPtrs {
+    void *p[CAMA_MAX_PEERS];
+};
+
+__global__ void peer_publish_kernel(const unsigned *__restrict__ count, unsigned step, PeerPtrs headers, int n) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    SlotHeader *h = static_cast<SlotHeader *>(headers.p[i]);
+    h->count = *count;
+    __threadfence_system();            // the records (written by the kernels before this one) and the count, then the step
+    st_release_sys(&h->step, step);
+}
+
+// status[0]: 0 = ok, 1 = timed out waiting for a peer (nothing expanded), 2 = a slot overflowed its capacity
+template <int FORMAT>
+__global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int world, unsigned step, long long capacity, const uint32_t *__restrict__ palette,
+                                                         uint8_t *__restrict__ frames, long long n_chunks, unsigned long long timeout_ns, int *status) {
+    __shared__ long long s_before[CAMA_MAX_PEERS + 1];
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        bool ok = true;
+        long long total = 0;
+        for (int r = 0; r < world && ok; ++r) {
+            const SlotHeader *h = static_cast<const SlotHeader *>(slots.p[r]);
+            while (ld_acquire_sys(&h->step) != step) {
+                if (global_ns() - t0 > timeout_ns) { ok = false; break; }
+                __nanosleep(200);
+            }
+            s_before[r] = total;
+            if (ok) {
+                const long long c = h->count;
+                if (c > capacity && blockIdx.x == 0) atomicMax(status, 2);
+                total += c < capacity ? c : capacity;
+            }
+        }
+        s_before[world] = total;
+        if (!ok && blockIdx.x == 0) atomicMax(status, 1);
+        s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const long long total = s_before[world];
+    constexpr int RW = FORMAT == CAMA_OVERLAY_BGR ? 8 : 3;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        int r = 0;
+        while (r + 1 < world && i >= s_before[r + 1]) ++r;
+        const uint32_t *rec = reinterpret_cast<const uint32_t *>(static_cast<const unsigned char *>(slots.p[r]) + CAMA_PEER_HEADER_BYTES) + (i - s_before[r]) * RW;
+        uint32_t w[6], chunk;
+        if (FORMAT == CAMA_OVERLAY_BGR) {
+            const uint4 a = reinterpret_cast<const uint4 *>(rec)[0], b = reinterpret_cast<const uint4 *>(rec)[1];
+            chunk = a.x;
+            w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
+        } else {
+            chunk = rec[0];
+            const uint32_t lo = rec[1], hi = rec[2];
+            uint32_t c[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                c[k] = palette[(lo >> (8 * k)) & 0xffu];
+                c[4 + k] = palette[(hi >> (8 * k)) & 0xffu];
+            }
+            w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
+            w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
+        }
+        if ((long long)chunk >= n_chunks) continue;
+        uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk * 24);
+        d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+    }
+}
+
+__global__ void palette_pack256_kernel(const uint8_t *__restrict__ palette_bgr, uint32_t *__restrict__ packed) {
+    const int e = threadIdx.x;
+    packed[e] = e == 0 ? 0u : (uint32_t)palette_bgr[3 * e] | ((uint32_t)palette_bgr[3 * e + 1] << 8) | ((uint32_t)palette_bgr[3 * e + 2] << 16);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cama_peer_slot_bytes(int64_t capacity_records, int record_bytes, size_t *bytes) {
+    CAMA_REQUIRE(bytes && capacity_records >= 0 && record_bytes > 0, "bad argument");
+    *bytes = align_up((size_t)CAMA_PEER_HEADER_BYTES + (size_t)capacity_records * (size_t)record_bytes, 256);
+    return CAMA_OK;
+}
+
+int cama_peer_alloc(cama_ctx *ctx, size_t bytes, void **dev_ptr, void *ipc_handle) {
+    CAMA_REQUIRE(ctx && dev_ptr && ipc_handle && bytes > 0, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CAMA_PEER_HANDLE_BYTES, "IPC handle size is part of the ABI");
+    DeviceGuard guard(ctx->device);
+    void *p = nullptr;
+    CAMA_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(CAMA_E_CUDA, "cama_peer_alloc: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return CAMA_OK;
+}
+
+int cama_peer_free(cama_ctx *ctx, void *dev_ptr) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    if (!dev_ptr) return CAMA_OK;
+    DeviceGuard guard(ctx->device);
+    CAMA_CUDA_TRY(cudaFree(dev_ptr));
+    return CAMA_OK;
+}
+
+int cama_peer_open(cama_ctx *ctx, int peer_device, const void *ipc_handle, void **dev_ptr) {
+    CAMA_REQUIRE(ctx && ipc_handle && dev_ptr, "bad argument");
+    DeviceGuard guard(ctx->device);
+    int can = 0;
+    CAMA_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(CAMA_E_UNSUPPORTED, "device %d cannot access the memory of device %d (no peer-to-peer path)", ctx->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+    } else if (e != cudaSuccess) {
+        return fail(CAMA_E_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void *p = nullptr;
+    CAMA_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return CAMA_OK;
+}
+
+int cama_peer_close(cama_ctx *ctx, void *dev_ptr) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    if (!dev_ptr) return CAMA_OK;
+    DeviceGuard guard(ctx->device);
+    CAMA_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return CAMA_OK;
+}
+
+int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t step, void *const *slot_headers, int n, void *stream) {
+    CAMA_REQUIRE(ctx && overlay_count && slot_headers, "NULL argument");
+    CAMA_REQUIRE(n > 0 && n <= CAMA_MAX_PEERS, "1..%d slots", CAMA_MAX_PEERS);
+    DeviceGuard guard(ctx->device);
+    PeerPtrs hp{};
+    for (int i = 0; i < n; ++i) {
+        CAMA_REQUIRE(slot_headers[i], "slot_headers[%d] is NULL", i);
+        hp.p[i] = slot_headers[i];
+    }
+    peer_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(overlay_count, step, hp, n);
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, uint32_t step, int64_t capacity_records, int format, const uint8_t *palette_bgr,
+                     void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams, int height, int width, int timeout_ms, int32_t *status,
+                     void *stream) {
+    CAMA_REQUIRE(ctx && slots && status, "NULL argument");
+    CAMA_REQUIRE(world > 0 && world <= CAMA_MAX_PEERS, "1..%d ranks", CAMA_MAX_PEERS);
+    CAMA_REQUIRE(format == CAMA_OVERLAY_BGR || format == CAMA_OVERLAY_PALETTE, "bad format");
+    CAMA_REQUIRE(format != CAMA_OVERLAY_PALETTE || (palette_bgr && palette_scratch), "the palette format needs palette_bgr and palette_scratch (device)");
+    CAMA_REQUIRE(n_frames >= 0 && n_cams > 0 && height > 0 && width > 0 && width % 8 == 0 && capacity_records >= 0, "bad shape");
+    const int64_t n_chunks = n_frames * n_cams * height * (width / 8);
+    CAMA_REQUIRE(n_chunks == 0 || (frames && ((uintptr_t)frames & 7) == 0), "frames must be 8-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerPtrs sp{};
+    for (int r = 0; r < world; ++r) {
+        CAMA_REQUIRE(slots[r] && ((uintptr_t)slots[r] & 255) == 0, "slots[%d] must be a 256-byte aligned device pointer", r);
+        sp.p[r] = slots[r];
+    }
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    // a few CTAs per SM: the record loop is grid-stride, and every CTA first waits for the peers' step numbers
+    const unsigned grid = (unsigned)ctx->sm_count * 8u;
+    if (format == CAMA_OVERLAY_PALETTE) {
+        palette_pack256_kernel<<<1, 256, 0, s>>>(palette_bgr, static_cast<uint32_t *>(palette_scratch));
+        CAMA_LAUNCHED(ctx);
+        peer_expand_kernel<CAMA_OVERLAY_PALETTE><<<grid, 256, 0, s>>>(sp, world, step, capacity_records, static_cast<const uint32_t *>(palette_scratch), frames, n_chunks, timeout_ns, status);
+    } else {
+        peer_expand_kernel<CAMA_OVERLAY_BGR><<<grid, 256, 0, s>>>(sp, world, step, capacity_records, nullptr, frames, n_chunks, timeout_ns, status);
+    }
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+}  // extern "C"

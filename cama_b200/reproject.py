@@ -153,7 +153,9 @@ class MapManager(BaseManager):
 
     def calculate_3d_instance_maps(self, bev_height, maps_2d):
         """BEV-pixel (CAMA) labels + height map -> dense world instances."""
-        if self._densify == "device" and bev_height.dtype == np.float32 and bev_height.ndim == 2:
+        # (the reference clips BOTH indices with shape[0]-1, :98: with fewer columns than rows it raises IndexError for
+        # some labels; such maps take the host path below, which raises like the reference does)
+        if self._densify == "device" and bev_height.dtype == np.float32 and bev_height.ndim == 2 and bev_height.shape[1] >= bev_height.shape[0]:
             return self._densify_on_device(maps_2d, np.ascontiguousarray(bev_height))
         instance_list = []
         for item in maps_2d:

@@ -10,6 +10,8 @@ the gathered tensor must equal the one-GPU render bit for bit.
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
 
@@ -108,3 +110,137 @@ def render_sharded(reproject, dataset, gather=True, group=None, mode="auto"):
     if not gather or world == 1:
         return idx[lo:hi], local
     return idx, gather_frames(local, len(idx), group=group)
+
+
+# ---------------------------------------------------------------------------------------------- peer exchange
+def slot_layout(world_size, capacity_records, record_bytes, header_bytes=256):
+    """Byte layout of a rank's mailbox: [2 parities][world sources] slots of header | records.
+    -> (slot_bytes, total_bytes, offset(parity, source))"""
+    slot = -(-(header_bytes + int(capacity_records) * int(record_bytes)) // 256) * 256
+    return slot, 2 * world_size * slot, (lambda parity, source: (parity * world_size + source) * slot)
+
+
+class PeerExchange:
+    """The sparse output of a frame-sharded clip, exchanged between the GPUs of one box through peer memory.
+
+    Every rank owns a mailbox (``cama_peer_alloc``) that all ranks map (CUDA IPC handles travel through
+    ``torch.distributed.all_gather_object``, once).  Per step a rank renders its frame block with the sparse output
+    pointed at its own slot and mirrored into the same slot on every peer (the raster's flushes cross NVLink while it
+    computes), publishes the slot, and expands the slots of all ranks into dense frames.  Nothing on the data path
+    goes through the host or through NCCL.  ``available`` is False when the box has no peer-to-peer path (the caller
+    then falls back to ``render_sharded(gather="sparse")``: NCCL all-gather of the records).
+    """
+
+    def __init__(self, rt, capacity_records, fmt, group=None, devices=None):
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        self.rt, self.group, self.fmt = rt, group, fmt
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > N.MAX_PEERS:
+            raise ValueError(f"at most {N.MAX_PEERS} ranks")
+        self.record_bytes = N.OVERLAY_RECORD_BYTES[fmt]
+        self.capacity = int(capacity_records)
+        self.slot_bytes, self.total_bytes, self.offset = slot_layout(self.world, self.capacity, self.record_bytes, N.PEER_HEADER_BYTES)
+        self.step = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=rt.device)
+        self.count = torch.zeros(4, dtype=torch.int32, device=rt.device)
+        self.base = [None] * self.world             # mailbox of every rank, as mapped into this process
+        self._own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(N.PEER_HANDLE_BYTES)
+        error = None
+        try:
+            N.check(N.lib().cama_peer_alloc(rt.ctx, self.total_bytes, ctypes.byref(self._own), handle))
+        except N.CamaError as exc:                  # (every rank still takes part in the collectives below)
+            error = str(exc)
+        device_index = rt.device.index if devices is None else devices[self.rank]
+        mine = {"handle": bytes(handle.raw), "device": int(device_index), "error": error}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        if all(e["error"] is None for e in everyone):
+            for r, e in enumerate(everyone):
+                if r == self.rank:
+                    self.base[r] = self._own.value
+                    continue
+                ptr = ctypes.c_void_p()
+                code = N.lib().cama_peer_open(rt.ctx, e["device"], e["handle"], ctypes.byref(ptr))
+                if code != N.CAMA_OK:
+                    error = N.lib().cama_last_error().decode("utf-8", "replace")
+                    break
+                self.base[r] = ptr.value
+        else:
+            error = error or "a peer could not allocate its mailbox"
+        verdicts = [None] * self.world
+        dist.all_gather_object(verdicts, error, group=group)
+        self.error = next((v for v in verdicts if v), None)
+        self.available = self.error is None
+        if not self.available:
+            self.close()
+
+    def close(self):
+        from . import _native as N
+        for r, ptr in enumerate(self.base):
+            if ptr is not None and r != self.rank:
+                N.lib().cama_peer_close(self.rt.ctx, ptr)
+        self.base = [None] * self.world
+        if self._own.value:
+            N.lib().cama_peer_free(self.rt.ctx, self._own)
+            self._own = ctypes.c_void_p()
+
+    def slot(self, owner, parity, source):
+        """device pointer (in this process) of the slot of `source`'s records in `owner`'s mailbox"""
+        return self.base[owner] + self.offset(parity, source)
+
+    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, n_frames_total, out, mode="auto", zero_stream=None):
+        """One step: render this rank's block (frames [frame_lo, frame_lo + len(w2c_dev)) of the clip), exchange, expand.
+
+        out          torch uint8 [n_frames_total, C, H, W, 3] on this device: all frames of the clip afterwards
+        zero_stream  optional side torch stream for the zero-fill of `out` (it then overlaps the render, which moves
+                     next to no memory); the expand waits for it
+        Asynchronous; check ``status()`` after synchronising.
+        """
+        import torch
+        from . import _native as N
+        rt = self.rt
+        self.step += 1
+        parity = self.step & 1
+        main = torch.cuda.current_stream()
+        if zero_stream is not None:
+            zero_stream.wait_stream(main)            # (the previous step's expand has finished writing `out`)
+            with torch.cuda.stream(zero_stream):
+                out.zero_()
+        else:
+            out.zero_()
+        hdr = N.PEER_HEADER_BYTES
+        own_slot = self.slot(self.rank, parity, self.rank)
+        overlay = {"records_ptr": own_slot + hdr, "count_ptr": self.count.data_ptr(), "capacity": self.capacity, "fmt": self.fmt,
+                   "mirrors": [self.slot(r, parity, self.rank) + hdr for r in range(self.world) if r != self.rank],
+                   "image_base": frame_lo * renderer.n_cams}
+        if int(w2c_dev.shape[0]) > 0:
+            renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
+        else:
+            self.count.zero_()
+        headers = (ctypes.c_void_p * self.world)(*[self.slot(r, parity, self.rank) for r in range(self.world)])
+        N.check(N.lib().cama_peer_publish(rt.ctx, self.count.data_ptr(), self.step, headers, self.world, rt.stream()))
+        if zero_stream is not None:
+            main.wait_stream(zero_stream)
+        slots = (ctypes.c_void_p * self.world)(*[self.slot(self.rank, parity, r) for r in range(self.world)])
+        pal_dev = scratch = None
+        if self.fmt == N.OVERLAY_PALETTE:
+            pal_dev = self._palette_dev(res)
+            scratch = rt.scratch("palette32", 1024)
+        N.check(N.lib().cama_peer_expand(rt.ctx, slots, self.world, self.step, self.capacity, self.fmt, rt.ptr(pal_dev), rt.ptr(scratch),
+                                         rt.ptr(out), int(n_frames_total), renderer.n_cams, renderer.height, renderer.width, 0,
+                                         self.status.data_ptr(), rt.stream()))
+        return out
+
+    def _palette_dev(self, res):
+        cached = getattr(res, "_palette_dev", None)
+        if cached is None:
+            cached = res._palette_dev = self.rt.to_device(np.ascontiguousarray(res.palette, dtype=np.uint8))
+        return cached
+
+    def status_code(self):
+        """0 ok, 1 a peer's step timed out, 2 a slot overflowed (synchronises)."""
+        return int(self.status.item())

@@ -17,8 +17,10 @@
  *     "host" pointers are ordinary host memory, read synchronously during the call.
  *   - every device call takes the cudaStream_t to enqueue on as a void* (0 = legacy
  *     default stream) and returns after enqueueing; no call synchronises unless its
- *     comment says so.  The context holds no mutable state besides a launch counter,
- *     so calls on different streams are independent.
+ *     comment says so.  Calls on different streams are independent as long as they use different
+ *     workspaces; the context itself carries a launch counter, the phase-profiling events
+ *     (cama_ctx_profile_*: enable/read from one thread at a time) and the helper streams of the
+ *     frame-group pipeline, which every cama_clip_render call orders behind its own stream.
  *   - images are uint8 [H,W,3] BGR, row-major, as in the reference (cv2 convention).
  *   - point arrays are row-major [n,3] (x,y,z) or [n,2] (v,u) = (row,col), like the
  *     reference's "points" arrays; ragged instance lists are flat arrays plus
@@ -37,9 +39,13 @@
 extern "C" {
 #endif
 
-#define CAMA_ABI_VERSION 2
+#define CAMA_ABI_VERSION 3
 #define CAMA_MAX_CAMERAS 8
 #define CAMA_TILE_VERTICES 256
+#define CAMA_WARP_VERTICES 32
+#define CAMA_MAX_PEERS 8          /* GPUs of one box that exchange the sparse output (cama_peer_*) */
+#define CAMA_PEER_HEADER_BYTES 256
+#define CAMA_PEER_HANDLE_BYTES 64
 
 typedef enum cama_status {
     CAMA_OK = 0,
@@ -213,6 +219,8 @@ typedef struct cama_clip_desc {
      * half-extent {cx,cy,cz,ex,ey,ez} of an axis-aligned box containing them.  A (tile, frame) whose
      * transformed box misses the crop box is skipped as a whole; results are unchanged. */
     const double *tile_bounds;      /* device float64 [ceil(n_vertices / CAMA_TILE_VERTICES), 6] or NULL */
+    const double *warp_bounds;      /* the same for every CAMA_WARP_VERTICES consecutive vertices (the unit one geometry warp
+                                     * works on): device float64 [ceil(n_vertices / CAMA_WARP_VERTICES), 6] or NULL */
     void *overlay_records;          /* device [overlay_capacity] records of overlay_format, or NULL */
     uint32_t *overlay_count;        /* device [1]: records appended (may exceed the capacity: the excess was dropped) */
     int64_t overlay_capacity;
@@ -220,11 +228,20 @@ typedef struct cama_clip_desc {
     int32_t pipeline_frames;        /* BINNED: frames per group of the frame-group pipeline (geometry of group g+1 under the raster of
                                      * group g, useful for clips of hundreds of frames); 0 = library default, < 0 = off */
     const uint8_t *instance_palette; /* device uint8 [n_instances]: palette entry (1..255) of every instance, or NULL */
+    /* Frame-sharded clips (cama_peer_* below): every record appended to overlay_records is also stored, at the same
+     * position, into overlay_mirrors[0 .. overlay_n_mirrors) — record arrays in the memory of peer GPUs, written over
+     * NVLink while the raster runs; chunk indices count from image overlay_image_base (this call's first
+     * (frame, camera) image inside the assembled clip: frame_lo * n_cams). */
+    void *overlay_mirrors[CAMA_MAX_PEERS];
+    int32_t overlay_n_mirrors;
+    int32_t reserved0;
+    int64_t overlay_image_base;
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
     int64_t records_total;          /* centre records emitted (incl. band-halo duplicates) */
-    int64_t records_max_per_frame;  /* largest per-frame count: the capacity a rerun needs */
+    int64_t records_per_frame_needed; /* ceil(records_total / n_frames): the record_capacity (per frame; the pool is shared by
+                                     * all frames of a call) a rerun needs after an overflow */
     int64_t record_capacity;        /* per-frame capacity this run used */
     int32_t overflow;               /* != 0: some frame exceeded the capacity, frames are incomplete */
     int32_t mode;                   /* mode actually used (CAMA_CLIP_PLANE / CAMA_CLIP_BINNED) */
@@ -285,6 +302,42 @@ int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, int64_t n, 
 int cama_overlay_expand(cama_ctx *ctx, const void *records, int64_t n, int format, const uint8_t *palette_bgr,
                         void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams, int height, int width,
                         int zero_first, void *stream);
+
+/* ---- frame-sharded clips: the sparse output exchanged between the GPUs of one box (BASELINE.json configs[3]) ------
+ *
+ * The frames of a clip are independent units (cama/dataset.py:88-106), so a site is split into contiguous frame blocks,
+ * one per GPU (cama_b200/shard.py).  To end up with EVERY frame on EVERY GPU the ranks do not all-gather the dense uint8
+ * frames (NVLink-bound: 3 GB per site) but the lit 8-pixel chunks: cama_clip_render's sparse output is written into a
+ * slot of the rank's own mailbox and mirrored, flush by flush, into the same slot of every peer's mailbox
+ * (overlay_mirrors: peer stores over NVLink while the raster runs — there is no separate collective);
+ * cama_peer_publish then releases the slot, and cama_peer_expand on every rank waits for all slots of the step and
+ * rebuilds the dense frames at HBM speed.  No host round trip, no NCCL call on the data path.
+ *
+ * A mailbox is device memory the LIBRARY allocates (the one exception to "the caller owns all buffers": it has to come
+ * from cudaMalloc to be exportable through CUDA IPC), laid out by the caller as [2 parities][world] slots of
+ * cama_peer_slot_bytes(); a slot = CAMA_PEER_HEADER_BYTES header {uint32 count, uint32 step, ...} | records.  Step s uses
+ * parity s & 1; steps are numbered from 1 and never reused. */
+int cama_peer_slot_bytes(int64_t capacity_records, int record_bytes, size_t *bytes);
+/* cudaMalloc + zero-fill of `bytes` on the context's device; ipc_handle: CAMA_PEER_HANDLE_BYTES bytes out (host), to be sent
+ * to the peer processes.  Synchronises. */
+int cama_peer_alloc(cama_ctx *ctx, size_t bytes, void **dev_ptr, void *ipc_handle);
+int cama_peer_free(cama_ctx *ctx, void *dev_ptr);
+/* Maps the mailbox another process allocated on device `peer_device` (same box) into this process; enables peer access
+ * from the context's device.  CAMA_E_UNSUPPORTED when there is no peer-to-peer path between the two devices. */
+int cama_peer_open(cama_ctx *ctx, int peer_device, const void *ipc_handle, void **dev_ptr);
+int cama_peer_close(cama_ctx *ctx, void *dev_ptr);
+/* After cama_clip_render on `stream`: writes *overlay_count (device) and then, with release semantics at system scope,
+ * `step` into the n slot headers (device pointers, own and peers'; host array). */
+int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t step, void *const *slot_headers, int n, void *stream);
+/* slots: host array of `world` device pointers, the slots of this rank's own mailbox that hold the records of rank
+ * 0..world-1 for `step`.  Waits on the device until every slot carries `step` (at most timeout_ms, <= 0: 2000), then
+ * writes the 8 pixels of every record into frames uint8 [n_frames,n_cams,H,W,3] (device, zero-filled by the caller).
+ * status: device int32 [1], caller zero-fills once; set to 1 when a peer's step did not arrive in time (nothing is
+ * written then), 2 when a slot held more records than capacity_records (frames incomplete).  palette_*: as
+ * cama_overlay_expand. */
+int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, uint32_t step, int64_t capacity_records, int format,
+                     const uint8_t *palette_bgr, void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams,
+                     int height, int width, int timeout_ms, int32_t *status, void *stream);
 
 /* ---- LiDAR aggregation (BASELINE.json configs[4]) -------------------------------- */
 
