@@ -6,9 +6,13 @@
 A step = one pass of the hot path over one clip: every frame x camera x dense map vertex
 transformed, cropped, projected, masked and stamped into the uint8 [F,C,540,960,3] frames
 (reference loop: cama/dataset.py:78-126).  Workload at N=1 = BASELINE.json configs[1]
-(40 frames x 6 cameras, 200 polylines, 0.1 m densify => ~96 k vertices); at N>1 every rank renders
-its own such clip (the scenes of a site, seeds 0..N-1), i.e. weak scaling, no data-path collective;
-`allgather` additionally reports the NCCL all-gather of the rendered frames north_star asks for.
+(40 frames x 6 cameras, 200 polylines, 0.1 m densify => ~96 k vertices).  At N>1 the workload is
+BASELINE.json configs[3]: the config-3 site (320 frames x 6 cameras, ~767 k vertices) SHARDED BY FRAME over
+the N GPUs (strong scaling), and a step ends with every frame of the site assembled in the HBM of every
+rank — the assembly is inside the timed region.  The ranks exchange the lit 8-pixel chunks through peer
+memory while the raster runs (cama_b200/shard.py::PeerExchange, csrc/peer.cu) instead of all-gathering
+the dense frames; the literal NCCL all-gather of the uint8 frames is timed beside it (`dense_allgather`),
+as are the compute-only figure and one GPU rendering the same site alone.
 
 One JSON line on rank 0:
   value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM; the K steps are dealt
@@ -48,7 +52,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config2_cama", "config3"])
+    ap.add_argument("--workload", default=None, choices=["config2", "config2_cama", "config3"],
+                    help="default: config2 on one GPU, config3 (the site, sharded by frame) on several")
     ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
@@ -513,10 +518,219 @@ def run_b200(args):
     tmp.cleanup()
 
 
+# ---------------------------------------------------------------------------------------------- GPU arm, N > 1
+def run_b200_sharded(args):
+    """BASELINE.json configs[3]: one site, its frames sharded over the ranks, every frame assembled on every rank."""
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    tmp = tempfile.TemporaryDirectory()
+    clip, dataset = make_clip(args.workload, tmp.name, 0)              # the same site on every rank (seeded)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from cama_b200 import shard, synth
+    from cama_b200 import _native as N
+    from cama_b200.batched import Reproject
+
+    rp = Reproject(synth.CAMA_CONFIGS, clip, device=local_rank)
+    rt, r = rp.rt, rp.renderer
+    res = rp.resident(dataset)
+    idx, w2c_host = rp.frame_poses(dataset)
+    F, C = len(idx), r.n_cams
+    cam_frames = F * C
+    lo, hi = shard.frame_block(F, rank, world)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=rt.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warm):
+        """-> ms per step: events on the launching stream, barrier + synchronize on both sides, max over ranks"""
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    asm = shard.SiteAssembler(rp, dataset, mode=args.mode)             # collective: sizes the slots, maps the peers' mailboxes
+    frames_all = torch.empty((F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    local = torch.empty((hi - lo, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    w2c_block = asm.w2c_dev
+    r.render(res, w2c_block, out=local, mode=args.mode, check=True)    # sizing pass of the dense block render
+
+    def step_assembled():
+        if asm.available:
+            asm.step(out=frames_all)
+        else:                                                          # no peer-to-peer path: NCCL all-gather of the records
+            records, n, fmt = r.render_overlay(res, w2c_block, mode=args.mode)
+            everyone, counts = shard.gather_records(records, n)
+            for peer in range(world):
+                p_lo, p_hi = shard.frame_block(F, peer, world)
+                if p_hi > p_lo:
+                    r.expand_overlay(everyone[peer], counts[peer], fmt, res.palette, p_hi - p_lo, out=frames_all[p_lo:p_hi])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_end = time.perf_counter() + args.ramp_seconds
+    while time.perf_counter() < t_end:
+        r.render(res, w2c_block, out=local, mode=args.mode, check=False)
+        torch.cuda.synchronize()
+    warm = max(args.warmup, 3)
+
+    # ---- the headline: K steps, each = render of the rank's block + exchange + all frames rebuilt on every rank
+    launches0 = rt.launches()
+    sampler.load(True)
+    ms_step = timed(step_assembled, args.steps, warm)
+    launches = (rt.launches() - launches0) // max(1, args.steps + warm) * args.steps
+    status = asm.exchange.status_code() if asm.available else 0
+    # zero-fill alone (the dominant kernel of the assembly: every frame byte written once), on the launching stream
+    ms_zero = timed(lambda: frames_all.zero_(), max(5, args.steps // 5), 2)
+    step_assembled()
+    torch.cuda.synchronize()
+    # ---- compute only: every rank renders its block densely, nothing is exchanged
+    ms_compute = timed(lambda: r.render(res, w2c_block, out=local, mode=args.mode, check=False), args.steps, warm)
+    # ---- north_star's literal collective: dense render + one NCCL all-gather of the uint8 frames
+    dense_steps = max(3, args.steps // 10)
+    gathered = torch.empty((world * shard.block_size(F, world), C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    padded = local if hi - lo == shard.block_size(F, world) else torch.zeros((shard.block_size(F, world), C, H, W, 3), dtype=torch.uint8, device=rt.device)
+
+    def step_dense():
+        r.render(res, w2c_block, out=padded[:hi - lo], mode=args.mode, check=False)
+        dist.all_gather_into_tensor(gathered, padded)
+
+    ms_dense = timed(step_dense, dense_steps, 2)
+    sampler.load(False)
+    dense_equal = bool(torch.equal(gathered[:F], frames_all))
+    del gathered
+    # ---- one GPU, same workload: every rank renders the whole site alone (rank 0's time is reported)
+    w2c_all = torch.from_numpy(w2c_host).to(rt.device)
+    whole = torch.empty((F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    r.render(res, w2c_all, out=whole, mode=args.mode, check=True)
+    single_steps = max(3, args.steps // 5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(single_steps):
+        r.render(res, w2c_all, out=whole, mode=args.mode, check=False)
+    e1.record(stream)
+    barrier()
+    ms_single_gpu = e0.elapsed_time(e1) / single_steps
+    # ---- verification inside the bench: the assembled frames of EVERY rank equal the one-GPU render of the site
+    equal = torch.tensor([int(torch.equal(frames_all, whole)), int(dense_equal)], dtype=torch.int32, device=rt.device)
+    dist.all_reduce(equal, op=dist.ReduceOp.MIN)
+    checksum = int(frames_all[:, :, ::9, ::9].sum().item())
+    del whole
+
+    # ---- end to end through the public call, frames in HOST memory: every rank takes its frame block through
+    # Reproject.__call__ (host pose seek + float32 inverse, H2D of the poses, sparse render, records D2H, host draw)
+    def e2e_loop(steps):
+        n_warm, t_warm = 0, time.perf_counter()
+        while n_warm < warm or time.perf_counter() - t_warm < 0.2:
+            rp(dataset, mode=args.mode, frame_range=(lo, hi))
+            n_warm += 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, host_frames = rp(dataset, mode=args.mode, frame_range=(lo, hi))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return dt, int(host_frames[:, :, ::9, ::9].sum()), dict(rp.last_transfer)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_s, e2e_sum, transfer = e2e_loop(e2e_steps)
+    e2e_s = max_over_ranks(e2e_s)
+    sums = torch.tensor([e2e_sum], dtype=torch.int64, device=rt.device)
+    dist.all_reduce(sums)
+    clocks = sampler.stop()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        frame_bytes = cam_frames * H * W * 3                          # written once on EVERY rank
+        vertex_bytes = (hi - lo) * 12 * res.n_vertices
+        records = int(transfer["records"])
+        line = {
+            "metric": METRIC, "value": cam_frames / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload) + f"; frames sharded over {world} GPUs in contiguous blocks (BASELINE.json configs[3]), "
+                                   "all frames assembled on every GPU inside the timed region",
+                       "frames": F, "cams": C, "cam_frames_per_step": cam_frames, "frames_per_gpu": hi - lo, "vertices": res.n_vertices,
+                       "instances": res.n_instances,
+                       "assembly": ("peer memory: the raster mirrors its lit-chunk records into every peer's mailbox over NVLink while it runs, "
+                                    "cama_peer_publish / cama_peer_expand (no NCCL call and no host round trip in the step)") if asm.available
+                                   else f"NCCL all-gather of the lit-chunk records + cama_overlay_expand (no peer-to-peer path: {asm.exchange.error})",
+                       "l2": f"no flush needed: every step writes {frame_bytes / 1e9:.2f} GB of frames per GPU (> 126 MB L2)",
+                       "background": "blank (black) frames, as in the reference CPU timing"},
+            "verified": {"assembled_equals_single_gpu_render_on_every_rank": bool(equal[0].item()),
+                         "dense_allgather_equals_assembled_on_every_rank": bool(equal[1].item()),
+                         "peer_status": status, "checksum": checksum},
+            "single_gpu_same_workload": {"value": cam_frames / (ms_single_gpu * 1e-3), "unit": UNIT, "ms_per_step": ms_single_gpu,
+                                         "note": "rank 0 renders all frames of the site alone, frames left in its HBM (what the assembled result is compared with)"},
+            "compute_only": {"value": cam_frames / (ms_compute * 1e-3), "unit": UNIT, "ms_per_step": ms_compute,
+                             "note": "every rank renders its frame block densely, nothing exchanged"},
+            "dense_allgather": {"value": cam_frames / (ms_dense * 1e-3), "unit": UNIT, "ms_per_step": ms_dense,
+                                "bytes_received_per_gpu": int(frame_bytes * (world - 1) / world),
+                                "nvlink_gbs_in": frame_bytes * (world - 1) / world / (ms_dense * 1e-3) / 1e9,
+                                "note": "dense render + ONE NCCL all_gather_into_tensor of the uint8 frames (north_star's literal collective): NVLink-bound"},
+            "exchange": {"records_per_gpu": records, "bytes_sent_per_gpu": records * 12 * (world - 1), "bytes_received_per_gpu": None},
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "e2e": {"value": cam_frames * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(w2c_host[lo:hi].nbytes) * world,
+                    "d2h_bytes_per_step": (int(transfer["d2h_bytes"]) + 48) * world, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "call": "every rank: cama_b200.batched.Reproject.__call__(dataset, frame_range=its block): host pose seek + float32 inverse, "
+                            "H2D of the poses from pinned memory, cama_clip_render (sparse output), D2H of the lit-chunk records, "
+                            "cama_overlay_apply_host into the rank's host frames; the site's frames end up in host memory once, split over the ranks",
+                    "checksum_all_ranks": int(sums.item()), "host_draw_threads_per_rank": int(rp.host_threads),
+                    "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "zero-fill of the assembled frames (cudaMemset via torch) + peer_expand_kernel: every frame byte of the site written once per rank",
+                         "achieved": frame_bytes / (ms_zero * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": frame_bytes / (ms_zero * 1e-3) / 1e9 / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "traffic": None, "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": ms_zero,
+                         "launch_ms_source": "CUDA events on the launching stream around the zero-fill alone, barrier on both sides, max over ranks",
+                         "whole_step": {"algorithmic_bytes": int(frame_bytes + vertex_bytes),
+                                        "achieved": (frame_bytes + vertex_bytes) / (ms_step * 1e-3) / 1e9,
+                                        "frac": (frame_bytes + vertex_bytes) / (ms_step * 1e-3) / 1e9 / peak,
+                                        "note": "per rank: all frames of the site written once + the rank's share of the vertex reads, over the whole step"}},
+        }
+        line["exchange"]["bytes_received_per_gpu"] = line["exchange"]["bytes_sent_per_gpu"]
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    if asm.available:
+        asm.exchange.close()
+    dist.destroy_process_group()
+    tmp.cleanup()
+
+
 def main():
     args = parse_args()
+    _, _, world = dist_env()
+    if args.workload is None:
+        args.workload = "config2" if max(world, args.gpus) == 1 else "config3"
     if args.impl == "reference":
         run_reference(args)
+    elif world > 1:
+        run_b200_sharded(args)
     else:
         run_b200(args)
 

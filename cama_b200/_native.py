@@ -20,6 +20,7 @@ WARP_VERTICES = 32
 MAX_PEERS = 8
 PEER_HEADER_BYTES = 256
 PEER_HANDLE_BYTES = 64
+CAMERA_TABLE_BYTES = 16 + 256 * 256
 OVERLAY_BGR, OVERLAY_PALETTE = 0, 1
 OVERLAY_RECORD_BYTES = {OVERLAY_BGR: 32, OVERLAY_PALETTE: 12}
 OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
@@ -54,6 +55,7 @@ class ClipDesc(Structure):
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
+        ("camera_table", c_void_p),
     ]
 
 
@@ -99,6 +101,7 @@ SIGNATURES = {
     "cama_densify_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int] + [ctypes.c_float] * 5
                           + [c_void_p, c_void_p]),
     "cama_remap_bilinear": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "cama_camera_table_build": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), c_int, POINTER(c_double), c_int, c_int, c_void_p, c_void_p]),
     "cama_clip_workspace_bytes": (c_int, [POINTER(ClipDesc), POINTER(c_size_t)]),
     "cama_clip_render": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_size_t, c_void_p]),
     "cama_clip_stats_read": (c_int, [c_void_p, POINTER(ClipDesc), c_void_p, c_void_p, POINTER(ClipStats)]),

@@ -24,6 +24,7 @@ from .dataset import ClipManager
 from .reproject import render_bgr_of_class
 from .runtime import CROP_KEYS, get_runtime
 
+_PINNED = False           # this process has taken its slice of the cores (Reproject._pin_host_threads)
 _MODES = {"auto": N.CLIP_AUTO, "plane": N.CLIP_PLANE, "binned": N.CLIP_BINNED}
 
 
@@ -103,6 +104,20 @@ class ClipRenderer:
         self.capacity = {}            # (resident id, n_frames) -> records per frame that were enough
         self.overlay_capacity = {}    # (resident id, n_frames) -> overlay records that were enough
         self.last_stats = None
+        self._camera_table = None     # cama_camera_table_build output for this rig (built on first use)
+
+    def camera_table(self):
+        """Device table of the cameras that can see each cell of the crop box (cama_camera_table_build); static per rig."""
+        if self._camera_table is None:
+            import torch
+            rt = self.rt
+            table = torch.zeros(N.CAMERA_TABLE_BYTES, dtype=torch.uint8, device=rt.device)
+            box = (ctypes.c_double * 6)(*self.crop_box)
+            N.check(N.lib().cama_camera_table_build(rt.ctx, N.dptr(self.chassis2cam), N.dptr(self.intrinsics), self.n_cams, box,
+                                                    self.height, self.width, rt.ptr(table), rt.stream()))
+            rt.synchronize()              # (built once; clips on other streams may be the first to read it)
+            self._camera_table = table
+        return self._camera_table
 
     def resident(self, instances, device_vertices=None):
         return _Resident(self.rt, instances, device_vertices)
@@ -131,6 +146,7 @@ class ClipRenderer:
         d.pipeline_frames = int(self.pipeline_frames)
         d.tile_bounds = res.tile_bounds.data_ptr() if getattr(res, "tile_bounds", None) is not None else None
         d.warp_bounds = res.warp_bounds.data_ptr() if getattr(res, "warp_bounds", None) is not None else None
+        d.camera_table = self.camera_table().data_ptr()
         if overlay is not None:
             if isinstance(overlay, dict):            # raw pointers (a mailbox slot of shard.PeerExchange)
                 d.overlay_records, d.overlay_count = overlay["records_ptr"], overlay["count_ptr"]
@@ -319,7 +335,13 @@ class ClipRenderer:
 class Reproject:
     """Batched drop-in for the frame loop: ``Reproject(configs, clip_path)(dataset)``."""
 
-    def __init__(self, configs, clip_path=None, device=None, clip_manager=None, densify="device"):
+    def __init__(self, configs, clip_path=None, device=None, clip_manager=None, densify="device", pin_host_threads=None):
+        """``pin_host_threads``: give this process — and with it the library's host-draw workers, which are created
+        later and inherit the mask — its own share of the cores: rank r of the n processes torchrun started on the
+        box takes the r-th of n contiguous slices of the CPUs the process may run on.  Default (None): only under
+        torchrun (LOCAL_WORLD_SIZE > 1), where the ranks' draw threads otherwise migrate over each other's cores and
+        a chunk-claiming loop waits for whichever thread was descheduled; CAMA_B200_PIN=0 turns it off."""
+        pinned = self._pin_host_threads(pin_host_threads)
         self.cm = clip_manager if clip_manager is not None else ClipManager(configs, clip_path, device=device, progress=False, densify=densify)
         self.configs = configs
         cams = self.cm.cm_list
@@ -347,8 +369,27 @@ class Reproject:
             cores = len(os.sched_getaffinity(0))
         except AttributeError:
             cores = os.cpu_count() or 1
-        self.host_threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self.host_threads = max(1, cores if pinned else cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self.last_transfer = None
+
+    @staticmethod
+    def _pin_host_threads(pin):
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        if pin is None:
+            pin = local_world > 1 and os.environ.get("CAMA_B200_PIN", "1") != "0"
+        global _PINNED
+        if _PINNED:
+            return True
+        if not pin or local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+            return False
+        cpus = sorted(os.sched_getaffinity(0))
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        per = len(cpus) // local_world
+        if per < 1:                                    # fewer cores than ranks: nothing to partition
+            return False
+        os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+        _PINNED = True
+        return True
 
     def resident(self, dataset):
         if dataset not in self._resident:
@@ -418,8 +459,11 @@ class Reproject:
             return None
         return np.array([order.index(name) for name in self.camera_names], dtype=np.int32)
 
-    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse", layout="frames", copy=False):
+    def __call__(self, dataset, backgrounds=None, mode="auto", transfer="sparse", layout="frames", copy=False, frame_range=None):
         """-> (image_idx list, uint8 numpy [F',C,H,W,3] in host memory).
+
+        ``frame_range=(lo, hi)`` renders only that block of the clip's renderable frames (positions in yield order) —
+        what one rank of a frame-sharded clip does (cama_b200/shard.py::frame_block).
 
         **Ownership of the returned array.**  With ``backgrounds`` the result IS that array (drawn on in place, as the
         reference draws on the camera images).  Without, the result is a buffer this object owns and REUSES: it stays
@@ -449,7 +493,7 @@ class Reproject:
             blank_job = self._helper().submit(self._apply_records, self._host_frames, self._host_tiles, prev.data_ptr(), n_prev, prev_fmt,
                                               prev_palette, N.OVERLAY_BLANK_CHUNKS)
         try:
-            idx, frames = self._call_sparse(dataset, backgrounds, mode, transfer, layout, blank_job)
+            idx, frames = self._call_sparse(dataset, backgrounds, mode, transfer, layout, blank_job, frame_range)
             if copy and backgrounds is None:
                 frames = frames.copy()
             return idx, frames
@@ -474,9 +518,12 @@ class Reproject:
         N.check(N.lib().cama_overlay_apply_host(rec_ptr, count, rec_fmt, None if palette is None else palette.ctypes.data,
                                                 ctypes.byref(target), op, self.host_threads))
 
-    def _call_sparse(self, dataset, backgrounds, mode, transfer, layout, blank_job):
+    def _call_sparse(self, dataset, backgrounds, mode, transfer, layout, blank_job, frame_range=None):
         import torch
         idx, w2c = self.frame_poses(dataset)
+        if frame_range is not None:
+            lo, hi = frame_range
+            idx, w2c = idx[lo:hi], w2c[lo:hi]
         tiles = None
         if layout == "mosaic":
             tiles = self.mosaic_tiles()

@@ -63,7 +63,10 @@ struct ClipArgs {
     const unsigned *n_live;
     const double *warp_bounds;         // [ceil(n_vertices / 32),6] centre + half-extent of every warp's 32 vertices, or nullptr
     unsigned *geo_counter;             // [1] dynamic claims of the geometry warps (cleared by prep)
-    const unsigned char *cam_table;    // [tab_ny][tab_nx] cameras that can see a chassis-frame cell (camera_table_build), or nullptr
+    const unsigned char *cam_table;    // 16-byte header {signature} | [tab_ny][tab_nx] cameras that can see a chassis-frame cell (cama_camera_table_build), or nullptr
+    unsigned long long tab_signature;  // of the cameras / crop box / image size of THIS call: a table built for others is ignored
+    int unit_frames;                   // frames per warp unit of the geometry kernel: 1, 2, 4 or 8
+    unsigned static_units;             // warp units dealt round-robin before the warps start claiming dynamically
     double tab_x0, tab_y0;
     float tab_inv_sx, tab_inv_sy;
     int tab_nx, tab_ny;
@@ -133,27 +136,29 @@ __device__ bool camera_sees_cell(const CamBlock &cams, int c, int width, int hei
     return !out;
 }
 
+// 8 lanes per cell, one camera each; the lane of camera 0 writes the cell's mask.  The table depends on the camera rig,
+// the crop box and the image size only: built once per rig (cama_camera_table_build), not per clip.
+__global__ void __launch_bounds__(256) camera_table_kernel(const __grid_constant__ CamBlock cams, int n_cams, int width, int height, const CamTable tab,
+                                                          unsigned long long signature, unsigned char *__restrict__ table) {
+    static_assert(CAMA_MAX_CAMERAS == 8, "camera table: one byte per cell, 8 lanes per cell");
+    const int n_cells = tab.nx * tab.ny;
+    const int k = blockIdx.x * 256 + threadIdx.x, cell = k >> 3, c = k & 7;
+    const bool sees = cell < n_cells && c < n_cams && camera_sees_cell(cams, c, width, height, tab, cell);
+    const unsigned votes = __ballot_sync(kFull, sees);
+    if (c == 0 && cell < n_cells) table[CAMA_CAMERA_TABLE_HEADER + cell] = (unsigned char)((votes >> (threadIdx.x & 24)) & 0xffu);
+    if (k == 0) *reinterpret_cast<unsigned long long *>(table) = signature;
+}
+
 // ------------------------------------------------------------------------------------------------ prep
 // (also clears the per-call counters, so that a clip costs kernel launches only: zero_words 32-bit words at `zero`,
 // the statistics block, the sparse-output counter)
 __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
                             const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
-                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette,
-                            const __grid_constant__ CamBlock cams, int n_cams, int width, int height, const CamTable tab, unsigned char *__restrict__ cam_table) {
+                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                    // (the previous clip's raster still reads the counters cleared here)
     pdl_trigger();
-    if (cam_table) {                               // 8 lanes per cell, one camera each; the lane of camera 0 writes the cell's mask
-        static_assert(CAMA_MAX_CAMERAS == 8, "camera table: one byte per cell, 8 lanes per cell");
-        const int n_cells = tab.nx * tab.ny;
-        for (int base = (i & ~31); base < n_cells * 8; base += gridDim.x * blockDim.x) {       // (warp-uniform bounds: the ballot needs every lane)
-            const int k = base + (threadIdx.x & 31), cell = k >> 3, c = k & 7;
-            const bool sees = cell < n_cells && c < n_cams && camera_sees_cell(cams, c, width, height, tab, cell);
-            const unsigned votes = __ballot_sync(kFull, sees);
-            if (c == 0 && cell < n_cells) cam_table[cell] = (unsigned char)((votes >> (threadIdx.x & 24)) & 0xffu);
-        }
-    }
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
     if (i < stats_words) stats[i] = 0u;
     if (i == 0 && overlay_count) *overlay_count = 0u;
@@ -393,20 +398,35 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
     if (leader) worklist[base + __popc(live & ((1u << lane) - 1u))] = ((unsigned long long)unit << 8) | mask;
 }
 
-// Work unit of a WARP = (32 consecutive vertices, chunk of 8 frames).  The kernel is a persistent grid of
+// Work unit of a WARP = (32 consecutive vertices, kUnitFrames consecutive frames).  The kernel is a persistent grid of
 // independent warps: every warp claims its next unit from a global counter (one returning atomic per unit,
-// issued a whole unit ahead of its use), keeps the 8 poses of the unit in its own slice of shared memory, and
+// issued a whole unit ahead of its use), keeps the poses of the unit in its own slice of shared memory, and
 // never meets a block-level barrier — so a warp whose vertices all fall outside the crop box moves on at once,
-// and no CTA slot idles behind its slowest warp (with one 256-vertex unit per CTA the achieved occupancy was a
-// third: the dead warps of a unit had left, the slot had not).  Per unit: the warp's own bounding box
-// (`warp_bounds`) decides which of the 8 frames it has to look at (lane = frame); a thread keeps its vertex in
-// registers; lanes hold consecutive vertices, so crop survival — and with it the camera tail — is almost
-// warp-uniform (polylines are spatially coherent).  Cameras: the table of camera_table_build gives every
-// surviving lane the cameras that can see its cell; the warp runs the OR of them (typically 1-2 of 6).
+// and no CTA slot idles behind its slowest warp.  Per unit: the warp's own bounding box (`warp_bounds`) decides
+// which of the unit's frames it has to look at (lane = frame); a thread keeps its vertex in registers; lanes hold
+// consecutive vertices, so crop survival — and with it the camera tail — is almost warp-uniform (polylines are
+// spatially coherent).  Cameras: the table of cama_camera_table_build gives every surviving lane the cameras that
+// can see its cell; the warp runs the OR of them (typically 1-2 of 6), in a ROLLED loop over the set bits: with the
+// loop unrolled six times the kernel was 52 KB of code and a quarter of the stall samples were instruction fetches
+// (independent warps are all over the code).
 // With a work list (sites: geometry_cull_kernel has culled (256-vertex tile, 8 frames) units) entry e covers the
-// eight warp units 8e .. 8e+7.
-// NCAMS > 0 fixes the camera count at compile time: the camera loop unrolls (0 = any count up to 8).
-template <int LAYOUT, bool BINNED, bool DEBUG, int NCAMS, bool PINHOLE>
+// 8 * kGeoFrames / kUnitFrames warp units of its tile and frames.
+// Frames per unit (a.unit_frames, a power of two <= 8): 4 for ordinary clips (shorter units balance better: 53.8 us
+// against 57.9 with 8 on config 2), 8 behind a work list (sites: most warp units die in the bounds test, and the
+// per-unit overhead — claim, poses, bounds — is what counts: 504 us against 651 with 4 on config 3).
+// Claims: the first a.static_units units are dealt round-robin (no atomic), the rest dynamically — the claims only
+// matter for the tail, and 30 k returning atomics on one address were 18 % of the stall samples.
+#ifndef CAMA_GEO_UNIT_FRAMES
+#define CAMA_GEO_UNIT_FRAMES 4
+#endif
+#ifndef CAMA_GEO_UNIT_FRAMES_SITE
+#define CAMA_GEO_UNIT_FRAMES_SITE 8
+#endif
+#ifndef CAMA_GEO_STATIC_PCT
+#define CAMA_GEO_STATIC_PCT 70
+#endif
+
+template <int LAYOUT, bool BINNED, bool DEBUG, bool PINHOLE>
 __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kernel(const ClipArgs a, const __grid_constant__ CamBlock cams) {
     __shared__ double sT_all[kGeoThreads / 32][kGeoFrames][12];
     __shared__ GeoStage stages[kGeoThreads / 32];
@@ -414,46 +434,60 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
     const int tid = threadIdx.x, lane = tid & 31;
     GeoStage &stage = stages[tid >> 5];
     double (*sT)[12] = sT_all[tid >> 5];
-    const long long n_tiles = (a.n_vertices + 31) / 32;                     // warp tiles
-    const int n_chunks = (a.n_frames + kGeoFrames - 1) / kGeoFrames;
+    const unsigned n_tiles = (unsigned)((a.n_vertices + 31) / 32);                          // warp tiles
+    const unsigned n_chunks8 = (unsigned)((a.n_frames + kGeoFrames - 1) / kGeoFrames);
+    const int kUnitFrames = a.unit_frames;                                                    // (runtime: 1, 2, 4 or 8)
+    const unsigned kUnitSplit = (unsigned)(kGeoFrames / kUnitFrames);
+    const unsigned n_chunks = (unsigned)((a.n_frames + kUnitFrames - 1) / kUnitFrames);
     const bool want_exact = DEBUG && a.vu_dense != nullptr;
     if (BINNED && lane == 0) stage.count = 0;
     __syncwarp();
     pdl_wait();
     pdl_trigger();
-    const long long n_work = a.worklist ? (long long)*a.n_live * 8 : n_tiles * n_chunks;
-    const long long first_dynamic = (long long)gridDim.x * kWarps;           // units [0, first_dynamic) are dealt statically
-    long long w = (long long)blockIdx.x * kWarps + (tid >> 5);
+    const unsigned n_work = a.worklist ? *a.n_live * (8u * kUnitSplit) : n_tiles * n_chunks;   // (< 2^32: checked by the host)
+    const unsigned n_warps = gridDim.x * kWarps;
+    const unsigned first_dynamic = min(a.static_units, n_work);                              // units [0, first_dynamic) are dealt round-robin
+    const bool use_table = a.cam_table != nullptr && *reinterpret_cast<const unsigned long long *>(a.cam_table) == a.tab_signature;
+    const unsigned char *table = a.cam_table + CAMA_CAMERA_TABLE_HEADER;
+    const unsigned all_cams = (1u << a.n_cams) - 1u;
+    unsigned w = blockIdx.x * kWarps + (tid >> 5);
+    if (w >= first_dynamic) {                                                                // (more warps than static units)
+        unsigned c0 = 0;
+        if (lane == 0) c0 = atomicAdd(a.geo_counter, 1u);
+        w = first_dynamic + __shfl_sync(kFull, c0, 0);
+    }
     while (w < n_work) {
+        const bool next_static = w + n_warps < first_dynamic;               // (uniform)
         unsigned claim = 0;
-        if (lane == 0) claim = atomicAdd(a.geo_counter, 1u);                // the unit after this one (used at the bottom of the loop)
-        long long tile;
+        if (!next_static && lane == 0) claim = atomicAdd(a.geo_counter, 1u);   // the unit after this one (used at the bottom of the loop)
+        unsigned tile;
         int f0;
-        unsigned frame_mask = 0xffu;
+        unsigned frame_mask = (1u << kUnitFrames) - 1u;
         if (a.worklist) {
-            const unsigned long long e = a.worklist[w >> 3];
-            tile = (long long)(e >> 8) / n_chunks * 8 + (w & 7);            // (a 256-vertex tile = 8 warp tiles)
-            f0 = (int)((long long)(e >> 8) % n_chunks) * kGeoFrames;
-            frame_mask = (unsigned)(e & 0xffu);
+            const unsigned long long e = a.worklist[w / (8u * kUnitSplit)];
+            const unsigned rem = w % (8u * kUnitSplit), unit8 = (unsigned)(e >> 8);
+            tile = unit8 / n_chunks8 * 8u + rem / kUnitSplit;              // (a 256-vertex tile = 8 warp tiles)
+            f0 = (int)(unit8 % n_chunks8) * kGeoFrames + (int)(rem % kUnitSplit) * kUnitFrames;
+            frame_mask &= (unsigned)(e & 0xffu) >> ((rem % kUnitSplit) * kUnitFrames);
         } else {
             tile = w / n_chunks;
-            f0 = (int)(w % n_chunks) * kGeoFrames;
+            f0 = (int)(w % n_chunks) * kUnitFrames;
         }
-        const int nf = min(kGeoFrames, a.n_frames - f0);
-        if (tile < n_tiles) {
+        const int nf = min(kUnitFrames, a.n_frames - f0);
+        if (tile < n_tiles && nf > 0 && frame_mask) {
             __syncwarp();
             for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
             __syncwarp();
             if (a.warp_bounds)
-                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.warp_bounds + tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
+                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.warp_bounds + (size_t)tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
             else if (!a.worklist && a.tile_bounds)                            // (with a work list the cull kernel has made the mask)
-                frame_mask = __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + (tile >> 3) * 6, sT[lane & (kGeoFrames - 1)], cams.box));
-            if (nf < kGeoFrames) frame_mask &= (1u << nf) - 1u;
+                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + (size_t)(tile >> 3) * 6, sT[lane & (kGeoFrames - 1)], cams.box));
+            frame_mask &= (1u << nf) - 1u;
         } else {
             frame_mask = 0u;
         }
         if (frame_mask) {
-            const long long n = tile * 32 + lane;
+            const long long n = (long long)tile * 32 + lane;
             double vx, vy, vz;
             int ord;
             const bool valid = load_vertex<LAYOUT>(a, n, vx, vy, vz, ord);
@@ -468,19 +502,16 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
                 const bool alive = valid && in_box(cams.box, cx, cy, cz);
                 if (__any_sync(kFull, alive)) {
                     if (DEBUG && alive && a.crop_counts) atomicAdd(&a.crop_counts[(size_t)f * a.n_instances + ord], 1);
-                    const int n_cams = NCAMS ? NCAMS : a.n_cams;
-                    unsigned lane_cams = alive ? 0xffu : 0u;                   // cameras that can see this lane's point at all
-                    if (a.cam_table && alive) {
+                    unsigned lane_cams = alive ? all_cams : 0u;               // cameras that can see this lane's point at all
+                    if (use_table && alive) {
                         const int ix = min(max((int)((float)(cx - a.tab_x0) * a.tab_inv_sx), 0), a.tab_nx - 1);
                         const int iy = min(max((int)((float)(cy - a.tab_y0) * a.tab_inv_sy), 0), a.tab_ny - 1);
-                        lane_cams = __ldg(a.cam_table + iy * a.tab_nx + ix);
+                        lane_cams = __ldg(table + iy * a.tab_nx + ix);
                     }
-                    const unsigned warp_cams = __reduce_or_sync(kFull, lane_cams);
                     double qx = 0.0, qy = 0.0, qz = 1.0;            // (lanes that are no candidate keep whatever the last camera left: masked)
-#pragma unroll
-                    for (int c = 0; c < (NCAMS ? NCAMS : CAMA_MAX_CAMERAS); ++c) {
-                        if (!NCAMS && c >= n_cams) break;
-                        if (!((warp_cams >> c) & 1u)) continue;     // (uniform)
+#pragma unroll 1
+                    for (unsigned cams_left = __reduce_or_sync(kFull, lane_cams) & all_cams; cams_left; cams_left &= cams_left - 1u) {
+                        const int c = __ffs(cams_left) - 1;         // (uniform)
                         const bool cand = ((lane_cams >> c) & 1u) && camera_candidate<PINHOLE>(cams, c, cx, cy, cz, a.width, a.height, qx, qy, qz);
                         if (!__any_sync(kFull, cand)) continue;
                         int vi = 0, ui = 0;
@@ -492,7 +523,7 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
                 if (BINNED && stage.count >= (unsigned)kStageFlush) stage_flush(a, stage);     // (warp-uniform)
             }
         }
-        w = first_dynamic + (long long)__shfl_sync(kFull, claim, 0);
+        w = next_static ? w + n_warps : first_dynamic + __shfl_sync(kFull, claim, 0);
     }
     if (BINNED && stage.count > 0u) stage_flush(a, stage);
 }
@@ -1230,6 +1261,48 @@ cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
+// Cell grid of the camera table over the crop box's x-y rectangle: cells of about a metre, at most 256 x 256; none
+// for a degenerate or unbounded box.
+bool table_geometry(const double *box, CamTable &tab) {
+    const double rx = box[1] - box[0], ry = box[3] - box[2];
+    if (!(rx > 0.0 && ry > 0.0 && rx <= 1e6 && ry <= 1e6)) return false;                  // (false for NaN / infinite boxes)
+    tab.nx = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(rx)));
+    tab.ny = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(ry)));
+    tab.x0 = box[0]; tab.y0 = box[2];
+    tab.sx = rx / tab.nx; tab.sy = ry / tab.ny;
+    return true;
+}
+
+// FNV-1a over everything the table depends on: a table built for another rig / box / image size is ignored by the kernel
+unsigned long long table_signature(const CamBlock &cams, int n_cams, int width, int height) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(cams.E, sizeof(cams.E)); mix(cams.K, sizeof(cams.K)); mix(cams.box, sizeof(cams.box));
+    const int dims[3] = {n_cams, width, height};
+    mix(dims, sizeof(dims));
+    return h | 1ull;                                           // (never 0: a zero-filled buffer is not a table)
+}
+
+void fill_cam_block(CamBlock &cams, int n_cams, const double *chassis2cam, const double *intrinsics, const double *crop_box, int width, int height) {
+    for (int c = 0; c < CAMA_MAX_CAMERAS; ++c) {
+        const bool live = c < n_cams;
+        for (int i = 0; i < 12; ++i) cams.E[c][i] = live ? chassis2cam[16 * c + i] : 0.0;
+        for (int i = 0; i < 9; ++i) cams.K[c][i] = live ? intrinsics[9 * c + i] : 0.0;
+        cams.k_row2_is_001[c] = live && cams.K[c][6] == 0.0 && cams.K[c][7] == 0.0 && cams.K[c][8] == 1.0;
+    }
+    for (int i = 0; i < 6; ++i) cams.box[i] = crop_box[i];
+    cams.wlim = (double)(width + 1);
+    cams.hlim = (double)(height + 1);
+    cams.all_pinhole = 1;
+    for (int c = 0; c < n_cams; ++c) {
+        const double *K = cams.K[c];
+        if (!(cams.k_row2_is_001[c] && K[1] == 0.0 && K[3] == 0.0)) cams.all_pinhole = 0;
+    }
+}
+
 struct ClipPlan {
     int mode;
     int band_rows, n_bands, x_bits;
@@ -1239,7 +1312,7 @@ struct ClipPlan {
     size_t raster_smem;
     // workspace offsets
     size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
-    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists, off_camtab;
+    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists;
     long long geo_units;
     size_t total;
     // frame-group pipeline (BINNED): the clip is rendered as `groups` sub-clips of `group_frames` frames, each with
@@ -1252,18 +1325,17 @@ constexpr int kRasterCtasPerSm = 4;
 constexpr int kDynEmptyPerCta = 5;
 constexpr int kDynEmptyPct = 60;                 // measured on config 2: 0 % 78.5 us, 40 % 74.4, 60 % 73.4, 80 % 75.5, 100 % 78.6 (CAMA_RASTER_DYN_EMPTY)
 constexpr int kDefaultBandRows = 16;
+bool BinnedSite(const cama_clip_desc *d, const cama_ctx *ctx, long long units) { return d->tile_bounds && units >= (long long)ctx->sm_count * 64; }
+
 template <bool BINNED>
 cudaError_t launch_geometry(bool pdl, bool f32, bool debug, unsigned grid, cudaStream_t s, const ClipArgs &a, const CamBlock &cams) {
-    static const bool generic_only = getenv("CAMA_GEO_GENERIC") != nullptr;     // experiment knob
-    if (f32 && !debug && a.n_cams == 6 && !generic_only) {          // the production shape: six cameras, float32 vertices
-        if (cams.all_pinhole) return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6, true>, grid, kGeoThreads, 0, s, a, cams);
-        return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 6, false>, grid, kGeoThreads, 0, s, a, cams);
+    if (f32 && !debug) {                                            // the production shape: float32 vertices, no per-instance outputs
+        if (cams.all_pinhole) return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, true>, grid, kGeoThreads, 0, s, a, cams);
+        return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, false>, grid, kGeoThreads, 0, s, a, cams);
     }
-    if (f32)
-        return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, 0, false>, grid, kGeoThreads, 0, s, a, cams)
-                     : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, false, 0, false>, grid, kGeoThreads, 0, s, a, cams);
-    return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, 0, false>, grid, kGeoThreads, 0, s, a, cams)
-                 : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, 0, false>, grid, kGeoThreads, 0, s, a, cams);
+    if (f32) return launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F32X4, BINNED, true, false>, grid, kGeoThreads, 0, s, a, cams);
+    return debug ? launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, true, false>, grid, kGeoThreads, 0, s, a, cams)
+                 : launch_k(pdl, clip_geometry_kernel<CAMA_VERTEX_F64X3, BINNED, false, false>, grid, kGeoThreads, 0, s, a, cams);
 }
 
 constexpr size_t kRasterSmemBudget = 56 * 1024;      // four CTAs per SM
@@ -1277,6 +1349,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     if (d->n_cams > CAMA_MAX_CAMERAS) return fail(CAMA_E_UNSUPPORTED, "at most %d cameras per call", CAMA_MAX_CAMERAS);
     CAMA_REQUIRE(d->vertex_layout == CAMA_VERTEX_F32X4 || d->vertex_layout == CAMA_VERTEX_F64X3, "bad vertex_layout");
     CAMA_REQUIRE((long long)d->n_frames * d->n_cams * d->height * d->width < (1ll << 40), "clip too large");
+    CAMA_REQUIRE(((d->n_vertices + 31) / 32 + 8) * (((long long)d->n_frames + 7) / 8 * 8) < (1ll << 32), "too many (vertex tile, frame) units for 32-bit indices");
     const int W = d->width, H = d->height;
     // BINNED needs: 16-byte rows for the bulk stores, a 16-bit {plane row | x} pixel code with at least
     // 8 plane rows, 32 occupancy segments of 64 px, a 16-bit ordinal
@@ -1314,7 +1387,6 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     p.off_stats = take(sizeof(ClipStatsDev));
     p.geo_units = ((d->n_vertices + kGeoThreads - 1) / kGeoThreads) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
     p.off_worklist = take(sizeof(unsigned long long) * (size_t)std::max<long long>(p.geo_units, 1));
-    p.off_camtab = take((size_t)kCamTableMaxDim * kCamTableMaxDim);
     p.off_zero = off;                                                      // cleared by prep every call: counters | hist (BINNED)
     p.off_counter = take(256);
     p.zero_bytes = off - p.off_zero;
@@ -1391,17 +1463,13 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     const bool binned = p.mode == CAMA_CLIP_BINNED;
     const bool pdl = binned && pdl_enabled() && !prof;
 
-    // camera table over the crop box's x-y rectangle (cells of about a metre, at most 256 x 256); none for a degenerate box
-    CamTable tab{};
+    // camera table (cama_camera_table_build, once per rig): which cameras can see a cell of the crop box at all
     {
         static const bool no_table = getenv("CAMA_GEO_NO_CAMTABLE") != nullptr;          // experiment knob
-        const double rx = d->crop_box[1] - d->crop_box[0], ry = d->crop_box[3] - d->crop_box[2];
-        if (!no_table && rx > 0.0 && ry > 0.0 && rx <= 1e6 && ry <= 1e6) {                // (false for NaN / infinite boxes)
-            tab.nx = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(rx)));
-            tab.ny = (int)std::min<double>(kCamTableMaxDim, std::max(1.0, std::ceil(ry)));
-            tab.x0 = d->crop_box[0]; tab.y0 = d->crop_box[2];
-            tab.sx = rx / tab.nx; tab.sy = ry / tab.ny;
-            a.cam_table = ws + p.off_camtab;
+        CamTable tab{};
+        if (!no_table && d->camera_table && table_geometry(d->crop_box, tab)) {
+            a.cam_table = static_cast<const unsigned char *>(d->camera_table);
+            a.tab_signature = table_signature(cams, d->n_cams, d->width, d->height);
             a.tab_x0 = tab.x0; a.tab_y0 = tab.y0;
             a.tab_inv_sx = (float)(1.0 / tab.sx); a.tab_inv_sy = (float)(1.0 / tab.sy);
             a.tab_nx = tab.nx; a.tab_ny = tab.ny;
@@ -1415,23 +1483,31 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     {
         NvtxRange nvtx_phase("prep");
         const long long zero_words = (long long)(p.zero_bytes / 4);
-        const long long n = std::max<long long>(std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20)),
-                                                (long long)tab.nx * tab.ny * 8);
+        const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
         // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
         CAMA_CUDA_TRY(launch_k(pdl, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
                                d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
                                d->instance_bgr, d->n_instances, lut,
                                reinterpret_cast<unsigned *>(ws + p.off_zero), zero_words,
                                reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette,
-                               cams, d->n_cams, d->width, d->height, tab, tab.nx ? ws + p.off_camtab : (unsigned char *)nullptr));
+                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
     const long long units = n_tiles * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);          // (256-vertex tile, 8 frames): what the cull kernel works on
-    const long long warp_units = ((d->n_vertices + 31) / 32) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
+    const bool site = BinnedSite(d, ctx, units);                     // big clips: the cull kernel makes a work list first
+    static const int uf_clip = getenv("CAMA_GEO_UNIT_FRAMES") ? atoi(getenv("CAMA_GEO_UNIT_FRAMES")) : CAMA_GEO_UNIT_FRAMES;
+    static const int uf_site = getenv("CAMA_GEO_UNIT_FRAMES_SITE") ? atoi(getenv("CAMA_GEO_UNIT_FRAMES_SITE")) : CAMA_GEO_UNIT_FRAMES_SITE;
+    static const int static_pct = getenv("CAMA_GEO_STATIC_PCT") ? atoi(getenv("CAMA_GEO_STATIC_PCT")) : CAMA_GEO_STATIC_PCT;
+    int unit_frames = site && p.mode == CAMA_CLIP_BINNED ? uf_site : uf_clip;
+    if (unit_frames != 1 && unit_frames != 2 && unit_frames != 4 && unit_frames != 8) unit_frames = 4;
+    a.unit_frames = unit_frames;
+    const long long warp_units = ((d->n_vertices + 31) / 32) * ((d->n_frames + unit_frames - 1) / unit_frames);
+    // (with a work list the number of live units is only known on the device: everything is claimed dynamically there)
+    a.static_units = site && p.mode == CAMA_CLIP_BINNED ? 0u : (unsigned)(warp_units * std::min(100, std::max(0, static_pct)) / 100);
     // persistent grid: every resident warp claims (32-vertex, 8-frame) units until none are left
-    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>((warp_units + 7) / 8, (long long)ctx->sm_count * CAMA_GEO_MINB));
+    static const int geo_ctas = getenv("CAMA_GEO_CTAS") ? std::max(1, atoi(getenv("CAMA_GEO_CTAS"))) : CAMA_GEO_MINB;      // experiment knob
+    const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>((warp_units + 7) / 8, (long long)ctx->sm_count * geo_ctas));
     const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
     const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;
 
@@ -1466,7 +1542,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     if (units > 0) {
         NvtxRange nvtx_phase("geometry");
         // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
-        if (d->tile_bounds && units >= (long long)ctx->sm_count * 64) {
+        if (site) {
             unsigned *n_live = reinterpret_cast<unsigned *>(ws + p.off_counter) + 2;
             unsigned long long *worklist = reinterpret_cast<unsigned long long *>(ws + p.off_worklist);
             CAMA_CUDA_TRY(launch_k(pdl, geometry_cull_kernel, (unsigned)((units * kGeoFrames + 255) / 256), 256, 0, s, d->tile_bounds, a.w2c64, units,
@@ -1550,6 +1626,27 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
 
 extern "C" {
 
+int cama_camera_table_build(cama_ctx *ctx, const double *chassis2cam, const double *intrinsics, int n_cams, const double *crop_box, int height,
+                            int width, void *table, void *stream) {
+    CAMA_REQUIRE(ctx && chassis2cam && intrinsics && crop_box && table, "NULL argument");
+    CAMA_REQUIRE(n_cams > 0 && n_cams <= CAMA_MAX_CAMERAS && height > 0 && width > 0, "bad shape");
+    CAMA_REQUIRE(((uintptr_t)table & 15) == 0, "table must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CamBlock cams;
+    fill_cam_block(cams, n_cams, chassis2cam, intrinsics, crop_box, width, height);
+    CamTable tab{};
+    if (!table_geometry(crop_box, tab)) {                      // no grid for this box: an all-zero header never matches a signature
+        CAMA_CUDA_TRY(cudaMemsetAsync(table, 0, CAMA_CAMERA_TABLE_HEADER, s));
+        return CAMA_OK;
+    }
+    const int n = tab.nx * tab.ny * 8;
+    camera_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cams, n_cams, width, height, tab, table_signature(cams, n_cams, width, height),
+                                                                static_cast<unsigned char *>(table));
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
 int cama_clip_workspace_bytes(const cama_clip_desc *desc, size_t *bytes) {
     CAMA_REQUIRE(bytes, "bytes is NULL");
     ClipPlan p;
@@ -1595,20 +1692,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     if (ctx->prof_calls < ctx->prof_capacity) prof = ctx->prof_events.data() + (size_t)(ctx->prof_calls++) * (CAMA_CLIP_PHASES + 1);
 
     CamBlock cams;
-    for (int c = 0; c < CAMA_MAX_CAMERAS; ++c) {
-        const bool live = c < d->n_cams;
-        for (int i = 0; i < 12; ++i) cams.E[c][i] = live ? d->chassis2cam[16 * c + i] : 0.0;
-        for (int i = 0; i < 9; ++i) cams.K[c][i] = live ? d->intrinsics[9 * c + i] : 0.0;
-        cams.k_row2_is_001[c] = live && cams.K[c][6] == 0.0 && cams.K[c][7] == 0.0 && cams.K[c][8] == 1.0;
-    }
-    for (int i = 0; i < 6; ++i) cams.box[i] = d->crop_box[i];
-    cams.wlim = (double)(d->width + 1);
-    cams.hlim = (double)(d->height + 1);
-    cams.all_pinhole = 1;
-    for (int c = 0; c < d->n_cams; ++c) {
-        const double *K = cams.K[c];
-        if (!(cams.k_row2_is_001[c] && K[1] == 0.0 && K[3] == 0.0)) cams.all_pinhole = 0;
-    }
+    fill_cam_block(cams, d->n_cams, d->chassis2cam, d->intrinsics, d->crop_box, d->width, d->height);
 
     ctx->last_render_grouped = p.groups > 1 && !prof;
     if (p.groups <= 1 || prof) {                       // one pass, one stream (phase events would serialise the lanes anyway)

@@ -85,8 +85,11 @@ def render_sharded(reproject, dataset, gather=True, group=None, mode="auto"):
 
     gather  False: only this rank's block; True / "dense": one all-gather of the uint8 frames (north_star's
             collective: NVLink-bound, the ranks exchange every frame byte); "sparse": the ranks render the sparse
-            output, all-gather the lit-chunk records and rebuild the dense frames locally with
-            cama_overlay_expand — same bytes in HBM at the end, ~25x fewer over NVLink (blank backgrounds).
+            output, all-gather the lit-chunk records (NCCL) and rebuild the dense frames locally with
+            cama_overlay_expand — same bytes in HBM at the end, ~25x fewer over NVLink (blank backgrounds);
+            "peer": the same exchange without NCCL and without the host — the raster mirrors its records into
+            the peers' memory while it runs (SiteAssembler / PeerExchange below); falls back to "sparse" on a box
+            without a peer-to-peer path.
     -> (image_idx list of the frames returned, torch uint8 [n, C, H, W, 3] on the rank's GPU)
     """
     import torch
@@ -95,6 +98,18 @@ def render_sharded(reproject, dataset, gather=True, group=None, mode="auto"):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     idx, w2c = reproject.frame_poses(dataset)
     lo, hi = frame_block(len(idx), rank, world)
+    if gather == "peer" and world > 1:
+        cache = reproject.__dict__.setdefault("_site_assemblers", {})
+        key = (dataset, id(group), mode)
+        if key not in cache:
+            cache[key] = SiteAssembler(reproject, dataset, group=group, mode=mode)
+        if cache[key].available:
+            frames = cache[key].step()
+            code = cache[key].exchange.status_code()
+            if code:
+                raise RuntimeError(f"peer assembly failed with status {code} (1: a peer's step timed out, 2: a slot overflowed)")
+            return idx, frames
+        gather = "sparse"
     if gather == "sparse" and world > 1:
         r, res = reproject.renderer, reproject.resident(dataset)
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c[lo:hi], dtype=np.float32).reshape(-1, 16)).to(reproject.rt.device)
@@ -244,3 +259,40 @@ class PeerExchange:
     def status_code(self):
         """0 ok, 1 a peer's step timed out, 2 a slot overflowed (synchronises)."""
         return int(self.status.item())
+
+
+class SiteAssembler:
+    """A frame-sharded clip assembled on every rank, step after step (BASELINE.json configs[3]).
+
+    Construction is collective: sizes the record slots from one checked sparse render per rank (max over ranks,
+    25 % headroom), builds the PeerExchange.  ``step()`` enqueues render + exchange + expand of this rank's frame
+    block and returns the tensor that holds ALL frames of the clip afterwards (the same tensor every step)."""
+
+    def __init__(self, reproject, dataset, group=None, mode="auto", overlap_zero=True):
+        import torch
+        import torch.distributed as dist
+        self.rp, self.dataset, self.mode = reproject, dataset, mode
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        r, rt = reproject.renderer, reproject.rt
+        self.res = reproject.resident(dataset)
+        self.idx, w2c = reproject.frame_poses(dataset)
+        self.n_frames = len(self.idx)
+        self.lo, self.hi = frame_block(self.n_frames, self.rank, self.world)
+        self.w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c[self.lo:self.hi], dtype=np.float32).reshape(-1, 16)).to(rt.device)
+        _, n, fmt = r.render_overlay(self.res, self.w2c_dev, mode=mode)          # settles the centre-record pool, counts the lit chunks
+        most = torch.tensor([int(n)], dtype=torch.int64, device=rt.device)
+        dist.all_reduce(most, op=dist.ReduceOp.MAX, group=group)
+        self.exchange = PeerExchange(rt, int(int(most.item()) * 1.25) + 4096, fmt, group=group)
+        self.available = self.exchange.available
+        self.frames = None
+        self.zero_stream = torch.cuda.Stream(device=rt.device) if overlap_zero else None
+
+    def step(self, out=None):
+        import torch
+        r = self.rp.renderer
+        if out is None:
+            if self.frames is None:
+                self.frames = torch.empty((self.n_frames, r.n_cams, r.height, r.width, 3), dtype=torch.uint8, device=self.rp.rt.device)
+            out = self.frames
+        return self.exchange.render_and_assemble(r, self.res, self.w2c_dev, self.lo, self.n_frames, out, mode=self.mode, zero_stream=self.zero_stream)

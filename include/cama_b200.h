@@ -46,6 +46,8 @@ extern "C" {
 #define CAMA_MAX_PEERS 8          /* GPUs of one box that exchange the sparse output (cama_peer_*) */
 #define CAMA_PEER_HEADER_BYTES 256
 #define CAMA_PEER_HANDLE_BYTES 64
+#define CAMA_CAMERA_TABLE_HEADER 16
+#define CAMA_CAMERA_TABLE_BYTES (CAMA_CAMERA_TABLE_HEADER + 256 * 256) /* device bytes of a camera table */
 
 typedef enum cama_status {
     CAMA_OK = 0,
@@ -236,6 +238,9 @@ typedef struct cama_clip_desc {
     int32_t overlay_n_mirrors;
     int32_t reserved0;
     int64_t overlay_image_base;
+    /* Optional culling aid: the table cama_camera_table_build made for THESE cameras, crop box and image size (a table
+     * built for other ones is recognised by its signature and ignored).  Results are unchanged. */
+    const void *camera_table;       /* device, CAMA_CAMERA_TABLE_BYTES, or NULL */
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -249,6 +254,17 @@ typedef struct cama_clip_stats {
     int32_t n_bands;
     int64_t overlay_records;        /* lit chunks produced (sparse output), 0 otherwise */
 } cama_clip_stats;
+
+/* Which cameras can see a point of the crop box at all?  Cuts the crop box's x-y rectangle into cells of about a metre
+ * and stores, per cell, the set of cameras for which the visibility conditions of CameraManager.project_to_image
+ * (cama/reproject.py:191-198: q_z > 0, 0 <= u < W, 0 <= v < H after cama/dataset.py:110-115's chassis->camera
+ * transform) can hold somewhere in the cell (conservatively: maximised over the cell and the box's z range, with a slack
+ * far above the rounding error).  cama_clip_render then runs, for every 32 vertices, only the cameras some vertex's cell
+ * lists (typically 1-2 of 6) — the frames are bit-identical with and without the table.  Depends on the camera rig, the
+ * crop box and the image size only: build once, pass as cama_clip_desc.camera_table.
+ *   chassis2cam, intrinsics, crop_box: host, as in cama_clip_desc;  table: device, CAMA_CAMERA_TABLE_BYTES, 16-byte aligned */
+int cama_camera_table_build(cama_ctx *ctx, const double *chassis2cam, const double *intrinsics, int n_cams,
+                            const double *crop_box, int height, int width, void *table, void *stream);
 
 /* Workspace (device bytes) a cama_clip_render call with this descriptor needs. */
 int cama_clip_workspace_bytes(const cama_clip_desc *desc, size_t *bytes);

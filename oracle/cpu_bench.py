@@ -58,6 +58,21 @@ def _numpy_frames(span):
     return done, check
 
 
+def _numpy_frames_images(span):
+    """The same with render_vectors (cama/dataset.py:119-126): every camera image is read from its JPEG, undistort-
+    resized and drawn on in place — the second CPU figure BASELINE.md asks for."""
+    lo, hi = span
+    oc, orc = _STATE["oc"], _STATE["orc"]
+    done, check = 0, 0
+    for image_idx, w2c in _STATE["poses"][lo:hi]:
+        chassis = orc.crop_instances(orc.transform_instances(oc.instance_maps[_STATE["dataset"]], w2c))
+        images = oc.render_vectors(oc.project_all(chassis), image_idx)
+        for cam in oc.cameras:
+            check += int(images[cam][::7, ::7].sum())
+            done += 1
+    return done, check
+
+
 def _c_frames(span):
     lo, hi = span
     from oracle import oracle_c
@@ -95,7 +110,7 @@ class CpuRunner:
 
     def step(self, kind="numpy", parallel=True, frames=None):
         """-> (seconds, cam-frames rendered).  ``frames`` limits the sample to the first n frames."""
-        fn = _numpy_frames if kind == "numpy" else _c_frames
+        fn = {"numpy": _numpy_frames, "numpy_images": _numpy_frames_images, "c": _c_frames}[kind]
         n = self.n_frames if frames is None else min(frames, self.n_frames)
         t0 = time.perf_counter()
         if parallel and self.pool is not None:

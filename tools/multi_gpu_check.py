@@ -3,11 +3,15 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 
-Every rank renders its frame block of the same synthetic config-2 clip, the blocks are all-gathered
-over NCCL (dense frames, and sparse records + device expand), and every rank checks the gathered clip bit for bit
-against its own single-GPU render; then the LiDAR sweeps of a clip are sharded and the all-reduced voxel counts
-are checked against the single-GPU aggregation.
+Every rank renders its frame block of the same synthetic config-2 clip, the blocks are assembled on every rank
+three ways — NCCL all-gather of the dense frames, NCCL all-gather of the sparse records + device expand, and the
+peer-memory exchange (the raster mirrors its records into the peers' mailboxes; cama_peer_publish / cama_peer_expand;
+several steps in a row, so both mailbox parities and the slot reuse are exercised) — and every rank checks the
+assembled clip bit for bit against its own single-GPU render; then the LiDAR sweeps of a clip are sharded and the
+all-reduced voxel counts are checked against the single-GPU aggregation.  Rank 0 prints one JSON line (kept under
+profiles/).
 """
+import json
 import os
 import sys
 import tempfile
@@ -37,6 +41,26 @@ def main():
         lo, hi = shard.frame_block(37, rank, world)
         idx_local, block = shard.render_sharded(rp, "nuscenes", gather=False)
         ok = ok and idx_local == idx[lo:hi] and bool((block == whole[lo:hi]).all())
+        report = {"world": world, "frames": 37, "dense_nccl_allgather": bool((gathered == whole).all()), "sparse_nccl_allgather": bool((gathered_s == whole).all())}
+        # peer-memory assembly: five steps in a row into the same output, every one checked; then a poisoned output buffer
+        asm = shard.SiteAssembler(rp, "nuscenes")
+        report["peer_available"] = bool(asm.available)
+        report["peer_error"] = asm.exchange.error
+        peer_ok = True
+        if asm.available:
+            for step in range(5):
+                out = asm.step()
+                if step == 3:
+                    torch.cuda.synchronize()
+                    out.fill_(0x5a)                               # the next step must overwrite every byte
+                    out = asm.step()
+                torch.cuda.synchronize()
+                peer_ok = peer_ok and asm.exchange.status_code() == 0 and bool((out == whole).all())
+            idx_p, gathered_p = shard.render_sharded(rp, "nuscenes", gather="peer")    # the public entry
+            peer_ok = peer_ok and idx_p == idx and bool((gathered_p == whole).all())
+            dist.barrier()
+        report["peer_assembly"] = peer_ok
+        ok = ok and peer_ok
         # LiDAR aggregation (configs[4]): sweeps sharded across the ranks, voxel counts summed with one all-reduce
         from cama_b200.lidar import LidarAggregator, allreduce_counts
         synth.write_lidar_sweeps(clip, n_sweeps=37, n_points=3000, seed=5, ragged=True)      # (every rank has its own copy of the clip)
@@ -48,6 +72,9 @@ def main():
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
+            report["lidar_allreduce"] = bool((total == whole_counts).all())
+            report["all_ranks_ok"] = bool(int(flag.item()))
+            print(json.dumps(report), flush=True)
             print(f"multi_gpu_check world={world}: {'OK' if int(flag.item()) else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
