@@ -185,10 +185,17 @@ def cpu_baseline(clip, dataset, budget_s):
         dt, cf = runner.step("numpy", parallel=True, frames=frames)
         dtc, cfc = runner.step("c", parallel=True, frames=n_frames)
         dtc1, cfc1 = runner.step("c", parallel=False, frames=min(n_frames, 8))
+        # the same loop with render_vectors (cama/dataset.py:119-126): camera JPEGs decoded, undistort-resized, drawn on
+        img_frames = min(n_frames, runner.workers)
+        synth.write_background_jpegs(clip, img_frames, seed=0)
+        dti, cfi = runner.step("numpy_images", parallel=True, frames=img_frames)
         return {"value": cf / dt, "unit": UNIT, "cores": runner.workers, "kind": "port",
                 "sample": f"{frames} of {n_frames} frames x {runner.n_cams} cams of the same clip, NumPy/OpenCV oracle "
                           f"(reference loop structure), frames sharded over {runner.workers} processes; blank backgrounds",
                 "single_process": {"value": cf1 / dt1, "unit": UNIT, "cores": 1, "sample": f"{probe_frames} frames"},
+                "with_images": {"value": cfi / dti, "unit": UNIT, "cores": runner.workers,
+                                "sample": f"{img_frames} frames x {runner.n_cams} cams through render_vectors: cv2.imread of a 1600x900 JPEG, "
+                                          "initUndistortRectifyMap + remap, then the same drawing (BASELINE.md's second CPU figure)"},
                 "c_port": {"value": cfc / dtc, "unit": UNIT, "cores": runner.workers, "single_core": cfc1 / dtc1,
                            "note": "scalar C restatement (oracle/oracle.c), not what the reference runs"},
                 "host": {"cpu": cpu_model(), "usable_cores": usable_cores(), "os_cpu_count": os.cpu_count()}}
@@ -227,7 +234,7 @@ def run_reference(args):
                       f"(reference loop structure), frames sharded over {runner.workers} processes; blank backgrounds")
             line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
-                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                     "config": {"workload": workload_name(args.workload), "frames": runner.n_frames, "cams": runner.n_cams,
                                "cam_frames_per_step": per_step_frames * runner.n_cams},
                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": runner.workers, "kind": "port", "sample": sample,
@@ -386,6 +393,16 @@ def run_b200(args):
     dense_steps = max(3, e2e_steps // 2)
     assert checksum == checksum_dense, "sparse and dense transfers disagree"
 
+    # ---- the zero-change drop-in path: the three calls unmodified main.py makes per frame (main.py:57-59), host lists of
+    # NumPy arrays in and out as the reference's protocol demands, one process
+    from tools.dropin_bench import dropin_loop
+    from cama_b200.dataset import ClipManager
+    cm_dropin = ClipManager(synth.CAMA_CONFIGS, clip, device=local_rank, progress=False)
+    dropin_loop(cm_dropin, dataset, H, W, max_frames=3)
+    torch.cuda.synchronize()
+    dropin_t, dropin_done, _ = dropin_loop(cm_dropin, dataset, H, W, max_frames=min(F, 20))
+    dropin_s = sum(dropin_t.values())
+
     # ---- optional: the all-gather of rendered frames north_star names (N > 1)
     gather = gather_sparse_s = None
     if world > 1 and not args.no_allgather:
@@ -486,6 +503,11 @@ def run_b200(args):
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,
                               "d2h_bytes_per_step": int(frame_bytes), "d2h_gbs": frame_bytes * dense_steps / dense_s / 1e9,
                               "note": "same call with transfer='dense': all frame bytes rendered in HBM and copied back (PCIe-bound)"}},
+            "dropin": {"value": dropin_done / dropin_s, "unit": UNIT, "cam_frames": dropin_done,
+                       "ms_per_frame": {k: 1e3 * v / (dropin_done / C) for k, v in dropin_t.items()},
+                       "call": "unmodified main.py's per-frame protocol on one process: ClipManager.yield_frame -> project_all_camera -> "
+                               "CameraManager.render_maps on blank frames, host lists of NumPy arrays in and out (one device operator per call; "
+                               "the clip's vertices stay resident, the cropped points are handed from yield_frame to project_all_camera on the device)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "binned_raster_kernel" if stats["mode"] == 2 else "plane_raster_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -58,61 +58,62 @@ __global__ void peer_publish_kernel(const unsigned *__restrict__ count, unsigned
     st_release_sys(&h->step, step);
 }
 
-// status[0]: 0 = ok, 1 = timed out waiting for a peer (nothing expanded), 2 = a slot overflowed its capacity
+// status[0]: 0 = ok, 1 = timed out waiting for a peer (that peer's records are not expanded), 2 = a slot overflowed its capacity
+// Slot after slot, starting with the rank's own (which is there first): wait for the slot's step number, then write its
+// records grid-stride — the records of the ranks that are already done are expanded while the others still render.
 template <int FORMAT>
-__global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int world, unsigned step, long long capacity, const uint32_t *__restrict__ palette,
+__global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int world, int first, unsigned step, long long capacity, const uint32_t *__restrict__ palette,
                                                          uint8_t *__restrict__ frames, long long n_chunks, unsigned long long timeout_ns, int *status) {
-    __shared__ long long s_before[CAMA_MAX_PEERS + 1];
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) {
-        const unsigned long long t0 = global_ns();
-        bool ok = true;
-        long long total = 0;
-        for (int r = 0; r < world && ok; ++r) {
-            const SlotHeader *h = static_cast<const SlotHeader *>(slots.p[r]);
-            while (ld_acquire_sys(&h->step) != step) {
-                if (global_ns() - t0 > timeout_ns) { ok = false; break; }
-                __nanosleep(200);
-            }
-            s_before[r] = total;
-            if (ok) {
-                const long long c = h->count;
-                if (c > capacity && blockIdx.x == 0) atomicMax(status, 2);
-                total += c < capacity ? c : capacity;
-            }
-        }
-        s_before[world] = total;
-        if (!ok && blockIdx.x == 0) atomicMax(status, 1);
-        s_ok = ok;
-    }
-    __syncthreads();
-    if (!s_ok) return;
-    const long long total = s_before[world];
+    __shared__ long long s_count;
     constexpr int RW = FORMAT == CAMA_OVERLAY_BGR ? 8 : 3;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        int r = 0;
-        while (r + 1 < world && i >= s_before[r + 1]) ++r;
-        const uint32_t *rec = reinterpret_cast<const uint32_t *>(static_cast<const unsigned char *>(slots.p[r]) + CAMA_PEER_HEADER_BYTES) + (i - s_before[r]) * RW;
-        uint32_t w[6], chunk;
-        if (FORMAT == CAMA_OVERLAY_BGR) {
-            const uint4 a = reinterpret_cast<const uint4 *>(rec)[0], b = reinterpret_cast<const uint4 *>(rec)[1];
-            chunk = a.x;
-            w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
-        } else {
-            chunk = rec[0];
-            const uint32_t lo = rec[1], hi = rec[2];
-            uint32_t c[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                c[k] = palette[(lo >> (8 * k)) & 0xffu];
-                c[4 + k] = palette[(hi >> (8 * k)) & 0xffu];
+    const unsigned long long t0 = global_ns();
+    for (int k = 0; k < world; ++k) {
+        const int r = (first + k) % world;
+        const SlotHeader *h = static_cast<const SlotHeader *>(slots.p[r]);
+        __syncthreads();                                   // (s_count of the previous slot has been read by everyone)
+        if (threadIdx.x == 0) {
+            long long c = -1;
+            while (ld_acquire_sys(&h->step) != step) {
+                if (global_ns() - t0 > timeout_ns) break;
+                __nanosleep(100);
             }
-            w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
-            w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
+            if (ld_acquire_sys(&h->step) == step) {
+                c = h->count;
+                if (c > capacity) {
+                    if (blockIdx.x == 0) atomicMax(status, 2);
+                    c = capacity;
+                }
+            } else if (blockIdx.x == 0) {
+                atomicMax(status, 1);
+            }
+            s_count = c;
         }
-        if ((long long)chunk >= n_chunks) continue;
-        uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk * 24);
-        d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+        __syncthreads();
+        const long long total = s_count;
+        const uint32_t *records = reinterpret_cast<const uint32_t *>(static_cast<const unsigned char *>(slots.p[r]) + CAMA_PEER_HEADER_BYTES);
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+            const uint32_t *rec = records + i * RW;
+            uint32_t w[6], chunk;
+            if (FORMAT == CAMA_OVERLAY_BGR) {
+                const uint4 a = reinterpret_cast<const uint4 *>(rec)[0], b = reinterpret_cast<const uint4 *>(rec)[1];
+                chunk = a.x;
+                w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
+            } else {
+                chunk = rec[0];
+                const uint32_t lo = rec[1], hi = rec[2];
+                uint32_t c[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    c[q] = palette[(lo >> (8 * q)) & 0xffu];
+                    c[4 + q] = palette[(hi >> (8 * q)) & 0xffu];
+                }
+                w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
+                w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
+            }
+            if ((long long)chunk >= n_chunks) continue;
+            uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk * 24);
+            d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+        }
     }
 }
 
@@ -199,11 +200,21 @@ int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t ste
     return CAMA_OK;
 }
 
-int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, uint32_t step, int64_t capacity_records, int format, const uint8_t *palette_bgr,
+int cama_frames_clear(cama_ctx *ctx, uint8_t *frames, size_t bytes, void *stream) {
+    CAMA_REQUIRE(ctx, "ctx is NULL");
+    if (bytes == 0) return CAMA_OK;
+    CAMA_REQUIRE(frames, "frames is NULL");
+    DeviceGuard guard(ctx->device);
+    CAMA_CUDA_TRY(cudaMemsetAsync(frames, 0, bytes, (cudaStream_t)stream));
+    return CAMA_OK;
+}
+
+int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, int own_rank, uint32_t step, int64_t capacity_records, int format, const uint8_t *palette_bgr,
                      void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams, int height, int width, int timeout_ms, int32_t *status,
                      void *stream) {
     CAMA_REQUIRE(ctx && slots && status, "NULL argument");
     CAMA_REQUIRE(world > 0 && world <= CAMA_MAX_PEERS, "1..%d ranks", CAMA_MAX_PEERS);
+    CAMA_REQUIRE(own_rank >= 0 && own_rank < world, "own_rank out of range");
     CAMA_REQUIRE(format == CAMA_OVERLAY_BGR || format == CAMA_OVERLAY_PALETTE, "bad format");
     CAMA_REQUIRE(format != CAMA_OVERLAY_PALETTE || (palette_bgr && palette_scratch), "the palette format needs palette_bgr and palette_scratch (device)");
     CAMA_REQUIRE(n_frames >= 0 && n_cams > 0 && height > 0 && width > 0 && width % 8 == 0 && capacity_records >= 0, "bad shape");
@@ -222,9 +233,9 @@ int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, uint32_t step
     if (format == CAMA_OVERLAY_PALETTE) {
         palette_pack256_kernel<<<1, 256, 0, s>>>(palette_bgr, static_cast<uint32_t *>(palette_scratch));
         CAMA_LAUNCHED(ctx);
-        peer_expand_kernel<CAMA_OVERLAY_PALETTE><<<grid, 256, 0, s>>>(sp, world, step, capacity_records, static_cast<const uint32_t *>(palette_scratch), frames, n_chunks, timeout_ns, status);
+        peer_expand_kernel<CAMA_OVERLAY_PALETTE><<<grid, 256, 0, s>>>(sp, world, own_rank, step, capacity_records, static_cast<const uint32_t *>(palette_scratch), frames, n_chunks, timeout_ns, status);
     } else {
-        peer_expand_kernel<CAMA_OVERLAY_BGR><<<grid, 256, 0, s>>>(sp, world, step, capacity_records, nullptr, frames, n_chunks, timeout_ns, status);
+        peer_expand_kernel<CAMA_OVERLAY_BGR><<<grid, 256, 0, s>>>(sp, world, own_rank, step, capacity_records, nullptr, frames, n_chunks, timeout_ns, status);
     }
     CAMA_LAUNCHED(ctx);
     return CAMA_OK;

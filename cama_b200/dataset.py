@@ -152,10 +152,24 @@ class ClipManager:
         poses = self.frame_poses(dataset)
         instances = self.instance_maps[dataset]
         for image_idx, world2chassis in (_progress(poses) if self._progress else poses):
-            yield image_idx, self.mm.transform_crop_3d_instance_maps(instances, world2chassis)
+            # (the clip's dense vertices are uploaded once and stay resident; the survivors stay on the device too,
+            # for project_all_camera)
+            yield image_idx, self.mm.transform_crop_3d_instance_maps(instances, world2chassis, resident=True)
 
     def project_all_camera(self, maps_3d):
         """{camera_name: visible (v,u) instances}, cameras in ``camera_list`` order."""
+        dev = MapManager.device_points_if_untouched(maps_3d)
+        if dev is not None:
+            # the list yield_frame returned, untouched: its points are still on the device -> all cameras' launches
+            # back to back, one synchronisation (a list the caller edited takes the generic path below)
+            from .reproject import unpack_instances
+            from .runtime import get_runtime
+            cams = [(cm.K, np.asarray(cm.chassis2camera, dtype=np.float64)) for cm in self.cm_list]
+            size = {(cm.width, cm.height) for cm in self.cm_list}
+            if len(size) == 1:
+                width, height = next(iter(size))
+                results = get_runtime(self._device).project_points_cameras(dev["points"], dev["offsets"], dev["n_inst"], cams, width, height)
+                return {cm.camera_name: unpack_instances(vu, offs, dev["classes"]) for cm, (vu, offs) in zip(self.cm_list, results)}
         return {cm.camera_name: cm.transform_project_to_image(maps_3d) for cm in self.cm_list}
 
     def render_vectors(self, maps_2d_dict, image_idx):

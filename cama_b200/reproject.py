@@ -72,6 +72,13 @@ def unpack_instances(flat, offsets, classes, drop_empty=True):
     return out
 
 
+class InstanceList(list):
+    """A list of instances (what the reference's methods return) that also remembers where its points live on
+    the device, so that the next call of the per-frame protocol (yield_frame -> project_all_camera) does not
+    pack and upload them again.  Behaves like the plain list in every other respect."""
+    __slots__ = ("device_points",)
+
+
 def densify_polyline(points, resolution):
     """Dense float32 points of one polyline (reference :49-63 / :79-93), vectorised.
 
@@ -103,6 +110,7 @@ class MapManager(BaseManager):
         assert densify in ("host", "device")
         self._densify = densify
         self._device_dense = {}        # id(instance list) -> (instance list, device float4 vertices)
+        self._resident_inputs = {}     # id(instance list) -> packed vertices on the device (transform_crop_3d_instance_maps(resident=True))
         self.solution = 0.1      # metre per BEV pixel, also the densify step
         self.center_x = 0
         self.center_y = 0
@@ -189,16 +197,57 @@ class MapManager(BaseManager):
             out = out.astype(np.float32)       # survivors keep the caller's dtype, as boolean indexing does
         return unpack_instances(out, out_offsets, classes)
 
-    def transform_crop_3d_instance_maps(self, maps, transform, crop_dict=None):
+    def transform_crop_3d_instance_maps(self, maps, transform, crop_dict=None, resident=False):
         """Fused transform + crop (one pass, one round trip); same result as calling the two
-        methods above in sequence, which is what the frame loop does (cama/dataset.py:99-105)."""
+        methods above in sequence, which is what the frame loop does (cama/dataset.py:99-105).
+
+        resident=True (ClipManager.yield_frame passes it for the clip's own instance maps, which do not change from
+        frame to frame): the packed vertices are uploaded once and stay on the device; the result is an
+        ``InstanceList`` whose points also stay there for ``project_all_camera``."""
         crop_dict = crop_dict if crop_dict is not None else self.crop_dict
         if len(maps) == 0:
             return []
-        flat, offsets, classes = pack_instances(maps)
         box = [crop_dict[k] for k in CROP_KEYS]
-        out, out_offsets = get_runtime(self._device).crop_points(flat, offsets, box, T=np.asarray(transform))
-        return unpack_instances(out, out_offsets, classes)
+        rt = get_runtime(self._device)
+        if not resident:
+            flat, offsets, classes = pack_instances(maps)
+            out, out_offsets = rt.crop_points(flat, offsets, box, T=np.asarray(transform))
+            return unpack_instances(out, out_offsets, classes)
+        hit = self._resident_inputs.get(id(maps))
+        if hit is None or hit["maps"] is not maps or hit["n_inst"] != len(maps):
+            flat, offsets, classes = pack_instances(maps)
+            is_f32 = flat.dtype == np.float32
+            hit = {"maps": maps, "n_inst": len(maps), "classes": classes, "is_f32": is_f32,
+                   "d_in": rt.to_device(flat if is_f32 else flat.astype(np.float64, copy=False)), "d_off": rt.to_device(offsets, np.int64)}
+            if len(self._resident_inputs) >= 4:
+                self._resident_inputs.clear()
+            self._resident_inputs[id(maps)] = hit
+        d_out, d_out_off, out_offsets = rt.crop_points_resident(hit["d_in"], hit["is_f32"], hit["d_off"], hit["n_inst"], box, np.asarray(transform))
+        host_flat = d_out.cpu().numpy()
+        result = InstanceList(unpack_instances(host_flat, out_offsets, hit["classes"]))
+        result.device_points = {"points": d_out, "offsets": d_out_off, "classes": hit["classes"], "n_inst": hit["n_inst"],
+                                "n_kept": len(result), "host_flat": host_flat, "host_sum": float(host_flat.sum()) if host_flat.size else 0.0}
+        return result
+
+    @staticmethod
+    def device_points_if_untouched(maps):
+        """The device copy of an InstanceList's points when the host list still says the same thing: same length,
+        every "points" array still the view of the flat host array it was created as, contents unchanged (sum).
+        A list the caller has edited returns None and goes through the generic (pack + upload) path."""
+        dev = getattr(maps, "device_points", None)
+        if dev is None or dev["n_kept"] != len(maps):
+            return None
+        flat = dev["host_flat"]
+        address, rows = flat.ctypes.data, 0
+        for inst in maps:                            # consecutive row ranges of `flat`, in order, nothing missing
+            pts = inst["points"]
+            if not isinstance(pts, np.ndarray) or pts.dtype != flat.dtype or pts.ndim != 2 or pts.strides != flat.strides \
+                    or pts.ctypes.data != address + rows * flat.strides[0]:
+                return None
+            rows += pts.shape[0]
+        if rows != flat.shape[0] or (flat.size and float(flat.sum()) != dev["host_sum"]):
+            return None
+        return dev
 
     # ------------------------------------------------------------------ debugging dumps (host)
     def save_pcd(self, maps, pcd_path):

@@ -174,6 +174,45 @@ class Runtime:
         out_off = d_out_off.cpu().numpy()
         return d_out[:int(out_off[-1])].cpu().numpy(), out_off
 
+    def crop_points_resident(self, d_in, is_f32, d_off, n_inst, box6, T):
+        """cama_crop_points on points that are already on the device (a dataset's dense vertices, uploaded once).
+        -> (survivors device [m,3] f64, device offsets [n_inst+1], host offsets)"""
+        torch = _torch()
+        n = int(d_in.shape[0])
+        d_out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        d_out_off = torch.empty(n_inst + 1, dtype=torch.int64, device=self.device)
+        ws, ws_bytes = self._compact_scratch(n)
+        T64 = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        box = np.ascontiguousarray(box6, dtype=np.float64)
+        N.check(N.lib().cama_crop_points(self.ctx, self.ptr(d_in), int(is_f32), n, N.dptr(T64), N.dptr(box), self.ptr(d_off), n_inst,
+                                         self.ptr(d_out), self.ptr(d_out_off), self.ptr(ws), ws_bytes, self.stream()))
+        out_off = d_out_off.cpu().numpy()
+        return d_out[:int(out_off[-1])], d_out_off, out_off
+
+    def project_points_cameras(self, d_pts, d_off, n_inst, cameras, width, height):
+        """cama_project_points for several cameras on the same device-resident points: every camera's launches are
+        enqueued back to back, then ONE synchronisation brings all (v,u) arrays and offsets back.
+        cameras: list of (K 3x3, T 4x4).  -> list of ((k,2) f64 host array, host offsets) per camera."""
+        torch = _torch()
+        n, n_cams = int(d_pts.shape[0]), len(cameras)
+        if n == 0:
+            return [(np.zeros((0, 2)), np.zeros(n_inst + 1, np.int64)) for _ in cameras]
+        d_vu = torch.empty((n_cams, n, 2), dtype=torch.float64, device=self.device)
+        d_offs = torch.empty((n_cams, n_inst + 1), dtype=torch.int64, device=self.device)
+        need = ctypes.c_size_t()
+        N.check(N.lib().cama_compact_workspace_bytes(n, ctypes.byref(need)))
+        ws = self.scratch("compact_cams", need.value * n_cams)          # one slice per camera: the launches of different cameras are in flight together
+        for c, (K, T) in enumerate(cameras):
+            T64 = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+            K64 = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+            N.check(N.lib().cama_project_points(self.ctx, self.ptr(d_pts), n, N.dptr(T64), N.dptr(K64), int(width), int(height),
+                                                self.ptr(d_off), n_inst, ctypes.c_void_p(d_vu[c].data_ptr()), ctypes.c_void_p(d_offs[c].data_ptr()),
+                                                ctypes.c_void_p(ws.data_ptr() + c * need.value), need.value, self.stream()))
+        offs = d_offs.cpu().numpy()                                  # (synchronises)
+        most = int(offs[:, -1].max())
+        vu = d_vu[:, :most].cpu().numpy() if most else np.zeros((n_cams, 0, 2))
+        return [(vu[c, :int(offs[c, -1])], offs[c]) for c in range(n_cams)]
+
     def project_points(self, flat, offsets, K, width, height, T=None):
         """cama_project_points -> ((k,2) f64 (v,u), new offsets)."""
         torch = _torch()

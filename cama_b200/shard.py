@@ -207,13 +207,15 @@ class PeerExchange:
         """device pointer (in this process) of the slot of `source`'s records in `owner`'s mailbox"""
         return self.base[owner] + self.offset(parity, source)
 
-    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, n_frames_total, out, mode="auto", zero_stream=None):
+    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, n_frames_total, out, mode="auto", render_stream=None):
         """One step: render this rank's block (frames [frame_lo, frame_lo + len(w2c_dev)) of the clip), exchange, expand.
 
-        out          torch uint8 [n_frames_total, C, H, W, 3] on this device: all frames of the clip afterwards
-        zero_stream  optional side torch stream for the zero-fill of `out` (it then overlaps the render, which moves
-                     next to no memory); the expand waits for it
-        Asynchronous; check ``status()`` after synchronising.
+        out            torch uint8 [n_frames_total, C, H, W, 3] on this device: all frames of the clip afterwards
+        render_stream  optional HIGH-PRIORITY torch stream for the render + publish; the zero-fill of `out` then runs
+                       beside it on the current stream (a plain side stream does not overlap: the memset kernel fills
+                       every SM and the render's CTAs queue behind it; with a higher priority the render — which moves
+                       next to no memory — gets its CTAs first and the memset takes the rest of the machine)
+        Asynchronous; check ``status_code()`` after synchronising.
         """
         import torch
         from . import _native as N
@@ -221,31 +223,35 @@ class PeerExchange:
         self.step += 1
         parity = self.step & 1
         main = torch.cuda.current_stream()
-        if zero_stream is not None:
-            zero_stream.wait_stream(main)            # (the previous step's expand has finished writing `out`)
-            with torch.cuda.stream(zero_stream):
-                out.zero_()
-        else:
-            out.zero_()
         hdr = N.PEER_HEADER_BYTES
         own_slot = self.slot(self.rank, parity, self.rank)
         overlay = {"records_ptr": own_slot + hdr, "count_ptr": self.count.data_ptr(), "capacity": self.capacity, "fmt": self.fmt,
                    "mirrors": [self.slot(r, parity, self.rank) + hdr for r in range(self.world) if r != self.rank],
                    "image_base": frame_lo * renderer.n_cams}
-        if int(w2c_dev.shape[0]) > 0:
-            renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
-        else:
-            self.count.zero_()
         headers = (ctypes.c_void_p * self.world)(*[self.slot(r, parity, self.rank) for r in range(self.world)])
-        N.check(N.lib().cama_peer_publish(rt.ctx, self.count.data_ptr(), self.step, headers, self.world, rt.stream()))
-        if zero_stream is not None:
-            main.wait_stream(zero_stream)
+
+        def render_and_publish():
+            if int(w2c_dev.shape[0]) > 0:
+                renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
+            else:
+                self.count.zero_()
+            N.check(N.lib().cama_peer_publish(rt.ctx, self.count.data_ptr(), self.step, headers, self.world, rt.stream()))
+
+        if render_stream is not None:
+            render_stream.wait_stream(main)          # (the previous step's expand: it still reads the slots of the other parity ... and `count`)
+            with torch.cuda.stream(render_stream):
+                render_and_publish()
+            N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream()))
+            main.wait_stream(render_stream)
+        else:
+            N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream()))
+            render_and_publish()
         slots = (ctypes.c_void_p * self.world)(*[self.slot(self.rank, parity, r) for r in range(self.world)])
         pal_dev = scratch = None
         if self.fmt == N.OVERLAY_PALETTE:
             pal_dev = self._palette_dev(res)
             scratch = rt.scratch("palette32", 1024)
-        N.check(N.lib().cama_peer_expand(rt.ctx, slots, self.world, self.step, self.capacity, self.fmt, rt.ptr(pal_dev), rt.ptr(scratch),
+        N.check(N.lib().cama_peer_expand(rt.ctx, slots, self.world, self.rank, self.step, self.capacity, self.fmt, rt.ptr(pal_dev), rt.ptr(scratch),
                                          rt.ptr(out), int(n_frames_total), renderer.n_cams, renderer.height, renderer.width, 0,
                                          self.status.data_ptr(), rt.stream()))
         return out
@@ -268,7 +274,7 @@ class SiteAssembler:
     25 % headroom), builds the PeerExchange.  ``step()`` enqueues render + exchange + expand of this rank's frame
     block and returns the tensor that holds ALL frames of the clip afterwards (the same tensor every step)."""
 
-    def __init__(self, reproject, dataset, group=None, mode="auto", overlap_zero=True):
+    def __init__(self, reproject, dataset, group=None, mode="auto", overlap_clear=True):
         import torch
         import torch.distributed as dist
         self.rp, self.dataset, self.mode = reproject, dataset, mode
@@ -286,7 +292,7 @@ class SiteAssembler:
         self.exchange = PeerExchange(rt, int(int(most.item()) * 1.25) + 4096, fmt, group=group)
         self.available = self.exchange.available
         self.frames = None
-        self.zero_stream = torch.cuda.Stream(device=rt.device) if overlap_zero else None
+        self.render_stream = torch.cuda.Stream(device=rt.device, priority=-1) if overlap_clear else None
 
     def step(self, out=None):
         import torch
@@ -295,4 +301,4 @@ class SiteAssembler:
             if self.frames is None:
                 self.frames = torch.empty((self.n_frames, r.n_cams, r.height, r.width, 3), dtype=torch.uint8, device=self.rp.rt.device)
             out = self.frames
-        return self.exchange.render_and_assemble(r, self.res, self.w2c_dev, self.lo, self.n_frames, out, mode=self.mode, zero_stream=self.zero_stream)
+        return self.exchange.render_and_assemble(r, self.res, self.w2c_dev, self.lo, self.n_frames, out, mode=self.mode, render_stream=self.render_stream)

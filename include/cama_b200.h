@@ -346,12 +346,14 @@ int cama_peer_close(cama_ctx *ctx, void *dev_ptr);
  * `step` into the n slot headers (device pointers, own and peers'; host array). */
 int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t step, void *const *slot_headers, int n, void *stream);
 /* slots: host array of `world` device pointers, the slots of this rank's own mailbox that hold the records of rank
- * 0..world-1 for `step`.  Waits on the device until every slot carries `step` (at most timeout_ms, <= 0: 2000), then
- * writes the 8 pixels of every record into frames uint8 [n_frames,n_cams,H,W,3] (device, zero-filled by the caller).
- * status: device int32 [1], caller zero-fills once; set to 1 when a peer's step did not arrive in time (nothing is
- * written then), 2 when a slot held more records than capacity_records (frames incomplete).  palette_*: as
+ * 0..world-1 for `step`.  Slot after slot, starting with own_rank's: waits on the device until the slot carries `step`
+ * (at most timeout_ms in all, <= 0: 2000), then writes the 8 pixels of each of its records into frames uint8
+ * [n_frames,n_cams,H,W,3] (device, zero-filled by the caller, e.g. with cama_frames_clear).
+ * status: device int32 [1], caller zero-fills once; set to 1 when a peer's step did not arrive in time (its records are
+ * missing), 2 when a slot held more records than capacity_records (frames incomplete).  palette_*: as
  * cama_overlay_expand. */
-int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, uint32_t step, int64_t capacity_records, int format,
+int cama_frames_clear(cama_ctx *ctx, uint8_t *frames, size_t bytes, void *stream);   /* cudaMemsetAsync(frames, 0, bytes) on `stream` */
+int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, int own_rank, uint32_t step, int64_t capacity_records, int format,
                      const uint8_t *palette_bgr, void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams,
                      int height, int width, int timeout_ms, int32_t *status, void *stream);
 

@@ -705,3 +705,48 @@ def test_config3_site_properties(rt, tmp_path):
     assert bool((block == whole[100:140]).all())
     halves = torch.cat([rp.render_device("nuscenes", w2c=w2c[:160]), rp.render_device("nuscenes", w2c=w2c[160:])])
     assert bool((halves == whole).all())
+
+
+# ------------------------------------------------------------------ pixel / image boundaries of the float32 fast path
+@pytest.mark.parametrize("eps_set", [0, 1, 2])
+def test_pixel_boundary_fuzz(rt, eps_set):
+    """candidate_pixel (csrc/clip.cu) decides most pixels from a float32 estimate of q_x/q_z and takes the IEEE
+    division only within 4e-3 of an integer.  Seeded fuzz of exactly that boundary through the production kernel
+    (float32 vertices, BINNED, no debug outputs) against oracle.c: projected coordinates u = j + e, v = i + e with
+    e from +-1e-12 to +-6e-3 (one pair per camera, eight cameras), depths from 0.5 to 128 m, including u = 0 +- e and
+    u = W +- e (the image-border comparisons of cama/reproject.py:192-198) — built exactly: K = [[1024,0,cx+e],..]
+    with float64 principal points, x = (j - cx) z / 1024 exactly representable in float32 for z a power of two —
+    plus random depths and positions.  Discs are 5 px apart, so a centre off by one pixel changes the image."""
+    from cama_b200.batched import ClipRenderer
+    eps = [[1e-12, -1e-12, 1e-9, -1e-7, 1e-5, -1e-4, 3.9e-3, -4.1e-3],
+           [2e-3, -3e-3, 5e-3, -6e-3, 1e-3, -1e-11, 1e-10, -1e-8],
+           [4.0e-3, -4.0e-3, 2.9e-3, -5.1e-3, 0.0, 1e-13, -1e-13, 3e-6]][eps_set]
+    rng = np.random.default_rng(100 + eps_set)
+    cx0, cy0 = 100.0, 60.0
+    K = np.stack([np.array([[1024.0, 0, cx0 + e], [0, 1024.0, cy0 + (e if c % 2 else -e)], [0, 0, 1.0]]) for c, e in enumerate(eps)])
+    E = np.stack([np.eye(4)] * 8)
+    zs = 2.0 ** np.arange(-1, 8)                                   # 0.5 .. 128
+    jj, ii = np.meshgrid(np.arange(0, W + 1, 5), np.arange(0, H + 1, 5))   # includes u = W and v = H: never visible unless e < 0
+    jj, ii = jj.ravel().astype(np.float64), ii.ravel().astype(np.float64)
+    z = zs[(jj.astype(int) // 5 + ii.astype(int) // 5) % len(zs)]
+    exact = np.stack([(jj - cx0) * z / 1024.0, (ii - cy0) * z / 1024.0, z], axis=1).astype(np.float32)
+    assert np.array_equal(exact.astype(np.float64)[:, 0] * 1024.0 / z + cx0, jj)      # the construction is exact
+    zr = rng.uniform(0.5, 200.0, size=60000)
+    rand = np.stack([(rng.uniform(-3, W + 3, size=zr.size) - cx0) * zr / 1024.0, (rng.uniform(-3, H + 3, size=zr.size) - cy0) * zr / 1024.0, zr], axis=1).astype(np.float32)
+    pts = np.concatenate([exact, rand])
+    offs = np.array([0, len(exact) // 2, len(exact), len(pts)], np.int64)
+    classes = ["lane_marking", "Road_teeth", "lane_marking"]
+    box = [-1000, 1000, -1000, 1000, -1000, 1000]
+    w2c = np.stack([np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)])
+    w2c[1, 2, 3] = 0.0                                             # (second frame identical: two frames exercise the frame loop)
+    want, cc, vc = oracle_c.clip_render(pts, offs, bgr_of(classes), w2c, E, K, box, H, W)
+    r = ClipRenderer(E, K, H, W, box, device=0)
+    res = r.resident([{"class": c, "points": pts[offs[i]:offs[i + 1]]} for i, c in enumerate(classes)])
+    w2c_dev = to_dev(w2c.reshape(-1, 16))
+    for mode in ("binned", "plane"):
+        frames = r.render(res, w2c_dev, mode=mode).cpu().numpy()              # the production kernel: no debug outputs
+        diff = np.argwhere((frames != want).any(-1))
+        assert diff.size == 0, f"{mode}: {len(diff)} pixels differ, first at frame/cam/row/col {diff[0].tolist()} (eps {eps[diff[0][1]]})"
+    _, dbg = r.render(res, w2c_dev, mode="binned", debug=True)
+    assert np.array_equal(dbg["visible_counts"].cpu().numpy(), vc) and np.array_equal(dbg["crop_counts"].cpu().numpy(), cc)
+    assert int(vc.sum()) > 500_000

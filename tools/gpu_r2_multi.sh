@@ -3,6 +3,7 @@
 N=${1:-2}; TAG=${2:-r2m$N}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/${TAG}_check.log 2>&1; echo "check rc=$?"; grep -E "^\{|multi_gpu_check|Error|error" gpurun_out/${TAG}_check.log | tail -5
+timeout 300 $TR --master-port 29513 tools/peer_breakdown.py 2>/dev/null | grep "^{" | tee gpurun_out/${TAG}_breakdown.json
 timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps ${STEPS:-30} --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
 python - <<PY
 import json

@@ -23,3 +23,4 @@ for l in sys.stdin:
 "
  done
 done
+timeout 300 python tools/dropin_bench.py 2>&1 | tail -1 | tee gpurun_out/${TAG}_dropin.json
