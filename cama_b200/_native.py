@@ -55,7 +55,7 @@ class ClipDesc(Structure):
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
-        ("camera_table", c_void_p),
+        ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("reserved1", c_int32),
     ]
 
 

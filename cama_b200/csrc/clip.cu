@@ -260,7 +260,7 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
 // reserved a pool slot and a bucket rank with returning atomics per warp spent a quarter of its
 // time waiting for them; one that staged per CTA spent a third of it in the per-frame barrier.)
 #ifndef CAMA_PIPE_FRAMES_DEFAULT
-#define CAMA_PIPE_FRAMES_DEFAULT 80
+#define CAMA_PIPE_FRAMES_DEFAULT 160
 #endif
 #ifndef CAMA_GEO_MINB
 #define CAMA_GEO_MINB 4                    // resident CTAs per SM the geometry kernel is compiled for
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) geometry_cull_kernel(const double *__rest
 #define CAMA_GEO_UNIT_FRAMES_SITE 8
 #endif
 #ifndef CAMA_GEO_STATIC_PCT
-#define CAMA_GEO_STATIC_PCT 70
+#define CAMA_GEO_STATIC_PCT 60
 #endif
 
 template <int LAYOUT, bool BINNED, bool DEBUG, bool PINHOLE>
@@ -1506,7 +1506,8 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     // (with a work list the number of live units is only known on the device: everything is claimed dynamically there)
     a.static_units = site && p.mode == CAMA_CLIP_BINNED ? 0u : (unsigned)(warp_units * std::min(100, std::max(0, static_pct)) / 100);
     // persistent grid: every resident warp claims (32-vertex, 8-frame) units until none are left
-    static const int geo_ctas = getenv("CAMA_GEO_CTAS") ? std::max(1, atoi(getenv("CAMA_GEO_CTAS"))) : CAMA_GEO_MINB;      // experiment knob
+    static const int geo_ctas_env = getenv("CAMA_GEO_CTAS") ? std::max(1, atoi(getenv("CAMA_GEO_CTAS"))) : 0;      // experiment knob
+    const int geo_ctas = geo_ctas_env ? geo_ctas_env : d->geometry_ctas_per_sm > 0 ? std::min(d->geometry_ctas_per_sm, CAMA_GEO_MINB) : CAMA_GEO_MINB;
     const unsigned geo_grid = (unsigned)std::max<long long>(1, std::min<long long>((warp_units + 7) / 8, (long long)ctx->sm_count * geo_ctas));
     const bool f32 = d->vertex_layout == CAMA_VERTEX_F32X4;
     const bool debug = d->crop_counts || d->visible_counts || d->vu_dense;

@@ -232,7 +232,11 @@ class PeerExchange:
 
         def render_and_publish():
             if int(w2c_dev.shape[0]) > 0:
-                renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
+                saved, renderer.geometry_ctas_per_sm = renderer.geometry_ctas_per_sm, (3 if render_stream is not None else renderer.geometry_ctas_per_sm)
+                try:                                  # (three geometry CTAs per SM: the zero-fill runs beside them)
+                    renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
+                finally:
+                    renderer.geometry_ctas_per_sm = saved
             else:
                 self.count.zero_()
             N.check(N.lib().cama_peer_publish(rt.ctx, self.count.data_ptr(), self.step, headers, self.world, rt.stream()))

@@ -241,6 +241,11 @@ typedef struct cama_clip_desc {
     /* Optional culling aid: the table cama_camera_table_build made for THESE cameras, crop box and image size (a table
      * built for other ones is recognised by its signature and ignored).  Results are unchanged. */
     const void *camera_table;       /* device, CAMA_CAMERA_TABLE_BYTES, or NULL */
+    /* Resident CTAs per SM of the (persistent) geometry kernel; 0 = default (4, which takes every register of an SM).
+     * 3 leaves room for a memory-bound kernel of another stream — e.g. the zero-fill of the assembled frames of a
+     * frame-sharded clip — to run beside it. */
+    int32_t geometry_ctas_per_sm;
+    int32_t reserved1;
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
