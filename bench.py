@@ -520,7 +520,7 @@ def run_b200(args):
                                         "achieved": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9,
                                         "frac": (frame_bytes + vertex_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
                          "phase_ms": {name: float(np.mean(phases[:, i])) for i, name in enumerate(N.PHASE_NAMES)}},
-            "records": {k: int(stats[k]) for k in ("records_total", "records_per_frame_needed", "record_capacity")},
+            "records": {k: int(stats[k]) for k in ("records_total", "record_capacity_needed", "record_capacity")},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -25,7 +25,7 @@ OVERLAY_BGR, OVERLAY_PALETTE = 0, 1
 OVERLAY_RECORD_BYTES = {OVERLAY_BGR: 32, OVERLAY_PALETTE: 12}
 OVERLAY_DRAW, OVERLAY_BLANK, OVERLAY_DRAW_CHUNKS, OVERLAY_BLANK_CHUNKS = 0, 1, 2, 3
 CLIP_PHASES = 4
-PHASE_NAMES = ("prep", "geometry", "sort", "raster")
+PHASE_NAMES = ("prep", "geometry", "lists", "raster")
 ABI_VERSION = 3
 
 
@@ -36,7 +36,7 @@ class CamaError(RuntimeError):
 
 
 class CapacityError(CamaError):
-    """The record pool of a clip render overflowed; rerun with stats.records_per_frame_needed."""
+    """The record pool of a clip render overflowed; rerun with stats.record_capacity_needed."""
 
 
 class ClipDesc(Structure):
@@ -70,7 +70,7 @@ class VoxelGrid(Structure):
 
 class ClipStats(Structure):
     _fields_ = [
-        ("records_total", c_int64), ("records_per_frame_needed", c_int64), ("record_capacity", c_int64),
+        ("records_total", c_int64), ("record_capacity_needed", c_int64), ("record_capacity", c_int64),
         ("overflow", c_int32), ("mode", c_int32), ("band_rows", c_int32), ("n_bands", c_int32),
         ("overlay_records", c_int64),
     ]

@@ -212,7 +212,7 @@ class ClipRenderer:
             code = N.lib().cama_clip_stats_read(rt.ctx, ctypes.byref(desc), rt.ptr(ws), rt.stream(), ctypes.byref(stats))
             self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
             if code == N.CAMA_E_CAPACITY and attempt < 2:
-                capacity = int(stats.records_per_frame_needed * 1.1) + 1024
+                capacity = int(stats.record_capacity_needed * 1.1) + 1024
                 self.capacity[key] = capacity
                 if dbg:
                     dbg["crop_counts"].zero_()
@@ -279,7 +279,7 @@ class ClipRenderer:
             self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
             retry = False
             if code == N.CAMA_E_CAPACITY:
-                capacity = int(stats.records_per_frame_needed * 1.1) + 1024
+                capacity = int(stats.record_capacity_needed * 1.1) + 1024
                 self.capacity[key] = capacity
                 retry = True
             else:

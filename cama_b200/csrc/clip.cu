@@ -4,12 +4,12 @@
 //
 // Pipeline (BINNED mode, the throughput path):
 //   prep      w2c float32 -> float64 (exact), instance colours -> packed LUT
-//   geometry  FP64: world->chassis, crop box, 6 x (chassis->camera, K, /z, mask); every visible
-//             centre becomes a 4-byte record {ordinal+1 : 16 | pixel-in-band-plane : 16} tagged
-//             with its (frame, camera, row-band) bucket and its rank inside that bucket
-//   scan      exclusive scan of the bucket histogram
-//   scatter   records -> bucket order
-//   raster    one CTA per (frame, camera, band): uint16 centre plane in shared memory
+//   geometry  FP64: world->chassis, crop box, cameras x (chassis->camera, K, /z, mask); every visible
+//             centre becomes a 4-byte record {ordinal+1 : 16 | row in its band group : 16 - x_bits | x : x_bits}
+//             appended straight to the record list of its (frame, camera, band group) — a group is a few
+//             consecutive bands; lists have a fixed capacity and a cursor, no sort pass follows
+//   classify  the (frame, camera, band) work items of the raster by the weight of their list
+//   raster    one CTA per (frame, camera, band), reading the band's rows out of its group's list: uint16 centre plane in shared memory
 //             (atomic max of ordinals), L1-radius-2 max-dilation with packed u16x2 max,
 //             colour LUT, optional composite over a background, rows staged in shared memory
 //             and written with bulk async copies (cp.async.bulk shared -> global).
@@ -77,11 +77,11 @@ struct ClipArgs {
     unsigned *plane;                   // [F,C,H,W]
     // BINNED
     int band_rows, n_bands, x_bits;
-    unsigned band_magic;               // ceil(2^32 / band_rows): row / band_rows == umulhi(row, band_magic) for rows < 65536
-    long long pool_cap;                // records the pool holds
-    unsigned *pool_count;              // [1] records appended (attempted) so far
-    unsigned *hist;                    // [F*C*NB] records per bucket
-    uint2 *pool;                       // [pool_cap] {bucket, payload} in arrival order
+    int group_rows, n_groups;          // rows of a band group (band_rows * bands per group), groups per image
+    unsigned group_magic;              // ceil(2^32 / group_rows): row / group_rows == umulhi(row, group_magic) for rows < 65536
+    unsigned list_cap;                 // records a list holds
+    unsigned *cursor;                  // [F*C*n_groups] records appended (attempted) to each list so far (cleared by prep)
+    unsigned *records;                 // [F*C*n_groups][list_cap] payloads
 };
 
 // ------------------------------------------------------------------------------------------------ camera table
@@ -282,14 +282,6 @@ __device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, boo
     const unsigned mask = __ballot_sync(kFull, pred);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    const unsigned lead_bucket = __shfl_sync(kFull, bucket, leader);
-    const bool uniform = __ballot_sync(kFull, pred && bucket == lead_bucket) == mask;    // lanes = consecutive vertices of a polyline
-    if (uniform) {
-        if (lane == leader) atomicAdd(&a.hist[lead_bucket], (unsigned)__popc(mask));     // result unused: a reduction
-    } else if (pred) {
-        atomicAdd(&a.hist[bucket], 1u);
-    }
     const unsigned slot = st.count + __popc(mask & ((1u << lane) - 1u));                  // the warp owns its stage: no atomic
     if (pred) st.rec[slot] = make_uint2(bucket, payload);
     __syncwarp();
@@ -297,15 +289,35 @@ __device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, boo
     __syncwarp();
 }
 
-// Warp-wide: move the warp's staged records to the pool.
+// Warp-wide: move the warp's staged records {list, payload} to their lists.  32 records per round: match.any groups
+// the lanes of a list (staged records come in runs: one list per (frame, camera) of the warp's 32 vertices), the first
+// lane of every group reserves the group's places with ONE returning atomic on the list's cursor, and the atomics of
+// up to four rounds are in flight before the first result is used — the latency of a reservation is paid once per
+// flush (>= 128 records), not once per append.  Records past a list's capacity are dropped (the cursor keeps counting:
+// band_classify_kernel reports the overflow).
 __device__ __forceinline__ void stage_flush(const ClipArgs &a, GeoStage &st) {
     const int lane = threadIdx.x & 31;
     const unsigned n = st.count;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(a.pool_count, n);
-    const long long b = __shfl_sync(kFull, base, 0);
-    for (unsigned i = lane; i < n; i += 32)
-        if (b + i < a.pool_cap) a.pool[b + i] = st.rec[i];
+    const unsigned lt = (1u << lane) - 1u;
+    for (unsigned i0 = 0; i0 < n; i0 += 128u) {
+        uint2 r[4];
+        unsigned peers[4], first[4];
+        bool live[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned i = i0 + 32u * k + lane;
+            live[k] = i < n;
+            r[k] = live[k] ? st.rec[i] : make_uint2(0xffffffffu, 0u);
+            peers[k] = __match_any_sync(kFull, r[k].x);
+            first[k] = 0u;
+            if (live[k] && lane == __ffs(peers[k]) - 1) first[k] = atomicAdd(&a.cursor[r[k].x], (unsigned)__popc(peers[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned pos = __shfl_sync(kFull, first[k], __ffs(peers[k]) - 1) + (unsigned)__popc(peers[k] & lt);
+            if (live[k] && pos < a.list_cap) a.records[(size_t)r[k].x * a.list_cap + pos] = r[k].y;
+        }
+    }
     __syncwarp();
     if (lane == 0) st.count = 0;
     __syncwarp();
@@ -329,19 +341,20 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, GeoStage &st, int
         const int prev_ord = __shfl_up_sync(kFull, ord, 1);
         if ((threadIdx.x & 31) != 0 && prev_code == code && prev_ord == ord) vis = false;
         if (!__any_sync(kFull, vis)) return;
-        const int rb = a.band_rows;
-        const int b0 = (int)__umulhi((unsigned)vi, a.band_magic);   // vi / rb
-        const int r = vi - b0 * rb;
-        const unsigned bucket = (unsigned)((f * a.n_cams + c) * a.n_bands + b0);
+        const int rg = a.group_rows;
+        const int g0 = (int)__umulhi((unsigned)vi, a.group_magic);  // vi / rg
+        const int r = vi - g0 * rg;                                  // row inside the band group (stored + 2: rows -2, -1 belong to the halo)
+        const unsigned list = (unsigned)((f * a.n_cams + c) * a.n_groups + g0);
         const unsigned key = (unsigned)(ord + 1) << 16;
-        warp_append(a, st, vis, bucket, key | (unsigned)(((r + 2) << a.x_bits) | ui));
-        // the two rows next to a band edge also matter to the neighbouring band (dilation radius 2)
-        const bool up = vis && r < 2 && b0 > 0;
-        const bool down = vis && r >= rb - 2 && b0 + 1 < a.n_bands;
+        warp_append(a, st, vis, list, key | (unsigned)(((r + 2) << a.x_bits) | ui));
+        // the two rows next to a group edge also matter to the neighbouring group (dilation radius 2); band edges
+        // inside a group need nothing: the bands of a group read the same list
+        const bool up = vis && r < 2 && g0 > 0;
+        const bool down = vis && r >= rg - 2 && g0 + 1 < a.n_groups;
         if (__any_sync(kFull, up || down)) {
-            const unsigned bucket2 = up ? bucket - 1 : bucket + 1;
-            const int r2 = up ? r + rb : r - rb;
-            warp_append(a, st, up || down, bucket2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
+            const unsigned list2 = up ? list - 1 : list + 1;
+            const int r2 = up ? r + rg : r - rg;
+            warp_append(a, st, up || down, list2, key | (unsigned)(((r2 + 2) << a.x_bits) | ui));
         }
     }
 }
@@ -562,168 +575,54 @@ __global__ void __launch_bounds__(256) plane_raster_kernel(const unsigned *__res
     }
 }
 
-// ------------------------------------------------------------------------------------------------ BINNED: scan + scatter
+// ------------------------------------------------------------------------------------------------ BINNED: work lists of the raster
 struct ClipStatsDev {
-    unsigned long long records_total;
-    unsigned long long records_per_frame_needed;
+    unsigned long long records_total;      // appended to all lists (attempted)
+    unsigned long long list_max;           // the fullest list (attempted)
     unsigned overflow;
     unsigned pad;
 };
 
-// single CTA: start[b] = exclusive scan of hist, start[nb] = total; pool overflow check.
-// 8192 buckets per round (config 2 has 8160: one round): two 16-byte loads per thread, a warp scan, a
-// scan of the 32 warp totals.
-constexpr int kScanPerThread = 8;
-__global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, int nb,
-                                                           const unsigned *__restrict__ pool_count, int n_frames, long long pool_cap,
-                                                           ClipStatsDev *__restrict__ stats, unsigned *__restrict__ lists /* [4][nb] */,
-                                                           unsigned *__restrict__ list_counts /* [4] */) {
-    __shared__ unsigned warp_sum[32];
-    __shared__ unsigned s_cursor[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned carry = 0;                                            // same value in every thread
-    if (tid < 4) s_cursor[tid] = 0;
-    __syncthreads();
+// One thread per raster work item = (frame, camera, band).  The items are sorted into four work lists by the weight
+// of their band group's record list: >= kHeavy / >= kMedium / >= 1 records (claimed dynamically by the raster CTAs, in
+// this order) and empty ones (a band of an empty group has nothing to draw: its zeros are bulk stores).  Within a list
+// the order is whatever the warps' atomics make it.  The first group-count threads also fold the statistics: total
+// and largest list length, overflow.
+constexpr unsigned kHeavyList = 6144, kMediumList = 768;
+__global__ void __launch_bounds__(256) band_classify_kernel(const unsigned *__restrict__ cursor, int n_lists, int n_items, int n_bands, int group_bands,
+                                                            int n_groups, unsigned list_cap, ClipStatsDev *__restrict__ stats,
+                                                            unsigned *__restrict__ lists /* [4][n_items] */, unsigned *__restrict__ list_counts /* [4] */) {
+    const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
     pdl_wait();
     pdl_trigger();
-    const unsigned long long pool_total = tid == 0 ? (unsigned long long)*pool_count : 0ull;      // (in flight with the counts)
-    for (int base = 0; base < nb; base += 1024 * kScanPerThread) {
-        const int idx = base + kScanPerThread * tid;
-        unsigned vals[kScanPerThread];
-        if (idx + kScanPerThread <= nb) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(hist + idx), v1 = *reinterpret_cast<const uint4 *>(hist + idx + 4);
-            vals[0] = v0.x; vals[1] = v0.y; vals[2] = v0.z; vals[3] = v0.w;
-            vals[4] = v1.x; vals[5] = v1.y; vals[6] = v1.z; vals[7] = v1.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < kScanPerThread; ++e) vals[e] = idx + e < nb ? hist[idx + e] : 0u;
-        }
-        unsigned mine = 0;
-#pragma unroll
-        for (int e = 0; e < kScanPerThread; ++e) mine += vals[e];
-        // Work lists for the raster, one per weight class: buckets with >= 2048, >= 256, >= 1 records (claimed
-        // dynamically, heaviest class first) and the empty ones (dealt out statically).  The four per-class
-        // counts of a thread ride in two words, 16 bits each (<= 8 per thread, <= 256 per warp), so the warp
-        // scan of the record counts carries them along.
-        int cls[kScanPerThread];
-        unsigned cnt01 = 0, cnt23 = 0;                             // class counts, 16 bits each
-#pragma unroll
-        for (int e = 0; e < kScanPerThread; ++e) {
-            cls[e] = idx + e < nb ? (vals[e] == 0u ? 3 : vals[e] >= 2048u ? 0 : vals[e] >= 256u ? 1 : 2) : -1;
-            cnt01 += cls[e] == 0 ? 1u : cls[e] == 1 ? 0x10000u : 0u;
-            cnt23 += cls[e] == 2 ? 1u : cls[e] == 3 ? 0x10000u : 0u;
-        }
-        unsigned inc = mine, inc01 = cnt01, inc23 = cnt23;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(kFull, inc, d), t01 = __shfl_up_sync(kFull, inc01, d), t23 = __shfl_up_sync(kFull, inc23, d);
-            if (lane >= d) { inc += t; inc01 += t01; inc23 += t23; }
-        }
-        __syncthreads();                                           // warp_sum of the previous round is consumed
-        if (lane == 31) warp_sum[warp] = inc;
-        unsigned slot[4] = {0u, 0u, 0u, 0u};                       // one shared-memory atomic per warp and class
-        if (lane == 31) {
-            if (inc01 & 0xffffu) slot[0] = atomicAdd(&s_cursor[0], inc01 & 0xffffu);
-            if (inc01 >> 16) slot[1] = atomicAdd(&s_cursor[1], inc01 >> 16);
-            if (inc23 & 0xffffu) slot[2] = atomicAdd(&s_cursor[2], inc23 & 0xffffu);
-            if (inc23 >> 16) slot[3] = atomicAdd(&s_cursor[3], inc23 >> 16);
-        }
-        __syncthreads();
-        unsigned w = warp_sum[lane], wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(kFull, wi, d);
-            if (lane >= d) wi += t;
-        }
-        const unsigned warps_before = __shfl_sync(kFull, wi - w, warp);       // exclusive prefix of this warp's total
-        const unsigned round_total = __shfl_sync(kFull, wi, 31);
-        unsigned before = carry + warps_before + inc - mine;
-        if (idx + kScanPerThread <= nb) {
-            uint4 o0, o1;
-            o0.x = before; before += vals[0]; o0.y = before; before += vals[1]; o0.z = before; before += vals[2]; o0.w = before; before += vals[3];
-            o1.x = before; before += vals[4]; o1.y = before; before += vals[5]; o1.z = before; before += vals[6]; o1.w = before;
-            *reinterpret_cast<uint4 *>(start + idx) = o0;
-            *reinterpret_cast<uint4 *>(start + idx + 4) = o1;
-        } else {
-#pragma unroll
-            for (int e = 0; e < kScanPerThread; ++e) {
-                if (idx + e < nb) start[idx + e] = before;
-                before += vals[e];
-            }
-        }
-        carry += round_total;
-        const unsigned ex01 = inc01 - cnt01, ex23 = inc23 - cnt23;            // exclusive prefixes inside the warp
-        slot[0] = __shfl_sync(kFull, slot[0], 31) + (ex01 & 0xffffu);
-        slot[1] = __shfl_sync(kFull, slot[1], 31) + (ex01 >> 16);
-        slot[2] = __shfl_sync(kFull, slot[2], 31) + (ex23 & 0xffffu);
-        slot[3] = __shfl_sync(kFull, slot[3], 31) + (ex23 >> 16);
-#pragma unroll
-        for (int e = 0; e < kScanPerThread; ++e) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (cls[e] == j) lists[(size_t)j * nb + slot[j]++] = (unsigned)(idx + e);
-        }
+    int cls = -1;
+    if (i < n_items) {
+        const int image = i / n_bands, band = i - image * n_bands;
+        const unsigned n = cursor[image * n_groups + band / group_bands];
+        cls = n == 0u ? 3 : n >= kHeavyList ? 0 : n >= kMediumList ? 1 : 2;
     }
-    __syncthreads();
-    if (tid < 4) list_counts[tid] = s_cursor[tid];
-    if (tid == 0) {
-        start[nb] = carry;
-        const unsigned long long total = pool_total;
-        stats->records_total = total;
-        stats->records_per_frame_needed = n_frames > 0 ? (total + n_frames - 1) / n_frames : 0;    // the pool is shared by the frames of a pass: mean per frame
-        stats->overflow = total > (unsigned long long)pool_cap ? 1u : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned m = __ballot_sync(kFull, cls == j);
+        if (m == 0u) continue;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&list_counts[j], (unsigned)__popc(m));
+        base = __shfl_sync(kFull, base, __ffs(m) - 1);
+        if (cls == j) lists[(size_t)j * n_items + base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i;
     }
-}
-
-// pool (arrival order) -> sorted (bucket order).  A record's place inside its bucket is taken from
-// the bucket's count, counted down; runs of equal buckets (records of one warp) share one atomic.
-// Four independent records per thread keep four load -> atomic -> store chains in flight.
-#ifndef CAMA_SCATTER_PER_THREAD
-#define CAMA_SCATTER_PER_THREAD 4
-#endif
-#ifndef CAMA_SCATTER_CTAS_PER_SM
-#define CAMA_SCATTER_CTAS_PER_SM 16
-#endif
-constexpr int kScatterPerThread = CAMA_SCATTER_PER_THREAD;
-__global__ void __launch_bounds__(256) record_scatter_kernel(const uint2 *__restrict__ pool, const unsigned *__restrict__ pool_count, long long pool_cap,
-                                                            const unsigned *__restrict__ start, unsigned *__restrict__ hist, long long sorted_cap,
-                                                            unsigned *__restrict__ sorted) {
-    pdl_wait();
-    pdl_trigger();
-    const long long n = min((long long)*pool_count, pool_cap);
-    const int lane = threadIdx.x & 31;
-    const long long tile = 256 * kScatterPerThread;
-    for (long long i0 = (long long)blockIdx.x * tile; i0 < n; i0 += (long long)gridDim.x * tile) {
-        uint2 r[kScatterPerThread];
-        bool live[kScatterPerThread];
+    // statistics over the lists (threads 0 .. n_lists-1), one atomic per warp and quantity
+    unsigned long long mine = i < n_lists ? cursor[i] : 0ull;
+    unsigned long long total = mine, most = mine;
 #pragma unroll
-        for (int k = 0; k < kScatterPerThread; ++k) {
-            const long long i = i0 + k * 256 + threadIdx.x;
-            live[k] = i < n;
-            r[k] = live[k] ? pool[i] : make_uint2(0u, 0u);
-        }
-        // records of one geometry warp sit together, so a window of 32 holds a handful of runs:
-        // one atomic per distinct bucket (match.any groups the lanes), all four windows issued before any result is used
-        unsigned peers[kScatterPerThread], first[kScatterPerThread];
-#pragma unroll
-        for (int k = 0; k < kScatterPerThread; ++k) {
-            const unsigned mask = __ballot_sync(kFull, live[k]);
-            peers[k] = 0u; first[k] = 0u;
-            if (live[k]) {
-                peers[k] = __match_any_sync(mask, r[k].x);
-                if (lane == __ffs(peers[k]) - 1) first[k] = atomicSub(&hist[r[k].x], (unsigned)__popc(peers[k]));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kScatterPerThread; ++k) {
-            const unsigned mask = __ballot_sync(kFull, live[k]);
-            if (live[k]) {
-                const unsigned got = __shfl_sync(mask, first[k], __ffs(peers[k]) - 1);
-                const unsigned place = got - 1u - (unsigned)__popc(peers[k] & ((1u << lane) - 1u));
-                const long long pos = (long long)start[r[k].x] + place;
-                if (pos < sorted_cap) sorted[pos] = r[k].y;
-            }
-        }
+    for (int d = 16; d > 0; d >>= 1) {
+        total += __shfl_xor_sync(kFull, total, d);
+        const unsigned long long o = __shfl_xor_sync(kFull, most, d);
+        most = o > most ? o : most;
+    }
+    if (lane == 0 && total) {
+        atomicAdd(&stats->records_total, total);
+        atomicMax(&stats->list_max, most);
+        if (most > list_cap) atomicOr(&stats->overflow, 1u);
     }
 }
 
@@ -777,9 +676,10 @@ struct RasterArgs {
     int n_strips;                          // 64-px segments per row
     int debug;                             // CAMA_RASTER_DEBUG experiments: 2 = no colour lookup
     int image_base;                        // sparse output: index of the first (frame, camera) image of this launch inside the clip
-    long long sorted_cap;
-    const unsigned *start;                 // [n_items+1]
-    const unsigned *sorted;
+    int group_bands, n_groups;             // bands per band group, groups per image
+    unsigned list_cap;
+    const unsigned *cursor;                // [n_images * n_groups] records appended to each list
+    const unsigned *records;               // [n_images * n_groups][list_cap]
     const unsigned *lut;
     const uint8_t *bg;
     uint8_t *frames;
@@ -1022,14 +922,16 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
     }
     if (MODE == 0) fence_proxy_async_shared();   // the zeros are read by bulk stores
     __syncthreads();
-    pdl_wait();                                  // everything above overlapped the tail of the scatter kernel
+    pdl_wait();                                  // everything above overlapped the tail of the previous kernel
     pdl_trigger();
     if ((a.debug & 32) && tid == 0 && blockIdx.x < 4096) g_raster_timeline[3 * blockIdx.x] = global_ns();
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(kRasterThreads) : "memory"); };
 
-    auto scatter = [&](unsigned rec) {
-        // (the validity checks only matter after a capacity overflow, when the pool holds stale records)
-        const unsigned x = rec & x_mask, row = (rec & 0xffffu) >> a.x_bits, ord1 = rec >> 16;
+    // a record of the band group's list -> this band's plane, if its row is one of the band's (row_off = the band's first
+    // row inside the group; rows are stored + 2, so the band's window [row_off - 2, row_off + rows + 2) is plane rows 0 ..)
+    auto scatter = [&](unsigned rec, unsigned row_off) {
+        // (x and ordinal checks: the fetch pads with 0xffffffff, and a list past its capacity holds stale records)
+        const unsigned x = rec & x_mask, row = ((rec & 0xffffu) >> a.x_bits) - row_off, ord1 = rec >> 16;
         if (row < (unsigned)plane_rows && x < (unsigned)W && ord1 <= (unsigned)a.n_instances) {
             smem_max_u16(plane, row * (unsigned)W + x, ord1);
             const unsigned bit = 1u << row, g = x / kSegPx, off = x % kSegPx;
@@ -1042,7 +944,7 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const long long i = begin + tid + q * kRasterThreads;
-            rec[q] = i < end ? __ldg(a.sorted + i) : 0xffffffffu;
+            rec[q] = i < end ? __ldg(a.records + i) : 0xffffffffu;
         }
     };
 
@@ -1068,7 +970,11 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
     };
     auto bounds = [&](int item, long long &blo, long long &bhi) {
         blo = bhi = 0;
-        if (item >= 0) { blo = a.start[item]; bhi = min((long long)a.start[item + 1], a.sorted_cap); }
+        if (item >= 0) {                       // the list of the item's band group
+            const int image = item / a.n_bands, list = image * a.n_groups + (item - image * a.n_bands) / a.group_bands;
+            blo = (long long)list * a.list_cap;
+            bhi = blo + min(a.cursor[list], a.list_cap);
+        }
     };
     // The last dyn_empty_pct % of the empty list are not dealt: a CTA that has finished its active buckets claims
     // them two at a time until they are gone, so the CTAs that drew light buckets take store work off the ones
@@ -1121,15 +1027,16 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
             uint8_t *out_base = a.frames + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes;
             const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
             const unsigned chunk_base = (unsigned)((((size_t)(a.image_base + item0 / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
-            // 1. centres of this bucket -> plane (max ordinal per pixel) + hit masks
+            // 1. centres of this band (out of its group's list) -> plane (max ordinal per pixel) + hit masks
+            const unsigned row_off = (unsigned)(((item0 % a.n_bands) % a.group_bands) * a.band_rows);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) scatter(pre[q]);
+            for (int q = 0; q < 4; ++q) scatter(pre[q], row_off);
             // (16-byte fetches of four consecutive records per thread and a software-pipelined loop were both measured slower)
             for (long long base = lo + 4 * kRasterThreads; base < hi; base += 4 * kRasterThreads) {
                 unsigned rec[4];
                 fetch(base, hi, rec);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) scatter(rec[q]);
+                for (int q = 0; q < 4; ++q) scatter(rec[q], row_off);
             }
             sync_compute();
             // 2. cells: dilation + colour + store.  Every warp walks the row pairs (lane = segment): a ballot gives the
@@ -1306,13 +1213,15 @@ void fill_cam_block(CamBlock &cams, int n_cams, const double *chassis2cam, const
 struct ClipPlan {
     int mode;
     int band_rows, n_bands, x_bits;
+    int group_bands, n_groups;      // bands per band group (one record list per (frame, camera, group)), groups per image
     int n_strips;
-    long long cap;          // records per frame
-    int n_buckets;
+    long long cap;          // records per list
+    int n_buckets;          // raster work items: frames x cameras x bands
+    long long n_lists;
     size_t raster_smem;
     // workspace offsets
     size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
-    size_t off_counter, off_hist, off_start, off_stats, off_w2c64, off_lut, off_pool, off_sorted, off_plane, off_worklist, off_lists;
+    size_t off_counter, off_cursor, off_stats, off_w2c64, off_lut, off_records, off_plane, off_worklist, off_lists;
     long long geo_units;
     size_t total;
     // frame-group pipeline (BINNED): the clip is rendered as `groups` sub-clips of `group_frames` frames, each with
@@ -1325,6 +1234,7 @@ constexpr int kRasterCtasPerSm = 4;
 constexpr int kDynEmptyPerCta = 5;
 constexpr int kDynEmptyPct = 60;                 // measured on config 2: 0 % 78.5 us, 40 % 74.4, 60 % 73.4, 80 % 75.5, 100 % 78.6 (CAMA_RASTER_DYN_EMPTY)
 constexpr int kDefaultBandRows = 16;
+constexpr int kDefaultGroupBands = 3;          // bands that share one record list (48 rows at 960 px: the 6-bit row field of a record holds 60)
 bool BinnedSite(const cama_clip_desc *d, const cama_ctx *ctx, long long units) { return d->tile_bounds && units >= (long long)ctx->sm_count * 64; }
 
 template <bool BINNED>
@@ -1401,18 +1311,21 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
         CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
         p.n_buckets = (int)nb;
+        // band groups: a record stores its row inside the group (+ 2 halo rows either side) in 16 - x_bits bits
+        static const int max_group_bands = getenv("CAMA_GROUP_BANDS") ? std::max(1, atoi(getenv("CAMA_GROUP_BANDS"))) : kDefaultGroupBands;   // tuning knob
+        p.group_bands = (int)std::max<long long>(1, std::min<long long>(max_group_bands, ((1ll << (16 - x_bits)) - 4) / band_rows));
+        p.n_groups = (p.n_bands + p.group_bands - 1) / p.group_bands;
+        p.n_lists = (long long)d->n_frames * d->n_cams * p.n_groups;
         long long cap = d->record_capacity;
-        if (cap <= 0) cap = std::max<long long>(d->n_vertices, 4096);      // one visible camera per vertex and frame
-        CAMA_REQUIRE((long long)d->n_frames * cap < (1ll << 32), "record pool too large for 32-bit bucket offsets");
+        if (cap <= 0) cap = std::min<long long>(std::max<long long>(d->n_vertices / 4, 2048), 16384);   // per list; an overflow is reported and the caller reruns
+        CAMA_REQUIRE(cap < (1ll << 31), "record_capacity too large");
         p.cap = cap;
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         if (d->overlay_records) p.raster_smem += sizeof(OvStage) * kRasterWarps;
-        p.off_hist = take(sizeof(unsigned) * ((size_t)nb + 1));              // (directly after the counter block)
+        p.off_cursor = take(sizeof(unsigned) * ((size_t)p.n_lists + 1));    // (directly after the counter block: cleared with it)
         p.zero_bytes = off - p.off_zero;
-        p.off_start = take(sizeof(unsigned) * ((size_t)nb + 1));
-        p.off_lists = take(sizeof(unsigned) * 4 * (size_t)nb);             // bucket lists of the raster, one per weight class
-        p.off_pool = take(sizeof(uint2) * (size_t)d->n_frames * cap);
-        p.off_sorted = take(sizeof(unsigned) * (size_t)d->n_frames * cap);
+        p.off_lists = take(sizeof(unsigned) * 4 * (size_t)nb);             // work lists of the raster, one per weight class
+        p.off_records = take(sizeof(unsigned) * (size_t)p.n_lists * (size_t)cap);
     }
     p.total = std::max<size_t>(off, 256);
     p.groups = 1;
@@ -1532,13 +1445,13 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
 
     // BINNED (the workspace slice may be laid out for more frames than this pass has: the last frame group)
     const int n_buckets = d->n_frames * d->n_cams * p.n_bands;
-    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits; a.pool_cap = (long long)d->n_frames * p.cap;
-    a.band_magic = (unsigned)(((1ull << 32) + p.band_rows - 1) / p.band_rows);
-    a.pool_count = reinterpret_cast<unsigned *>(ws + p.off_counter) + 1;      // word 0 of the counter block is spare
-    a.hist = reinterpret_cast<unsigned *>(ws + p.off_hist);
-    a.pool = reinterpret_cast<uint2 *>(ws + p.off_pool);
-    unsigned *start = reinterpret_cast<unsigned *>(ws + p.off_start);
-    unsigned *sorted = reinterpret_cast<unsigned *>(ws + p.off_sorted);
+    const int n_lists = d->n_frames * d->n_cams * p.n_groups;
+    a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.x_bits = p.x_bits;
+    a.group_rows = p.band_rows * p.group_bands; a.n_groups = p.n_groups;
+    a.group_magic = (unsigned)(((1ull << 32) + a.group_rows - 1) / a.group_rows);
+    a.list_cap = (unsigned)p.cap;
+    a.cursor = reinterpret_cast<unsigned *>(ws + p.off_cursor);
+    a.records = reinterpret_cast<unsigned *>(ws + p.off_records);
     CAMA_CUDA_TRY(mark(1));
     if (units > 0) {
         NvtxRange nvtx_phase("geometry");
@@ -1565,16 +1478,10 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     unsigned *lists = reinterpret_cast<unsigned *>(ws + p.off_lists);
     unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
     {
-    NvtxRange nvtx_phase("sort");
-    CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, bucket_scan_kernel, 1, 1024, 0, s, a.hist, start, n_buckets, a.pool_count, d->n_frames, a.pool_cap, stats,
-                           lists, list_counts));
-    CAMA_LAUNCHED(ctx);
-    {   // grid-stride over the records appended; sized for the pool, capped at a few CTAs per SM slot
-        const long long tile = 256 * kScatterPerThread;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((a.pool_cap + tile - 1) / tile, (long long)ctx->sm_count * CAMA_SCATTER_CTAS_PER_SM));
-        CAMA_CUDA_TRY(launch_k(pdl, record_scatter_kernel, grid, 256, 0, s, a.pool, a.pool_count, a.pool_cap, start, a.hist, a.pool_cap, sorted));
-    }
-    CAMA_LAUNCHED(ctx);
+        NvtxRange nvtx_phase("classify");
+        CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, band_classify_kernel, (unsigned)((std::max(n_buckets, n_lists) + 255) / 256), 256, 0, s, a.cursor, n_lists, n_buckets,
+                               p.n_bands, p.group_bands, p.n_groups, a.list_cap, stats, lists, list_counts));
+        CAMA_LAUNCHED(ctx);
     }
     if (lanes_split) {
         CAMA_CUDA_TRY(cudaEventRecord(lanes.sort_done, s));
@@ -1585,10 +1492,10 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     NvtxRange nvtx_raster("raster");
     RasterArgs r{};
     r.n_items = n_buckets; r.n_bands = p.n_bands; r.band_rows = p.band_rows; r.height = d->height; r.width = d->width;
-    r.n_instances = d->n_instances; r.sorted_cap = (long long)d->n_frames * p.cap;
+    r.n_instances = d->n_instances; r.group_bands = p.group_bands; r.n_groups = p.n_groups; r.list_cap = (unsigned)p.cap;
     r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.image_base = image_base;
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
-    r.start = start; r.sorted = sorted; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    r.cursor = a.cursor; r.records = a.records; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     r.lists = lists; r.list_counts = list_counts;
     r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     r.empty_counter = reinterpret_cast<unsigned *>(ws + p.off_counter) + 3;
@@ -1784,11 +1691,11 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     unsigned overflow = 0;
     for (const ClipStatsDev &b : h) {
         total += b.records_total;
-        max_per_frame = std::max(max_per_frame, b.records_per_frame_needed);
+        max_per_frame = std::max(max_per_frame, b.list_max);
         overflow |= b.overflow;
     }
     out->records_total = (int64_t)total;
-    out->records_per_frame_needed = (int64_t)max_per_frame;
+    out->record_capacity_needed = (int64_t)max_per_frame;
     out->record_capacity = p.cap;
     out->overflow = (int32_t)overflow;
     out->mode = p.mode;
@@ -1796,7 +1703,7 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->n_bands = p.n_bands;
     out->overlay_records = sparse ? n_overlay : 0;
     if (overflow)
-        return fail(CAMA_E_CAPACITY, "record pool overflow: %llu records per frame needed, capacity %lld", max_per_frame, p.cap);
+        return fail(CAMA_E_CAPACITY, "record list overflow: the fullest list needs %llu records, capacity %lld", max_per_frame, p.cap);
     return CAMA_OK;
 }
 

@@ -54,7 +54,7 @@ typedef enum cama_status {
     CAMA_E_INVALID = -1,    /* bad argument (null pointer, negative size, misaligned buffer ...) */
     CAMA_E_CUDA = -2,       /* a CUDA runtime call failed; text in cama_last_error() */
     CAMA_E_WORKSPACE = -3,  /* caller's workspace is smaller than cama_*_workspace_bytes() */
-    CAMA_E_CAPACITY = -4,   /* clip path: record pool overflowed; rerun with the capacity in cama_clip_stats */
+    CAMA_E_CAPACITY = -4,   /* clip path: a record list overflowed; rerun with the capacity in cama_clip_stats */
     CAMA_E_NODEVICE = -5,   /* no CUDA device / not an sm_100 device */
     CAMA_E_UNSUPPORTED = -6 /* shape outside what the requested mode supports */
 } cama_status;
@@ -77,7 +77,7 @@ int cama_ctx_sm_count(const cama_ctx *ctx, int *count);
  * stream around its phases (no synchronisation, a few hundred ns each) until max_calls calls have
  * been recorded; max_calls = 0 disables and frees the events.  cama_ctx_profile_read waits for
  * call `call` (0-based since enable) to finish and returns the milliseconds of each phase. */
-#define CAMA_CLIP_PHASES 4 /* 0 prep + clears, 1 geometry, 2 bucket scan + scatter (BINNED), 3 raster */
+#define CAMA_CLIP_PHASES 4 /* 0 prep + clears, 1 geometry, 2 work lists of the raster (BINNED), 3 raster */
 int cama_ctx_profile_enable(cama_ctx *ctx, int max_calls);
 int cama_ctx_profile_calls(const cama_ctx *ctx, int *calls);
 int cama_ctx_profile_read(cama_ctx *ctx, int call, float *phase_ms /* [CAMA_CLIP_PHASES] */);
@@ -213,7 +213,8 @@ typedef struct cama_clip_desc {
     int32_t *crop_counts;           /* device int32 [n_frames,n_instances] or NULL; caller zero-fills */
     int32_t *visible_counts;        /* device int32 [n_frames,n_cams,n_instances] or NULL; caller zero-fills */
     double *vu_dense;               /* device float64 [n_frames,n_cams,n_vertices,2] or NULL; NaN where not visible */
-    int64_t record_capacity;        /* BINNED: centre records per frame the workspace is sized for; 0 = default */
+    int64_t record_capacity;        /* BINNED: centre records each (frame, camera, band group) list of the workspace holds;
+                                     * 0 = default (min(max(n_vertices / 4, 2048), 16384)) */
     /* Sparse output (BINNED mode, background must be NULL): when overlay_records != NULL the lit chunks are
      * appended there and `frames` is not written (and may be NULL).  What a host consumer needs crosses PCIe
      * as ~10 % of the dense bytes; the dense frames never exist. */
@@ -250,10 +251,9 @@ typedef struct cama_clip_desc {
 
 typedef struct cama_clip_stats {
     int64_t records_total;          /* centre records emitted (incl. band-halo duplicates) */
-    int64_t records_per_frame_needed; /* ceil(records_total / n_frames): the record_capacity (per frame; the pool is shared by
-                                     * all frames of a call) a rerun needs after an overflow */
-    int64_t record_capacity;        /* per-frame capacity this run used */
-    int32_t overflow;               /* != 0: some frame exceeded the capacity, frames are incomplete */
+    int64_t record_capacity_needed; /* length of the fullest record list: the record_capacity a rerun needs after an overflow */
+    int64_t record_capacity;        /* per-list capacity this run used */
+    int32_t overflow;               /* != 0: some list exceeded the capacity, frames are incomplete */
     int32_t mode;                   /* mode actually used (CAMA_CLIP_PLANE / CAMA_CLIP_BINNED) */
     int32_t band_rows;              /* BINNED: output rows per band */
     int32_t n_bands;

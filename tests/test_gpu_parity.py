@@ -329,12 +329,12 @@ def test_record_pool_overflow_is_detected_and_retried(rt):
     N.check(N.lib().cama_clip_render(r.rt.ctx, ctypes.byref(desc), r.rt.ptr(ws), ws.numel(), r.rt.stream()))
     stats = N.ClipStats()
     code = N.lib().cama_clip_stats_read(r.rt.ctx, ctypes.byref(desc), r.rt.ptr(ws), r.rt.stream(), ctypes.byref(stats))
-    assert code == N.CAMA_E_CAPACITY and stats.overflow == 1 and stats.records_per_frame_needed > 64
+    assert code == N.CAMA_E_CAPACITY and stats.overflow == 1 and stats.record_capacity_needed > 64
     # 2. the Python wrapper reruns with the reported capacity and gets the right frames
     r.capacity[(id(res), 3)] = 64
     frames = r.render(res, w2c, mode="binned")
     assert np.array_equal(frames.cpu().numpy(), g["frames"])
-    assert r.last_stats["overflow"] == 0 and r.last_stats["record_capacity"] >= stats.records_per_frame_needed
+    assert r.last_stats["overflow"] == 0 and r.last_stats["record_capacity"] >= stats.record_capacity_needed
 
 
 def test_abi_argument_errors(rt):

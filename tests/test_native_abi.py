@@ -37,7 +37,7 @@ def test_sass_is_sm100a_with_bulk_copy_and_fp64():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", B.ensure_built()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("DFMA", "UBLKCP", "VIMNMX3.U16x2", "ATOMS.CAS", "MUFU.RCP", "MATCH.ANY"):
+    for mnemonic in ("DFMA", "UBLKCP", "VIMNMX3.U16x2", "ATOMS.CAS", "MUFU.RCP", "MATCH.ANY", "REDUX"):
         assert mnemonic in sass, mnemonic
 
 
@@ -50,7 +50,12 @@ def test_descriptor_layout_and_workspace_query():
     need = ctypes.c_size_t()
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     binned = need.value
-    assert 40 * 100000 * 12 <= binned < 40 * 100000 * 12 + (1 << 22)      # 8-byte pool + 4-byte sorted records
+    lists = 40 * 6 * 12                                  # 34 bands of 16 rows in groups of 3 -> 12 record lists per image
+    assert lists * 16384 * 4 <= binned < lists * 16384 * 4 + (1 << 22)     # default capacity: 16384 4-byte records per list
+    d.record_capacity = 5000
+    N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
+    assert lists * 5000 * 4 <= need.value < lists * 5000 * 4 + (1 << 22)
+    d.record_capacity = 0
     d.mode = N.CLIP_PLANE
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     assert need.value >= 40 * 6 * 540 * 960 * 4

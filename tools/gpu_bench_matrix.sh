@@ -8,7 +8,7 @@ import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); ph=d['roofline']['phase_ms']
-        print('value %.0f  ms/step %.4f  geometry %.1f us  sort %.1f us  raster %.1f us  frac %.3f' % (d['value'], d['ms_per_step'], ph['geometry']*1e3, ph['sort']*1e3, ph['raster']*1e3, d['roofline']['frac']))
+        print('value %.0f  ms/step %.4f  geometry %.1f us  lists %.1f us  raster %.1f us  frac %.3f' % (d['value'], d['ms_per_step'], ph['geometry']*1e3, ph['lists']*1e3, ph['raster']*1e3, d['roofline']['frac']))
     else: print(l.rstrip()[-300:])
 "
 done

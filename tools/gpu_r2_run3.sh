@@ -19,7 +19,7 @@ import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); ph=d['roofline']['phase_ms']
-        print('value %.0f  ms/step %.4f single %.4f geometry %.1f us  sort %.1f us  raster %.1f us  frac %.3f whole %.3f e2e %.0f' % (d['value'], d['ms_per_step'], d['single_stream']['ms_per_step'], ph['geometry']*1e3, ph['sort']*1e3, ph['raster']*1e3, d['roofline']['frac'], d['roofline']['whole_step']['frac'], d['e2e']['value']))
+        print('value %.0f  ms/step %.4f single %.4f geometry %.1f us  lists %.1f us  raster %.1f us  frac %.3f whole %.3f e2e %.0f' % (d['value'], d['ms_per_step'], d['single_stream']['ms_per_step'], ph['geometry']*1e3, ph['lists']*1e3, ph['raster']*1e3, d['roofline']['frac'], d['roofline']['whole_step']['frac'], d['e2e']['value']))
 "
  done
 done
