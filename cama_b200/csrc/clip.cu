@@ -584,11 +584,11 @@ struct ClipStatsDev {
 };
 
 // One thread per raster work item = (frame, camera, band).  The items are sorted into four work lists by the weight
-// of their band group's record list: >= kHeavy / >= kMedium / >= 1 records (claimed dynamically by the raster CTAs, in
+// of their band group's record list: >= kHeavyBand / >= kMediumBand (per band of the group) / >= 1 records (claimed dynamically by the raster CTAs, in
 // this order) and empty ones (a band of an empty group has nothing to draw: its zeros are bulk stores).  Within a list
 // the order is whatever the warps' atomics make it.  The first group-count threads also fold the statistics: total
 // and largest list length, overflow.
-constexpr unsigned kHeavyList = 6144, kMediumList = 768;
+constexpr unsigned kHeavyBand = 2048, kMediumBand = 256;       // records per band of the group
 __global__ void __launch_bounds__(256) band_classify_kernel(const unsigned *__restrict__ cursor, int n_lists, int n_items, int n_bands, int group_bands,
                                                             int n_groups, unsigned list_cap, ClipStatsDev *__restrict__ stats,
                                                             unsigned *__restrict__ lists /* [4][n_items] */, unsigned *__restrict__ list_counts /* [4] */) {
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(256) band_classify_kernel(const unsigned *__re
     if (i < n_items) {
         const int image = i / n_bands, band = i - image * n_bands;
         const unsigned n = cursor[image * n_groups + band / group_bands];
-        cls = n == 0u ? 3 : n >= kHeavyList ? 0 : n >= kMediumList ? 1 : 2;
+        cls = n == 0u ? 3 : n >= kHeavyBand * (unsigned)group_bands ? 0 : n >= kMediumBand * (unsigned)group_bands ? 1 : 2;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1234,7 +1234,10 @@ constexpr int kRasterCtasPerSm = 4;
 constexpr int kDynEmptyPerCta = 5;
 constexpr int kDynEmptyPct = 60;                 // measured on config 2: 0 % 78.5 us, 40 % 74.4, 60 % 73.4, 80 % 75.5, 100 % 78.6 (CAMA_RASTER_DYN_EMPTY)
 constexpr int kDefaultBandRows = 16;
-constexpr int kDefaultGroupBands = 3;          // bands that share one record list (48 rows at 960 px: the 6-bit row field of a record holds 60)
+// Bands that share one record list.  1: every band has its own list and reads nothing it does not draw.  Larger groups
+// mean fewer, longer lists (less workspace, fewer halo duplicates) but every band scans its whole group: measured on
+// config 2, raster 81 us with 1, 90 with 2, 110 with 3 (CAMA_GROUP_BANDS).
+constexpr int kDefaultGroupBands = 1;
 bool BinnedSite(const cama_clip_desc *d, const cama_ctx *ctx, long long units) { return d->tile_bounds && units >= (long long)ctx->sm_count * 64; }
 
 template <bool BINNED>
@@ -1317,7 +1320,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         p.n_groups = (p.n_bands + p.group_bands - 1) / p.group_bands;
         p.n_lists = (long long)d->n_frames * d->n_cams * p.n_groups;
         long long cap = d->record_capacity;
-        if (cap <= 0) cap = std::min<long long>(std::max<long long>(d->n_vertices / 4, 2048), 16384);   // per list; an overflow is reported and the caller reruns
+        if (cap <= 0) cap = std::min<long long>(std::max<long long>(d->n_vertices / 4, 2048), 8192 * (long long)p.group_bands);   // per list; an overflow is reported and the caller reruns
         CAMA_REQUIRE(cap < (1ll << 31), "record_capacity too large");
         p.cap = cap;
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;

@@ -214,7 +214,7 @@ typedef struct cama_clip_desc {
     int32_t *visible_counts;        /* device int32 [n_frames,n_cams,n_instances] or NULL; caller zero-fills */
     double *vu_dense;               /* device float64 [n_frames,n_cams,n_vertices,2] or NULL; NaN where not visible */
     int64_t record_capacity;        /* BINNED: centre records each (frame, camera, band group) list of the workspace holds;
-                                     * 0 = default (min(max(n_vertices / 4, 2048), 16384)) */
+                                     * 0 = default (min(max(n_vertices / 4, 2048), 8192 per band of the group)) */
     /* Sparse output (BINNED mode, background must be NULL): when overlay_records != NULL the lit chunks are
      * appended there and `frames` is not written (and may be NULL).  What a host consumer needs crosses PCIe
      * as ~10 % of the dense bytes; the dense frames never exist. */

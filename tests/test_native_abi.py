@@ -50,8 +50,8 @@ def test_descriptor_layout_and_workspace_query():
     need = ctypes.c_size_t()
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     binned = need.value
-    lists = 40 * 6 * 12                                  # 34 bands of 16 rows in groups of 3 -> 12 record lists per image
-    assert lists * 16384 * 4 <= binned < lists * 16384 * 4 + (1 << 22)     # default capacity: 16384 4-byte records per list
+    lists = 40 * 6 * 34                                  # 34 bands of 16 rows, one record list each
+    assert lists * 8192 * 4 <= binned < lists * 8192 * 4 + (1 << 22)       # default capacity: 8192 4-byte records per list
     d.record_capacity = 5000
     N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
     assert lists * 5000 * 4 <= need.value < lists * 5000 * 4 + (1 << 22)

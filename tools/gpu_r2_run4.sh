@@ -3,7 +3,7 @@
 TAG=${1:-r2d}
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest_gpu.log
 {
-for E in "X=1" "CAMA_GROUP_BANDS=1" "CAMA_GROUP_BANDS=2"; do
+for E in "X=1" "CAMA_GEO_STAGE=1"; do
   env $E timeout 200 python tools/quick_bench.py --workload config2 --steps 40 --tag "config2 $E" 2>&1 | tail -1
   env $E timeout 200 python tools/quick_bench.py --workload config3 --steps 20 --tag "config3 $E" 2>&1 | tail -1
 done
