@@ -16,7 +16,7 @@ as are the compute-only figure and one GPU rendering the same site alone.
 
 One JSON line on rank 0:
   value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM; the K steps are dealt
-               over --lanes CUDA streams (default 2: independent clips overlap); single_stream = one stream
+               over --lanes CUDA streams (default 3: independent clips overlap); single_stream = one stream
   e2e          same metric through Reproject.__call__: host pose lookup + float32 inverse, H2D of
                the poses, render, lit-chunk records back over PCIe and drawn into the host frames
                (e2e.dense: every frame byte copied back instead)
@@ -57,7 +57,11 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="CUDA streams the K steps are dealt over (independent clips overlap); 1 = one stream")
+    ap.add_argument("--lanes", type=int, default=3, help="CUDA streams the K steps are dealt over (independent clips overlap); 1 = one stream")
+    ap.add_argument("--geometry-ctas", type=int, default=3,
+                    help="resident geometry CTAs per SM while clips overlap on several streams (cama_clip_desc.geometry_ctas_per_sm; 4 takes every "
+                         "register of an SM, 3 lets raster CTAs of another clip in); the single-stream loops use the library default")
+    ap.add_argument("--raster-ctas", type=int, default=0, help="cama_clip_desc.raster_ctas_per_sm for the overlapping clips (0 = library default)")
     ap.add_argument("--ramp-seconds", type=float, default=0.4, help="untimed clock-ramp loop before the warm-up (0 under ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded cpu_baseline sample")
     return ap.parse_args()
@@ -246,6 +250,15 @@ def run_reference(args):
             runner.close()
 
 
+def host_memory_probe(threads):
+    """STREAM-like fill / copy bandwidth of this process's host threads (cama_host_bandwidth_probe), GB/s."""
+    import ctypes
+    from cama_b200 import _native as N
+    fill, copy = ctypes.c_double(), ctypes.c_double()
+    N.check(N.lib().cama_host_bandwidth_probe(512 << 20, int(threads), ctypes.byref(fill), ctypes.byref(copy)))
+    return fill.value, copy.value
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     rank, local_rank, world = dist_env()
@@ -284,7 +297,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def step(occupancy=(0, 0)):
+        rp.renderer.geometry_ctas_per_sm, rp.renderer.raster_ctas_per_sm = occupancy
         rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=False)
 
     # Throughput mode: the K steps are dealt over `lanes` streams, each with its own workspace and output frames,
@@ -293,7 +307,10 @@ def run_b200(args):
     lane_streams = [torch.cuda.Stream(device=rt.device) for _ in range(n_lanes)]
     lane_frames = [frames] + [torch.empty_like(frames) for _ in range(n_lanes - 1)]
 
+    overlap_occupancy = (args.geometry_ctas, args.raster_ctas) if n_lanes > 1 else (0, 0)
+
     def lane_step(k):
+        rp.renderer.geometry_ctas_per_sm, rp.renderer.raster_ctas_per_sm = overlap_occupancy
         lane = k % n_lanes
         with torch.cuda.stream(lane_streams[lane]):
             rp.renderer.render(res, w2c_dev, out=lane_frames[lane], mode=args.mode, check=False, lane=lane)
@@ -346,7 +363,7 @@ def run_b200(args):
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        step()
+        step((0, 0))
     ev1.record(stream)
     barrier()
     ms_single = ev0.elapsed_time(ev1)
@@ -358,13 +375,14 @@ def run_b200(args):
     barrier()
     ev2.record(stream)
     for _ in range(args.steps):
-        step()
+        step(overlap_occupancy)
     ev3.record(stream)
     barrier()
     sampler.load(False)
     ms_instrumented = ev2.elapsed_time(ev3)
     phases = rt.profile_read()                      # [K, 4] ms
     rt.profile_enable(0)
+    rp.renderer.geometry_ctas_per_sm = rp.renderer.raster_ctas_per_sm = 0       # (library defaults for everything below)
 
     # ---- end to end through the public call: host poses -> finished frames in host memory.
     # Default transfer: the lit 8-pixel chunks cross PCIe and libcama_b200's host routine draws them into
@@ -392,6 +410,7 @@ def run_b200(args):
     dense_s, checksum_dense, transfer_dense = e2e_loop("dense", max(3, e2e_steps // 2))
     dense_steps = max(3, e2e_steps // 2)
     assert checksum == checksum_dense, "sparse and dense transfers disagree"
+    host_fill_gbs, host_copy_gbs = host_memory_probe(rp.host_threads)
 
     # ---- the zero-change drop-in path: the three calls unmodified main.py makes per frame (main.py:57-59), host lists of
     # NumPy arrays in and out as the reference's protocol demands, one process
@@ -486,7 +505,7 @@ def run_b200(args):
                        "l2": f"no flush needed: every step writes {frame_bytes / 1e6:.0f} MB of frames (> 126 MB L2); "
                              f"the {res.n_vertices * 16 / 1e6:.1f} MB vertex array is L2-resident by nature (re-read for each of the {F} frames)",
                        "background": "blank (black) frames, as in the reference CPU timing",
-                       "streams": n_lanes,
+                       "streams": n_lanes, "geometry_ctas_per_sm": overlap_occupancy[0] or 4, "raster_ctas_per_sm": overlap_occupancy[1] or 4,
                        "streams_note": f"the K steps are dealt over {n_lanes} CUDA streams with separate workspaces and output frames (independent clips "
                                        "overlap); single_stream = the same K steps back to back on one stream"},
             "single_stream": {"value": world * cam_frames / (ms_single / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_single / args.steps},
@@ -499,6 +518,10 @@ def run_b200(args):
                             "cama_overlay_apply_host blanks the previous overlay (helper thread, during the former) and draws the new one "
                             "into the host frames [F,C,540,960,3]",
                     "transfer": "sparse", "overlay_records": int(transfer["records"]), "checksum": checksum,
+                    "host_memory": {"fill_gbs": host_fill_gbs, "copy_gbs": host_copy_gbs, "threads": int(rp.host_threads),
+                                    "line_traffic_bytes_per_step": int(transfer["records"]) * 2 * 128,
+                                    "note": "the call is bound by the host's memory system: every lit chunk is blanked and drawn, each time a read-for-ownership "
+                                            "and a write-back of a 64-byte line of the 373 MB host frames; fill/copy = STREAM-like figures of the same worker pool"},
                     "host_draw_threads": int(rp.host_threads), "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,
                               "d2h_bytes_per_step": int(frame_bytes), "d2h_gbs": frame_bytes * dense_steps / dense_s / 1e9,
@@ -677,8 +700,11 @@ def run_b200_sharded(args):
     e2e_steps = max(3, min(args.steps, 20))
     e2e_s, e2e_sum, transfer = e2e_loop(e2e_steps)
     e2e_s = max_over_ranks(e2e_s)
-    sums = torch.tensor([e2e_sum], dtype=torch.int64, device=rt.device)
+    sums = torch.tensor([e2e_sum, int(transfer["records"])], dtype=torch.int64, device=rt.device)
     dist.all_reduce(sums)
+    barrier()                                                          # every rank probes at the same time: the contended figure
+    host_bw = torch.tensor(host_memory_probe(rp.host_threads), dtype=torch.float64, device=rt.device)
+    dist.all_reduce(host_bw)
     clocks = sampler.stop()
 
     if rank == 0:
@@ -722,7 +748,12 @@ def run_b200_sharded(args):
                     "call": "every rank: cama_b200.batched.Reproject.__call__(dataset, frame_range=its block): host pose seek + float32 inverse, "
                             "H2D of the poses from pinned memory, cama_clip_render (sparse output), D2H of the lit-chunk records, "
                             "cama_overlay_apply_host into the rank's host frames; the site's frames end up in host memory once, split over the ranks",
-                    "checksum_all_ranks": int(sums.item()), "host_draw_threads_per_rank": int(rp.host_threads),
+                    "checksum_all_ranks": int(sums[0].item()), "host_draw_threads_per_rank": int(rp.host_threads),
+                    "host_memory": {"fill_gbs_all_ranks": float(host_bw[0].item()), "copy_gbs_all_ranks": float(host_bw[1].item()),
+                                    "line_traffic_bytes_per_step": int(sums[1].item()) * 2 * 128,
+                                    "bound_ms_per_step": int(sums[1].item()) * 2 * 128 / max(float(host_bw[1].item()), 1e-9) / 1e6,
+                                    "note": "host-DRAM bound: every lit chunk is blanked and drawn, each a read-for-ownership + write-back of a 64-byte line; "
+                                            "all ranks share the box's memory system (fill/copy: STREAM-like figures of all ranks' worker pools at once)"},
                     "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "zero-fill of the assembled frames (cudaMemset via torch) + peer_expand_kernel: every frame byte of the site written once per rank",

@@ -55,7 +55,7 @@ class ClipDesc(Structure):
         ("overlay_records", c_void_p), ("overlay_count", c_void_p), ("overlay_capacity", c_int64),
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
-        ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("reserved1", c_int32),
+        ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("raster_ctas_per_sm", c_int32),
     ]
 
 
@@ -97,6 +97,8 @@ SIGNATURES = {
     "cama_render_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "cama_render_points": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                    c_size_t, c_void_p]),
+    "cama_render_points_overlay": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64,
+                                           c_void_p, c_size_t, c_void_p]),
     "cama_densify_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float, c_void_p, c_void_p]),
     "cama_densify_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int] + [ctypes.c_float] * 5
                           + [c_void_p, c_void_p]),
@@ -117,6 +119,7 @@ SIGNATURES = {
     "cama_frames_clear": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cama_peer_expand": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_uint32, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cama_host_bandwidth_probe": (c_int, [c_int64, c_int, POINTER(c_double), POINTER(c_double)]),
     "cama_overlay_expand": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -106,6 +106,7 @@ class ClipRenderer:
         self.last_stats = None
         self._camera_table = None     # cama_camera_table_build output for this rig (built on first use)
         self.geometry_ctas_per_sm = 0 # cama_clip_desc.geometry_ctas_per_sm (0 = library default)
+        self.raster_ctas_per_sm = 0   # cama_clip_desc.raster_ctas_per_sm (0 = library default; 3 when independent clips run on several streams)
 
     def camera_table(self):
         """Device table of the cameras that can see each cell of the crop box (cama_camera_table_build); static per rig."""
@@ -149,6 +150,7 @@ class ClipRenderer:
         d.warp_bounds = res.warp_bounds.data_ptr() if getattr(res, "warp_bounds", None) is not None else None
         d.camera_table = self.camera_table().data_ptr()
         d.geometry_ctas_per_sm = int(self.geometry_ctas_per_sm)
+        d.raster_ctas_per_sm = int(self.raster_ctas_per_sm)
         if overlay is not None:
             if isinstance(overlay, dict):            # raw pointers (a mailbox slot of shard.PeerExchange)
                 d.overlay_records, d.overlay_count = overlay["records_ptr"], overlay["count_ptr"]

@@ -488,18 +488,18 @@ __global__ void __launch_bounds__(kGeoThreads, CAMA_GEO_MINB) clip_geometry_kern
         }
         const int nf = min(kUnitFrames, a.n_frames - f0);
         if (tile < n_tiles && nf > 0 && frame_mask) {
-            __syncwarp();
-            for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
-            __syncwarp();
-            if (a.warp_bounds)
-                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.warp_bounds + (size_t)tile * 6, sT[lane & (kGeoFrames - 1)], cams.box));
-            else if (!a.worklist && a.tile_bounds)                            // (with a work list the cull kernel has made the mask)
-                frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(a.tile_bounds + (size_t)(tile >> 3) * 6, sT[lane & (kGeoFrames - 1)], cams.box));
+            // which of the unit's frames can the warp's 32 vertices matter to?  lane = frame, poses straight from global
+            // memory (L1): seven units in ten end here, and only the others stage their poses in shared memory
+            const double *bounds = a.warp_bounds ? a.warp_bounds + (size_t)tile * 6 : (!a.worklist && a.tile_bounds) ? a.tile_bounds + (size_t)(tile >> 3) * 6 : nullptr;
+            if (bounds) frame_mask &= __ballot_sync(kFull, lane < nf && tile_may_survive(bounds, a.w2c64 + (size_t)(f0 + (lane & (kGeoFrames - 1))) * 12, cams.box));
             frame_mask &= (1u << nf) - 1u;
         } else {
             frame_mask = 0u;
         }
         if (frame_mask) {
+            __syncwarp();
+            for (int i = lane; i < nf * 12; i += 32) (&sT[0][0])[i] = a.w2c64[(size_t)f0 * 12 + i];
+            __syncwarp();
             const long long n = (long long)tile * 32 + lane;
             double vx, vy, vz;
             int ord;
@@ -1506,7 +1506,8 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     static const int dyn_empty_per_cta = getenv("CAMA_RASTER_DYN_PER_CTA") ? std::max(0, atoi(getenv("CAMA_RASTER_DYN_PER_CTA"))) : kDynEmptyPerCta;
     r.dyn_empty_pct = dyn_empty_pct;
     r.dyn_empty_per_cta = dyn_empty_per_cta;
-    static const int raster_ctas = getenv("CAMA_RASTER_CTAS") ? std::max(1, atoi(getenv("CAMA_RASTER_CTAS"))) : kRasterCtasPerSm;      // experiment knob
+    static const int raster_ctas_env = getenv("CAMA_RASTER_CTAS") ? std::max(1, atoi(getenv("CAMA_RASTER_CTAS"))) : 0;      // experiment knob
+    const int raster_ctas = raster_ctas_env ? raster_ctas_env : d->raster_ctas_per_sm > 0 ? std::min(d->raster_ctas_per_sm, kRasterCtasPerSm) : kRasterCtasPerSm;
     const unsigned raster_grid = (unsigned)std::min<long long>(n_buckets, (long long)ctx->sm_count * raster_ctas);
     const bool rpdl = pdl && !lanes_split;
     if (d->overlay_records) {

@@ -174,6 +174,48 @@ __global__ void __launch_bounds__(kBlock) render_dilate_kernel(const unsigned *_
     }
 }
 
+// The same dilation, but instead of writing into a device image: one thread per 8-pixel chunk, and every chunk with a
+// painted pixel becomes a cama_overlay_record {chunk, mask, 24 BGR bytes} (one returning atomic per warp).  A host
+// image then gets exactly the bytes render_dilate_kernel would have changed (cama_overlay_apply_host, DRAW) without
+// crossing PCIe twice.
+__global__ void __launch_bounds__(kBlock) render_chunks_kernel(const unsigned *__restrict__ plane, const uint8_t *__restrict__ inst_bgr, int height, int width,
+                                                              cama_overlay_record *__restrict__ records, unsigned *__restrict__ count, long long capacity) {
+    const long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const int chunks_per_row = width >> 3;
+    const bool in_range = q < (long long)height * chunks_per_row;
+    cama_overlay_record rec;
+    rec.chunk = (uint32_t)q;
+    rec.mask = 0u;
+    if (in_range) {
+        const int y = (int)(q / chunks_per_row), x0 = (int)(q % chunks_per_row) * 8;
+        const int pw = width + 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned *c = plane + (size_t)(y + 2) * pw + (x0 + k + 2);
+            unsigned m = c[0];
+            m = max(m, max(max(c[-1], c[1]), max(c[-2], c[2])));
+            m = max(m, max(max(c[-pw - 1], c[-pw]), c[-pw + 1]));
+            m = max(m, max(max(c[pw - 1], c[pw]), c[pw + 1]));
+            m = max(m, max(c[-2 * pw], c[2 * pw]));
+            rec.bgr[3 * k] = rec.bgr[3 * k + 1] = rec.bgr[3 * k + 2] = 0;
+            if (m) {
+                const uint8_t *col = inst_bgr + 3 * (size_t)(m - 1);
+                rec.bgr[3 * k] = col[0]; rec.bgr[3 * k + 1] = col[1]; rec.bgr[3 * k + 2] = col[2];
+                rec.mask |= 1u << k;
+            }
+        }
+    }
+    const bool lit = rec.mask != 0u;
+    const unsigned votes = __ballot_sync(0xffffffffu, lit);
+    if (votes == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(votes) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(votes));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const long long slot = (long long)base + __popc(votes & ((1u << lane) - 1u));
+    if (lit && slot < capacity) records[slot] = rec;
+}
+
 static int fill_op(PointOp &op, const void *pts, int is_f32, int64_t n, const double *T) {
     op.pts = pts;
     op.n = n;
@@ -393,6 +435,33 @@ int cama_render_points(cama_ctx *ctx, const double *vu, int64_t n, const int64_t
     CAMA_LAUNCHED(ctx);
     const long long px = (long long)height * width;
     render_dilate_kernel<<<(unsigned)((px + kBlock - 1) / kBlock), kBlock, 0, s>>>(plane, inst_bgr, image, height, width);
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+int cama_render_points_overlay(cama_ctx *ctx, const double *vu, int64_t n, const int64_t *in_offsets, int64_t n_inst, const uint8_t *inst_bgr,
+                               int height, int width, cama_overlay_record *records, uint32_t *count, int64_t capacity, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+    CAMA_REQUIRE(ctx && count, "NULL argument");
+    CAMA_REQUIRE(n >= 0 && n_inst >= 0 && width > 0 && height > 0 && capacity >= 0, "bad size");
+    CAMA_REQUIRE(width % 8 == 0, "the overlay form needs a width that is a multiple of 8 (chunks never straddle a row)");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CAMA_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
+    if (n == 0) return CAMA_OK;
+    CAMA_REQUIRE(vu && in_offsets && inst_bgr && n_inst > 0 && (records || capacity == 0), "NULL buffer");
+    CAMA_REQUIRE(n_inst < (int64_t)UINT_MAX, "too many instances");
+    CAMA_REQUIRE(((uintptr_t)records & 15) == 0, "records must be 16-byte aligned");
+    size_t need = 0;
+    cama_render_workspace_bytes(height, width, &need);
+    if (workspace_bytes < need || !workspace) return fail(CAMA_E_WORKSPACE, "render workspace: need %zu bytes, got %zu", need, workspace_bytes);
+    unsigned *plane = static_cast<unsigned *>(workspace);
+    CAMA_CUDA_TRY(cudaMemsetAsync(plane, 0, sizeof(unsigned) * (size_t)(height + 4) * (width + 4), s));
+    render_scatter_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>(vu, n, reinterpret_cast<const long long *>(in_offsets), n_inst,
+                                                                                  plane, height, width);
+    CAMA_LAUNCHED(ctx);
+    const long long chunks = (long long)height * (width / 8);
+    render_chunks_kernel<<<(unsigned)((chunks + kBlock - 1) / kBlock), kBlock, 0, s>>>(plane, inst_bgr, height, width, records, count, capacity);
     CAMA_LAUNCHED(ctx);
     return CAMA_OK;
 }

@@ -3,6 +3,8 @@
 // pixels whose colour is already decided), either plain [F,C,H,W,3] frames or the 2x3 camera mosaic of
 // /root/reference/cama/tools.py:22-25.  Pure byte movement, on the library's worker pool (host_pool.h).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -305,6 +307,48 @@ extern "C" int cama_overlay_apply_host(const void *records, int64_t n, int forma
         PalJob job{rec, n, &t, op, pair};
         HostPool::instance().run(threads, n, kHostChunk, apply_pal_range, &job);
     }
+    return CAMA_OK;
+}
+
+// STREAM-like probe of what the host's memory system gives the worker pool: a parallel fill and a parallel copy over
+// buffers far larger than the caches.  bench.py quotes it next to the end-to-end figure, which is bound by exactly this
+// (every lit chunk of the host frames is a read-for-ownership and a write-back of a cache line, twice per call).
+namespace {
+struct ProbeJob {
+    unsigned char *a, *b;
+    int op;
+};
+void probe_range(void *ctx, int64_t lo, int64_t hi) {
+    const ProbeJob &j = *static_cast<const ProbeJob *>(ctx);
+    if (j.op == 0) memset(j.a + lo, 1, (size_t)(hi - lo));
+    else memcpy(j.b + lo, j.a + lo, (size_t)(hi - lo));
+}
+}  // namespace
+
+extern "C" int cama_host_bandwidth_probe(int64_t bytes, int n_threads, double *fill_gbs, double *copy_gbs) {
+    CAMA_REQUIRE(bytes >= (1 << 20) && fill_gbs && copy_gbs, "bad argument");
+    int threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    unsigned char *a = static_cast<unsigned char *>(malloc((size_t)bytes)), *b = static_cast<unsigned char *>(malloc((size_t)bytes));
+    if (!a || !b) {
+        free(a); free(b);
+        return fail(CAMA_E_INVALID, "cama_host_bandwidth_probe: out of host memory");
+    }
+    ProbeJob job{a, b, 0};
+    const int64_t chunk = 1 << 20;
+    auto seconds = [&](int op) {
+        job.op = op;
+        double best = 1e30;
+        for (int rep = 0; rep < 4; ++rep) {                    // (the first pass also faults the pages in)
+            const auto t0 = std::chrono::steady_clock::now();
+            HostPool::instance().run(threads, bytes, chunk, probe_range, &job);
+            best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+        return best;
+    };
+    *fill_gbs = (double)bytes / seconds(0) / 1e9;               // bytes written
+    seconds(1);
+    *copy_gbs = 2.0 * (double)bytes / seconds(1) / 1e9;         // bytes read + bytes written
+    free(a); free(b);
     return CAMA_OK;
 }
 

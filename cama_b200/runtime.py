@@ -232,7 +232,11 @@ class Runtime:
         return d_out[:int(out_off[-1])].cpu().numpy(), out_off
 
     def render_points(self, image, vu_flat, offsets, inst_bgr):
-        """cama_render_points: stamps into ``image`` (uint8 HxWx3 numpy) in place and returns it."""
+        """render_maps on a host image (uint8 HxWx3 numpy): stamps in place and returns it.
+
+        The image itself never crosses PCIe when its width is a multiple of 8 (and it is writeable and contiguous):
+        cama_render_points_overlay returns the lit 8-pixel chunks (~160 KB for a 540x960 frame of config 2) and
+        cama_overlay_apply_host draws them into ``image``.  Otherwise: upload, cama_render_points, download."""
         torch = _torch()
         assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3, "image must be uint8 [H,W,3]"
         vu = np.ascontiguousarray(vu_flat, dtype=np.float64)
@@ -240,13 +244,26 @@ class Runtime:
         if n == 0:
             return image
         height, width = image.shape[:2]
-        d_img = self.to_device(image)
         d_vu = self.to_device(vu)
         d_off = self.to_device(offsets, np.int64)
         d_bgr = self.to_device(inst_bgr, np.uint8)
         need = ctypes.c_size_t()
         N.check(N.lib().cama_render_workspace_bytes(height, width, ctypes.byref(need)))
         ws = self.scratch("render", need.value)
+        if width % 8 == 0 and image.flags.writeable and image.flags.c_contiguous:
+            capacity = height * (width // 8)
+            records = self.scratch("render_records", capacity * 32)
+            count = self.scratch_tensor("render_count", (4,), torch.int32)
+            N.check(N.lib().cama_render_points_overlay(self.ctx, self.ptr(d_vu), n, self.ptr(d_off), n_inst, self.ptr(d_bgr), height, width,
+                                                       self.ptr(records), self.ptr(count), capacity, self.ptr(ws), need.value, self.stream()))
+            lit = int(count[:1].cpu().item())                            # (synchronises)
+            if lit:
+                host = self._pinned_records(lit)
+                host[:lit * 32].copy_(records[:lit * 32])
+                target = N.OverlayTarget(image.ctypes.data, 1, 1, height, width, 0, None)
+                N.check(N.lib().cama_overlay_apply_host(host.data_ptr(), lit, N.OVERLAY_BGR, None, ctypes.byref(target), N.OVERLAY_DRAW, 1))
+            return image
+        d_img = self.to_device(image)
         N.check(N.lib().cama_render_points(self.ctx, self.ptr(d_vu), n, self.ptr(d_off), n_inst, self.ptr(d_bgr), self.ptr(d_img),
                                            height, width, self.ptr(ws), need.value, self.stream()))
         result = d_img.cpu().numpy()
@@ -254,6 +271,14 @@ class Runtime:
             image[...] = result            # the reference draws in place (cv2.circle mutates its argument)
             return image
         return result
+
+    def _pinned_records(self, n_records):
+        torch = _torch()
+        buf = self._scratch.get("render_records_host")
+        if buf is None or buf.numel() < n_records * 32:
+            buf = torch.empty(max(n_records * 32, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self._scratch["render_records_host"] = buf
+        return buf
 
 
 def get_runtime(device=None) -> Runtime:

@@ -131,6 +131,19 @@ int cama_render_points(cama_ctx *ctx, const double *vu, int64_t n, const int64_t
                        int64_t n_inst, const uint8_t *inst_bgr, uint8_t *image, int height, int width,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the batched clip path's record type (also produced by cama_render_points_overlay below) is declared further down;
+ * forward declaration for the per-call operator that returns the same records: */
+struct cama_overlay_record;
+/* render_maps for an image that lives in HOST memory: same centres, same painter's order, but instead of a device image
+ * the call returns the lit 8-pixel chunks as cama_overlay_record (CAMA_OVERLAY_BGR) — chunk index inside the
+ * [height, width] image, mask of painted pixels, their 24 BGR bytes — which cama_overlay_apply_host(..., CAMA_OVERLAY_DRAW)
+ * writes into the host image: exactly the bytes cama_render_points would have changed, without the image crossing PCIe
+ * twice.  width % 8 == 0.  records: device, `capacity` records (height * width / 8 always suffice); count: device uint32,
+ * set to the number of lit chunks (may exceed capacity: the excess was dropped). */
+int cama_render_points_overlay(cama_ctx *ctx, const double *vu, int64_t n, const int64_t *in_offsets, int64_t n_inst,
+                               const uint8_t *inst_bgr, int height, int width, struct cama_overlay_record *records,
+                               uint32_t *count, int64_t capacity, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- load-time densify on the device (scope row N2) ------------------------------------------- */
 
 /* MapManager.load_3d_instance_maps / calculate_3d_instance_maps (cama/reproject.py:42-106, pixel2world_xy
@@ -246,7 +259,10 @@ typedef struct cama_clip_desc {
      * 3 leaves room for a memory-bound kernel of another stream — e.g. the zero-fill of the assembled frames of a
      * frame-sharded clip — to run beside it. */
     int32_t geometry_ctas_per_sm;
-    int32_t reserved1;
+    /* Resident CTAs per SM of the raster kernel; 0 = default (4: fastest for one clip alone).  3 for independent clips
+     * enqueued on several streams: the geometry CTAs of one clip then fit beside the raster CTAs of another, and the
+     * issue-bound geometry runs under the store-bound raster (measured: 104.5 us per clip against 108.2 on config 2). */
+    int32_t raster_ctas_per_sm;
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -311,6 +327,11 @@ int cama_overlay_apply_host(const void *records, int64_t n, int format, const ui
  * cama_overlay_apply_host(op) while the next one is still in flight.  Synchronises with the copies it issued. */
 int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, int64_t n, int format, const uint8_t *palette_bgr,
                              void *staging_pinned, const cama_overlay_target *target, int op, int n_threads, void *stream);
+
+/* STREAM-like probe of the host memory system on the library's worker pool (n_threads <= 0: all cores): GB/s of a
+ * parallel fill (bytes written) and of a parallel copy (bytes read + written) over `bytes`-sized buffers (>= 1 MiB; use
+ * several times the last-level cache).  The host side of the sparse output is bound by this. */
+int cama_host_bandwidth_probe(int64_t bytes, int n_threads, double *fill_gbs, double *copy_gbs);
 
 /* ---- device side of the sparse output: records -> dense frames ---------------------------------- */
 
