@@ -520,8 +520,9 @@ def run_b200(args):
                     "transfer": "sparse", "overlay_records": int(transfer["records"]), "checksum": checksum,
                     "host_memory": {"fill_gbs": host_fill_gbs, "copy_gbs": host_copy_gbs, "threads": int(rp.host_threads),
                                     "line_traffic_bytes_per_step": int(transfer["records"]) * 2 * 128,
-                                    "note": "the call is bound by the host's memory system: every lit chunk is blanked and drawn, each time a read-for-ownership "
-                                            "and a write-back of a 64-byte line of the 373 MB host frames; fill/copy = STREAM-like figures of the same worker pool"},
+                                    "note": "fill/copy: STREAM-like figures of the worker pool that blanks and draws the lit chunks; line_traffic = "
+                                            "records x 2 (blank + draw) x 128 B, what the call would move to and from DRAM if no lit line stayed in the "
+                                            "last-level cache between blank and draw (an upper estimate: ~80 MB of distinct lines per clip do)"},
                     "host_draw_threads": int(rp.host_threads), "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,
                               "d2h_bytes_per_step": int(frame_bytes), "d2h_gbs": frame_bytes * dense_steps / dense_s / 1e9,
@@ -752,8 +753,9 @@ def run_b200_sharded(args):
                     "host_memory": {"fill_gbs_all_ranks": float(host_bw[0].item()), "copy_gbs_all_ranks": float(host_bw[1].item()),
                                     "line_traffic_bytes_per_step": int(sums[1].item()) * 2 * 128,
                                     "bound_ms_per_step": int(sums[1].item()) * 2 * 128 / max(float(host_bw[1].item()), 1e-9) / 1e6,
-                                    "note": "host-DRAM bound: every lit chunk is blanked and drawn, each a read-for-ownership + write-back of a 64-byte line; "
-                                            "all ranks share the box's memory system (fill/copy: STREAM-like figures of all ranks' worker pools at once)"},
+                                    "note": "fill/copy: STREAM-like figures of all ranks' worker pools running at once (they share the box's memory system); "
+                                            "line_traffic = records x 2 (blank + draw) x 128 B = DRAM traffic if no lit line stays in the last-level cache "
+                                            "(with N ranks x 373 MB of host frames few do); bound_ms_per_step = that traffic at the copy bandwidth"},
                     "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "zero-fill of the assembled frames (cudaMemset via torch) + peer_expand_kernel: every frame byte of the site written once per rank",

@@ -42,11 +42,16 @@ class BaseManager:
                 "Crosswalk_Line": np.array([255, 215, 0])}
 
 
+_RENDER_BGR = {}
+
+
 def render_bgr_of_class(class_name):
     """BGR triple render_maps paints an instance with: every class except lane_marking is drawn as
-    Crosswalk_Line (reference :251-254)."""
+    Crosswalk_Line (reference :251-254).  (Looked up once per class: get_color_maps builds four arrays per call.)"""
     key = class_name if class_name == LANE_CLASS else OTHER_CLASS
-    return BaseManager.get_color_maps()[key][::-1]
+    if key not in _RENDER_BGR:
+        _RENDER_BGR[key] = BaseManager.get_color_maps()[key][::-1].copy()
+    return _RENDER_BGR[key]
 
 
 def pack_instances(instances):

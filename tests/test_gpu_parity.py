@@ -750,3 +750,69 @@ def test_pixel_boundary_fuzz(rt, eps_set):
     _, dbg = r.render(res, w2c_dev, mode="binned", debug=True)
     assert np.array_equal(dbg["visible_counts"].cpu().numpy(), vc) and np.array_equal(dbg["crop_counts"].cpu().numpy(), cc)
     assert int(vc.sum()) > 500_000
+
+
+# ------------------------------------------------------------------ culling aids and occupancy knobs never change a pixel
+def test_culling_aids_and_occupancy_knobs_do_not_change_frames(rt, config2_clip):
+    """camera table (cama_camera_table_build), warp bounds, tile bounds, geometry / raster occupancy: all of them
+    only skip or reschedule work.  Also: a table built for ANOTHER rig is recognised by its signature and ignored."""
+    import torch
+    from cama_b200.batched import ClipRenderer, Reproject
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    r, res = rp.renderer, rp.resident("nuscenes")
+    _, w2c = rp.frame_poses("nuscenes")
+    w2c_dev = to_dev(w2c[:12])
+    want = r.render(res, w2c_dev, mode="binned").clone()
+    table = r.camera_table()
+    assert int(table[16:].count_nonzero().item()) > 1000 and int((table[16:] == 0).sum().item()) > 100      # some cells see cameras, some none
+    # no table at all / a table of another rig (different intrinsics => different signature)
+    other = ClipRenderer(r.chassis2cam, r.intrinsics * 1.01, r.height, r.width, r.crop_box, device=0)
+    for stand_in in (torch.zeros_like(table), other.camera_table()):
+        r._camera_table = stand_in
+        try:
+            assert torch.equal(r.render(res, w2c_dev, mode="binned"), want)
+        finally:
+            r._camera_table = table
+    # no bounds
+    saved = res.warp_bounds, res.tile_bounds
+    for wb, tb in ((None, saved[1]), (saved[0], None), (None, None)):
+        res.warp_bounds, res.tile_bounds = wb, tb
+        try:
+            assert torch.equal(r.render(res, w2c_dev, mode="binned"), want)
+        finally:
+            res.warp_bounds, res.tile_bounds = saved
+    # occupancy
+    for geo, ras in ((3, 0), (2, 3), (1, 1)):
+        r.geometry_ctas_per_sm, r.raster_ctas_per_sm = geo, ras
+        try:
+            assert torch.equal(r.render(res, w2c_dev, mode="binned"), want)
+        finally:
+            r.geometry_ctas_per_sm = r.raster_ctas_per_sm = 0
+    assert torch.equal(r.render(res, w2c_dev, mode="plane"), want)
+
+
+def test_render_maps_on_host_images_both_paths(rt):
+    """CameraManager.render_maps on a host image: the overlay-record path (writeable image, width % 8 == 0) and the
+    upload / download path (read-only image) paint the same bytes as the golden frames; untouched pixels keep their value."""
+    from cama_b200.runtime import get_runtime
+    g = load_golden("golden_clip_nuscenes_exact.npz")
+    runtime = get_runtime(0)
+    rng = np.random.default_rng(9)
+    n_inst = len(g["inst_classes"])
+    bgr = bgr_of(g["inst_classes"])
+    pos = 0
+    for c in range(2):                                      # frame 0, cameras 0 and 1
+        counts = g["vu_counts"][0, c]
+        n = int(counts.sum())
+        vu = g["vu_points"][pos:pos + n]
+        pos += n
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        background = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        lit = g["frames"][0, c].any(-1)
+        want = np.where(lit[..., None], g["frames"][0, c], background)
+        img = background.copy()
+        assert runtime.render_points(img, vu, offs, bgr) is img and np.array_equal(img, want)
+        frozen = background.copy()
+        frozen.setflags(write=False)
+        assert np.array_equal(runtime.render_points(frozen, vu, offs, bgr), want) and np.array_equal(frozen, background)
+    assert n_inst == len(offs) - 1
