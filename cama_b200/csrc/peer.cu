@@ -20,6 +20,9 @@
 // A slot is rewritten two steps later; the stream order render(s) -> publish(s) -> expand(s) -> render(s+1) on every
 // rank makes that safe (a rank can only publish step s+2 after its expand of step s+1 has seen every peer's step s+1,
 // which those peers published after finishing their expand of step s).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 using namespace cama;
@@ -65,12 +68,15 @@ template <int FORMAT>
 __global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int world, int first, unsigned step, long long capacity, const uint32_t *__restrict__ palette,
                                                          uint8_t *__restrict__ frames, long long n_chunks, unsigned long long timeout_ns, int *status) {
     __shared__ long long s_count;
+    __shared__ uint32_t s_pal[256];
     constexpr int RW = FORMAT == CAMA_OVERLAY_BGR ? 8 : 3;
+    constexpr int kPer = 4;                                // independent records per thread and pass: four load -> lookup -> store chains in flight
+    if (FORMAT == CAMA_OVERLAY_PALETTE) s_pal[threadIdx.x] = palette[threadIdx.x];
     const unsigned long long t0 = global_ns();
     for (int k = 0; k < world; ++k) {
         const int r = (first + k) % world;
         const SlotHeader *h = static_cast<const SlotHeader *>(slots.p[r]);
-        __syncthreads();                                   // (s_count of the previous slot has been read by everyone)
+        __syncthreads();                                   // (s_count of the previous slot has been read by everyone; the palette is in place)
         if (threadIdx.x == 0) {
             long long c = -1;
             while (ld_acquire_sys(&h->step) != step) {
@@ -91,29 +97,57 @@ __global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int wo
         __syncthreads();
         const long long total = s_count;
         const uint32_t *records = reinterpret_cast<const uint32_t *>(static_cast<const unsigned char *>(slots.p[r]) + CAMA_PEER_HEADER_BYTES);
-        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-            const uint32_t *rec = records + i * RW;
-            uint32_t w[6], chunk;
-            if (FORMAT == CAMA_OVERLAY_BGR) {
-                const uint4 a = reinterpret_cast<const uint4 *>(rec)[0], b = reinterpret_cast<const uint4 *>(rec)[1];
-                chunk = a.x;
-                w[0] = a.z; w[1] = a.w; w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
-            } else {
-                chunk = rec[0];
-                const uint32_t lo = rec[1], hi = rec[2];
-                uint32_t c[8];
+        for (long long i0 = (long long)blockIdx.x * (256 * kPer) + threadIdx.x; i0 < total; i0 += (long long)gridDim.x * (256 * kPer)) {
+            uint32_t chunk[kPer], w[kPer][6];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    c[q] = palette[(lo >> (8 * q)) & 0xffu];
-                    c[4 + q] = palette[(hi >> (8 * q)) & 0xffu];
+            for (int q = 0; q < kPer; ++q) {
+                const long long i = i0 + (long long)q * 256;
+                chunk[q] = 0xffffffffu;
+                if (i >= total) continue;
+                const uint32_t *rec = records + i * RW;
+                if (FORMAT == CAMA_OVERLAY_BGR) {
+                    const uint4 a = reinterpret_cast<const uint4 *>(rec)[0], b = reinterpret_cast<const uint4 *>(rec)[1];
+                    chunk[q] = a.x;
+                    w[q][0] = a.z; w[q][1] = a.w; w[q][2] = b.x; w[q][3] = b.y; w[q][4] = b.z; w[q][5] = b.w;
+                } else {
+                    chunk[q] = rec[0];
+                    w[q][0] = rec[1]; w[q][1] = rec[2];
                 }
-                w[0] = __byte_perm(c[0], c[1], 0x4210); w[1] = __byte_perm(c[1], c[2], 0x5421); w[2] = __byte_perm(c[2], c[3], 0x6542);
-                w[3] = __byte_perm(c[4], c[5], 0x4210); w[4] = __byte_perm(c[5], c[6], 0x5421); w[5] = __byte_perm(c[6], c[7], 0x6542);
             }
-            if ((long long)chunk >= n_chunks) continue;
-            uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk * 24);
-            d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                if ((long long)chunk[q] >= n_chunks) continue;                 // (also the lanes past the end)
+                if (FORMAT == CAMA_OVERLAY_PALETTE) {
+                    const uint32_t lo = w[q][0], hi = w[q][1];
+                    uint32_t c[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        c[e] = s_pal[(lo >> (8 * e)) & 0xffu];
+                        c[4 + e] = s_pal[(hi >> (8 * e)) & 0xffu];
+                    }
+                    w[q][0] = __byte_perm(c[0], c[1], 0x4210); w[q][1] = __byte_perm(c[1], c[2], 0x5421); w[q][2] = __byte_perm(c[2], c[3], 0x6542);
+                    w[q][3] = __byte_perm(c[4], c[5], 0x4210); w[q][4] = __byte_perm(c[5], c[6], 0x5421); w[q][5] = __byte_perm(c[6], c[7], 0x6542);
+                }
+                uint2 *d = reinterpret_cast<uint2 *>(frames + (size_t)chunk[q] * 24);
+                d[0] = make_uint2(w[q][0], w[q][1]); d[1] = make_uint2(w[q][2], w[q][3]); d[2] = make_uint2(w[q][4], w[q][5]);
+            }
         }
+    }
+}
+
+// Zero-fill with many short-lived CTAs (64 KiB each) and streaming stores.  cudaMemsetAsync is as fast alone, but its
+// CTAs stay resident until the fill is done, so the render of the same step — enqueued on a higher-priority stream
+// exactly so that it can run beside the fill — only got its CTAs when the fill had finished; with short CTAs the block
+// scheduler hands every freed slot to the pending high-priority CTAs first.  evict-first stores keep the fill from
+// flushing the vertices and records of the render out of L2.
+constexpr int kClearThreads = 256, kClearPerThread = 16;             // 256 threads x 16 x 16 B = 64 KiB per CTA
+__global__ void __launch_bounds__(kClearThreads) frames_clear_kernel(uint4 *__restrict__ dst, long long n16) {
+    const long long base = (long long)blockIdx.x * (kClearThreads * kClearPerThread) + threadIdx.x;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < kClearPerThread; ++k) {
+        const long long i = base + (long long)k * kClearThreads;
+        if (i < n16) __stcs(dst + i, zero);
     }
 }
 
@@ -205,7 +239,19 @@ int cama_frames_clear(cama_ctx *ctx, uint8_t *frames, size_t bytes, void *stream
     if (bytes == 0) return CAMA_OK;
     CAMA_REQUIRE(frames, "frames is NULL");
     DeviceGuard guard(ctx->device);
-    CAMA_CUDA_TRY(cudaMemsetAsync(frames, 0, bytes, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool use_memset = getenv("CAMA_CLEAR_MEMSET") != nullptr;          // experiment knob
+    if (use_memset || ((uintptr_t)frames & 15) != 0) {
+        CAMA_CUDA_TRY(cudaMemsetAsync(frames, 0, bytes, s));
+        return CAMA_OK;
+    }
+    const long long n16 = (long long)(bytes / 16);
+    const long long per_cta = (long long)kClearThreads * kClearPerThread;
+    if (n16 > 0) {
+        frames_clear_kernel<<<(unsigned)((n16 + per_cta - 1) / per_cta), kClearThreads, 0, s>>>(reinterpret_cast<uint4 *>(frames), n16);
+        CAMA_LAUNCHED(ctx);
+    }
+    if (bytes % 16) CAMA_CUDA_TRY(cudaMemsetAsync(frames + (size_t)n16 * 16, 0, bytes % 16, s));
     return CAMA_OK;
 }
 

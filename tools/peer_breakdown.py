@@ -43,7 +43,7 @@ def timed(fn, steps=20, warm=3):
 
 
 res = {"world": world, "frames_per_rank": asm.hi - asm.lo, "capacity": px.capacity}
-res["clear_cudaMemset"] = timed(lambda: N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream())))
+res["clear_library"] = timed(lambda: N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream())))
 res["clear_torch_zero_"] = timed(lambda: out.zero_())
 local_frames = torch.empty((asm.hi - asm.lo, C, 540, 960, 3), dtype=torch.uint8, device=rt.device)
 r.render(asm.res, asm.w2c_dev, out=local_frames, check=True)
