@@ -56,7 +56,6 @@ def parse_args():
                     help="default: config2 on one GPU, config3 (the site, sharded by frame) on several")
     ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-allgather", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="CUDA streams the K steps are dealt over (independent clips overlap); 1 = one stream")
     ap.add_argument("--geometry-ctas", type=int, default=3,
                     help="resident geometry CTAs per SM while clips overlap on several streams (cama_clip_desc.geometry_ctas_per_sm; 4 takes every "
@@ -262,8 +261,7 @@ def host_memory_probe(threads):
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     rank, local_rank, world = dist_env()
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert world == 1, "several ranks run run_b200_sharded"
     tmp = tempfile.TemporaryDirectory()
     clip, dataset = make_clip(args.workload, tmp.name, rank)
 
@@ -275,8 +273,6 @@ def run_b200(args):
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from cama_b200 import synth
     from cama_b200 import _native as N
@@ -293,8 +289,6 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
 
     def step(occupancy=(0, 0)):
@@ -422,59 +416,7 @@ def run_b200(args):
     dropin_t, dropin_done, _ = dropin_loop(cm_dropin, dataset, H, W, max_frames=min(F, 20))
     dropin_s = sum(dropin_t.values())
 
-    # ---- optional: the all-gather of rendered frames north_star names (N > 1)
-    gather = gather_sparse_s = None
-    if world > 1 and not args.no_allgather:
-        full = torch.empty((world * F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
-        for _ in range(2):
-            dist.all_gather_into_tensor(full, frames)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        g0.record(stream)
-        for _ in range(args.steps):
-            step()
-            dist.all_gather_into_tensor(full, frames)
-        g1.record(stream)
-        barrier()
-        gather = g0.elapsed_time(g1)
-        # the same exchange, sparse: every rank renders lit-chunk records, the records are all-gathered and each rank
-        # rebuilds all dense frames with cama_overlay_expand (cama_b200/shard.py); same bytes in HBM at the end
-        from cama_b200 import shard
-        r = rp.renderer
-
-        def sparse_step():
-            records, n, fmt = r.render_overlay(res, w2c_dev, mode=args.mode)
-            everyone, counts = shard.gather_records(records, n)
-            for peer in range(world):
-                r.expand_overlay(everyone[peer], counts[peer], fmt, res.palette, F, out=full[peer * F:(peer + 1) * F])
-
-        for _ in range(2):
-            sparse_step()
-        gather_check = bool((full[rank * F:(rank + 1) * F] == frames).all())
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            sparse_step()
-        barrier()
-        gather_sparse_s = time.perf_counter() - t0
-        assert gather_check, "sparse all-gather: own block differs from the dense render"
-
     clocks = sampler.stop()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=rt.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    ms_total = max_over_ranks(ms_total)
-    ms_single = max_over_ranks(ms_single)
-    e2e_s = max_over_ranks(e2e_s)
-    dense_s = max_over_ranks(dense_s)
-    if gather is not None:
-        gather = max_over_ranks(gather)
-        gather_sparse_s = max_over_ranks(gather_sparse_s)
 
     if rank == 0:
         peaks = {}
@@ -499,7 +441,7 @@ def run_b200(args):
             "metric": METRIC, "value": world * cam_frames / (ms_per_step * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload) + (f"; one such clip per GPU (seeds 0..{world - 1})" if world > 1 else ""),
+            "config": {"workload": workload_name(args.workload),
                        "frames": F, "cams": C, "cam_frames_per_step_per_gpu": cam_frames, "vertices": res.n_vertices,
                        "instances": res.n_instances, "raster_mode": {1: "plane", 2: "binned"}[stats["mode"]],
                        "l2": f"no flush needed: every step writes {frame_bytes / 1e6:.0f} MB of frames (> 126 MB L2); "
@@ -548,19 +490,7 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if gather is not None:
-            ms_g = gather / args.steps
-            line["allgather"] = {"value": world * cam_frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                                 "bytes_received_per_gpu": int((world - 1) * frame_bytes),
-                                 "note": "render + NCCL all_gather_into_tensor of the uint8 frames of all ranks",
-                                 "sparse": {"value": world * cam_frames * args.steps / gather_sparse_s, "unit": UNIT,
-                                            "ms_per_step": 1e3 * gather_sparse_s / args.steps,
-                                            "note": "sparse render + NCCL all-gather of the lit-chunk records + cama_overlay_expand of every rank's "
-                                                    "records into dense frames on every rank (host-timed, includes the record-count read-back)"}}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     tmp.cleanup()
 
 
@@ -784,6 +714,8 @@ def main():
         args.workload = "config2" if max(world, args.gpus) == 1 else "config3"
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py --gpus {args.gpus} ...")
     elif world > 1:
         run_b200_sharded(args)
     else:

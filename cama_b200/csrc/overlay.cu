@@ -352,8 +352,8 @@ extern "C" int cama_host_bandwidth_probe(int64_t bytes, int n_threads, double *f
     return CAMA_OK;
 }
 
-// Device records -> host frames in one call: the records are copied to the caller's pinned staging buffer in three
-// slices (1/8, 1/4, 5/8) on `stream`, and each slice is applied to the target while the next one is still crossing
+// Device records -> host frames in one call: the records are copied to the caller's pinned staging buffer in a few
+// slices (six by default) on `stream`, and each slice is applied to the target while the next one is still crossing
 // PCIe (records are independent: unique chunks, any order).  The same pipeline Reproject.__call__ ran from Python,
 // without the per-slice interpreter and tensor-dispatch overhead.
 extern "C" int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, int64_t n, int format, const uint8_t *palette_bgr,
@@ -364,15 +364,26 @@ extern "C" int cama_overlay_fetch_apply(cama_ctx *ctx, const void *records_dev, 
     if (n == 0) return CAMA_OK;
     CAMA_REQUIRE(records_dev && staging_pinned, "NULL buffer");
     const size_t rb = format == CAMA_OVERLAY_BGR ? sizeof(cama_overlay_record) : sizeof(cama_overlay_record_palette);
-    int64_t cuts[4] = {0, n, n, n};
+    // slices: a small first one (its draw starts early), then growing ones; the call ends one slice's draw after the
+    // last byte has crossed PCIe, so the last slice should be short too (three slices 1/8, 1/4, 5/8 left the draw of
+    // 5/8 of the records exposed)
+    constexpr int kMaxSlices = 8;
+    static const int want_slices = getenv("CAMA_FETCH_SLICES") ? std::min(kMaxSlices, std::max(1, atoi(getenv("CAMA_FETCH_SLICES")))) : 6;
+    int64_t cuts[kMaxSlices + 1];
     int n_slices = 1;
-    if (n >= (1 << 16)) {
-        cuts[1] = n / 8; cuts[2] = (3 * n) / 8; cuts[3] = n;
-        n_slices = 3;
+    cuts[0] = 0;
+    cuts[1] = n;
+    if (n >= (1 << 16) && want_slices > 1) {
+        n_slices = want_slices;
+        // weights 1, 2, 3, 3, 3, ... normalised
+        double w[kMaxSlices], total = 0.0;
+        for (int k = 0; k < n_slices; ++k) { w[k] = k < 2 ? k + 1.0 : 3.0; total += w[k]; }
+        double acc = 0.0;
+        for (int k = 0; k < n_slices; ++k) { acc += w[k]; cuts[k + 1] = k + 1 == n_slices ? n : (int64_t)((double)n * acc / total); }
     }
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
-    while (ctx->fetch_events.size() < 3) {
+    while (ctx->fetch_events.size() < (size_t)kMaxSlices) {
         cudaEvent_t e;
         CAMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->fetch_events.push_back(e);
