@@ -56,6 +56,7 @@ class ClipDesc(Structure):
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
         ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("raster_ctas_per_sm", c_int32),
+        ("mosaic_cols", c_int32), ("mosaic_tile_of_cam", c_int32 * 8), ("reserved2", c_int32),
     ]
 
 

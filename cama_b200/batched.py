@@ -124,7 +124,7 @@ class ClipRenderer:
     def resident(self, instances, device_vertices=None):
         return _Resident(self.rt, instances, device_vertices)
 
-    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None):
+    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None, mosaic=None):
         d = N.ClipDesc()
         d.struct_bytes = ctypes.sizeof(N.ClipDesc)
         d.mode = _MODES[mode] if isinstance(mode, str) else int(mode)
@@ -150,6 +150,11 @@ class ClipRenderer:
         d.warp_bounds = res.warp_bounds.data_ptr() if getattr(res, "warp_bounds", None) is not None else None
         d.camera_table = self.camera_table().data_ptr()
         d.geometry_ctas_per_sm = int(self.geometry_ctas_per_sm)
+        if mosaic is not None:
+            cols, tiles = mosaic
+            d.mosaic_cols = int(cols)
+            for c, tile in enumerate(tiles):
+                d.mosaic_tile_of_cam[c] = int(tile)
         d.raster_ctas_per_sm = int(self.raster_ctas_per_sm)
         if overlay is not None:
             if isinstance(overlay, dict):            # raw pointers (a mailbox slot of shard.PeerExchange)
@@ -169,8 +174,11 @@ class ClipRenderer:
             d.instance_palette = res.palette_index.data_ptr() if fmt == N.OVERLAY_PALETTE else None
         return d
 
-    def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False, lane=0):
+    def render(self, res, w2c_dev, out=None, background=None, mode="auto", check=True, debug=False, want_vu=False, lane=0, mosaic=None):
         """Enqueue one clip on the current stream.
+
+        mosaic      (cols, tile_of_cam): write the frames as the camera mosaic of VideoGenerator.concate_image
+                    (cama/tools.py:22-25) — out / background are then uint8 [F, rows*H, cols*W, 3] — instead of [F,C,H,W,3]
 
         lane        which workspace to use: clips enqueued on different torch streams must use different lanes
                     (the kernels of independent clips then overlap: the geometry of one runs under the raster of
@@ -188,8 +196,11 @@ class ClipRenderer:
         rt = self.rt
         n_frames = int(w2c_dev.shape[0])
         shape = (n_frames, self.n_cams, self.height, self.width, 3)
-        if out is None:
-            out = torch.empty(shape, dtype=torch.uint8, device=rt.device)
+        if mosaic is not None:
+            cols = int(mosaic[0])
+            shape = (n_frames, -(-self.n_cams // cols) * self.height, cols * self.width, 3)
+        if out is None:                      # (a mosaic with tiles no camera maps to keeps them black)
+            out = (torch.zeros if mosaic is not None else torch.empty)(shape, dtype=torch.uint8, device=rt.device)
         assert tuple(out.shape) == shape and out.dtype == torch.uint8 and out.is_contiguous()
         dbg = None
         if debug:
@@ -203,7 +214,7 @@ class ClipRenderer:
         key = (id(res), n_frames)
         capacity = self.capacity.get(key, 0)
         for attempt in range(3):
-            desc = self._desc(res, w2c_dev, n_frames, out, background, mode, capacity, dbg)
+            desc = self._desc(res, w2c_dev, n_frames, out, background, mode, capacity, dbg, mosaic=mosaic)
             need = ctypes.c_size_t()
             N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
             ws = rt.scratch("clip" if lane == 0 else f"clip{lane}", need.value)
@@ -435,8 +446,12 @@ class Reproject:
                               torch.from_numpy(np.ascontiguousarray(np.stack([m[1] for m in maps]), dtype=np.float32)).to(self.rt.device))
         return self._maps_dev
 
-    def render_device(self, dataset, w2c=None, out=None, background=None, mode="auto", check=True, raw_backgrounds=None):
+    def render_device(self, dataset, w2c=None, out=None, background=None, mode="auto", check=True, raw_backgrounds=None, layout="frames"):
         """Frames as a torch uint8 [F',C,H,W,3] tensor on the GPU (w2c: host float32 [F',16]).
+
+        ``layout="mosaic"``: the raster writes straight into the 2x3 camera mosaic VideoGenerator.concate_image builds
+        (cama/tools.py:22-25) — torch uint8 [F', 2H, 3W, 3] — so a GPU encoder gets its frames without a host hop and
+        without a second pass over them (``background``, if given, must have that layout too).
 
         ``raw_backgrounds``: torch uint8 [F',C,Hs,Ws,3] camera images at their native size on this device;
         they are undistort-resized (cama/reproject.py:232-240) into the frames, then drawn on in place — the
@@ -452,7 +467,15 @@ class Reproject:
             resized = self.renderer.remap(flat, mx, my, out=None if out is None else out.reshape(f * c, *out.shape[2:]))
             background = out = resized.reshape(f, c, *resized.shape[1:])
         w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c, dtype=np.float32).reshape(-1, 16)).to(self.rt.device)
-        return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check)
+        mosaic = None
+        if layout == "mosaic":
+            tiles = self.mosaic_tiles()
+            if tiles is None or raw_backgrounds is not None:
+                raise ValueError("layout='mosaic' needs the six mosaic cameras (and takes backgrounds already in the mosaic layout)")
+            mosaic = (3, tiles)
+        elif layout != "frames":
+            raise ValueError(f"unknown layout {layout!r}")
+        return self.renderer.render(self.resident(dataset), w2c_dev, out=out, background=background, mode=mode, check=check, mosaic=mosaic)
 
     def mosaic_tiles(self):
         """tile index (row-major in the 2x3 grid of cama/tools.py:22-25) of every camera, or None when the

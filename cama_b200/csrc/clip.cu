@@ -693,6 +693,13 @@ struct RasterArgs {
     long long ov_cap;
     void *ov_mirrors[CAMA_MAX_PEERS];      // record arrays on peer GPUs that receive every flush too (frame-sharded clips)
     int ov_n_mirrors;
+    // where image (frame f, camera c) lives in `frames` / `bg`: f * frame_stride + cam_offset[c], rows `pitch` bytes apart.
+    // Plain [F,C,H,W,3] frames: frame_stride = C*H*W*3, cam_offset[c] = c*H*W*3, pitch = W*3; the camera mosaic of
+    // VideoGenerator.concate_image (cama/tools.py:22-25): frame_stride = rows*H*cols*W*3, pitch = cols*W*3.
+    int n_cams;
+    unsigned pitch;
+    unsigned long long frame_stride;
+    unsigned long long cam_offset[CAMA_MAX_CAMERAS];
 };
 
 // Sparse output (MODE 2: 32-byte BGR records, MODE 3: 12-byte palette records): lit 8-pixel chunks are
@@ -849,7 +856,7 @@ __device__ __forceinline__ void row_max(const uint4 &A, unsigned L, unsigned R, 
 //   out(y) = max(raw[y-2], h3[y-1], h5[y], h3[y+1], raw[y+2])     (the 13-px L1 ball; h3/h5 = 3/5-wide row max)
 template <int MODE>
 __device__ __forceinline__ void raster_cell(const unsigned short *plane, const unsigned *__restrict__ lut, int W, int xc, bool lane_on,
-                                            int y, bool two, uint8_t *out_px, const uint8_t *bg_px, unsigned row_bytes,
+                                            int y, bool two, uint8_t *out_px, const uint8_t *bg_px, unsigned pitch,
                                             const OvSink &ov, unsigned chunk) {
     const unsigned short *row = plane + (size_t)y * W + xc;
     const bool has_l = xc > 0, has_r = xc + 8 < W;
@@ -879,7 +886,7 @@ __device__ __forceinline__ void raster_cell(const unsigned short *plane, const u
     m[1] = max3_u16x2(max3_u16x2(A[1].y, t2.y, f3.y), t4.y, A[5].y);
     m[2] = max3_u16x2(max3_u16x2(A[1].z, t2.z, f3.z), t4.z, A[5].z);
     m[3] = max3_u16x2(max3_u16x2(A[1].w, t2.w, f3.w), t4.w, A[5].w);
-    store_row<MODE>(lut, m, lane_on && two, out_px + row_bytes, MODE == 1 ? bg_px + row_bytes : nullptr, ov, chunk + (unsigned)(W >> 3));
+    store_row<MODE>(lut, m, lane_on && two, out_px + pitch, MODE == 1 ? bg_px + pitch : nullptr, ov, chunk + (unsigned)(W >> 3));
 }
 
 // One work item = one (frame, camera, band).  Shared memory: uint16 centre plane [(band_rows+5)][W] | hit
@@ -901,8 +908,10 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
     const int W = a.width;
     const int plane_rows = a.band_rows + 4;
     const unsigned plane_bytes = (unsigned)((plane_rows + 1) * W) * 2u;      // one spare (always zero) row: the odd last row reads it
-    const unsigned row_bytes = (unsigned)W * 3u;
+    const unsigned row_bytes = (unsigned)W * 3u, pitch = a.pitch;               // bytes of a row / distance between rows (equal for plain frames)
+    const bool contiguous = pitch == row_bytes;
     const unsigned zero_bytes = (unsigned)kZeroRows * row_bytes;
+    auto image_offset = [&](int image) -> size_t { return (size_t)(image / a.n_cams) * a.frame_stride + a.cam_offset[image % a.n_cams]; };
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
     unsigned *hits = reinterpret_cast<unsigned *>(smem + plane_bytes);
     unsigned char *zeros = smem + plane_bytes + kHitBytes;
@@ -990,12 +999,16 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
             const int item = (int)empty_list[pos];
             const int y_first = (item % a.n_bands) * a.band_rows;
             const int rows_out = min(a.band_rows, a.height - y_first);
-            uint8_t *out_base = a.frames + ((size_t)(item / a.n_bands) * a.height + y_first) * row_bytes;
-            unsigned left = (unsigned)rows_out * row_bytes, off = 0;
-            while (left) {
-                const unsigned n = min(left, zero_bytes);
-                bulk_store_shared_to_global(out_base + off, zeros, n);
-                off += n; left -= n;
+            uint8_t *out_base = a.frames + image_offset(item / a.n_bands) + (size_t)y_first * pitch;
+            if (contiguous) {
+                unsigned left = (unsigned)rows_out * row_bytes, off = 0;
+                while (left) {
+                    const unsigned n = min(left, zero_bytes);
+                    bulk_store_shared_to_global(out_base + off, zeros, n);
+                    off += n; left -= n;
+                }
+            } else {                                   // (mosaic: the rows of an image are not adjacent)
+                for (int y = 0; y < rows_out; ++y) bulk_store_shared_to_global(out_base + (size_t)y * pitch, zeros, row_bytes);
             }
             bulk_commit_group();
     };
@@ -1024,8 +1037,9 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
         {
             const int y_first = (item0 % a.n_bands) * a.band_rows;
             const int rows_out = min(a.band_rows, a.height - y_first);
-            uint8_t *out_base = a.frames + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes;
-            const uint8_t *bg_base = MODE == 1 ? a.bg + ((size_t)(item0 / a.n_bands) * a.height + y_first) * row_bytes : nullptr;
+            const size_t band_offset = image_offset(item0 / a.n_bands) + (size_t)y_first * pitch;
+            uint8_t *out_base = a.frames + band_offset;
+            const uint8_t *bg_base = MODE == 1 ? a.bg + band_offset : nullptr;
             const unsigned chunk_base = (unsigned)((((size_t)(a.image_base + item0 / a.n_bands) * a.height + y_first) * W) >> 3);   // MODE 2
             // 1. centres of this band (out of its group's list) -> plane (max ordinal per pixel) + hit masks
             const unsigned row_off = (unsigned)(((item0 % a.n_bands) % a.group_bands) * a.band_rows);
@@ -1063,13 +1077,13 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
                     if (((dark >> lane) & 1u) && (lane == 0 || !((dark >> (lane - 1)) & 1u))) {          // first segment of a dark run
                         const unsigned after = m & ~((2u << lane) - 1u);                                    // lit segments beyond it
                         const int x_a = lane * kSegPx, x_b = min((after ? __ffs(after) - 1 : n_strips) * kSegPx, W);
-                        uint8_t *dst = out_base + (size_t)y * row_bytes + (size_t)x_a * 3;
+                        uint8_t *dst = out_base + (size_t)y * pitch + (size_t)x_a * 3;
                         const unsigned bytes = (unsigned)(x_b - x_a) * 3u;
-                        if (two && bytes == row_bytes) {
+                        if (two && bytes == row_bytes && contiguous) {
                             bulk_store_shared_to_global(dst, zeros, 2u * row_bytes);                        // dark across the width: both rows at once
                         } else {
                             bulk_store_shared_to_global(dst, zeros, bytes);
-                            if (two) bulk_store_shared_to_global(dst + row_bytes, zeros, bytes);
+                            if (two) bulk_store_shared_to_global(dst + pitch, zeros, bytes);
                         }
                         bulk_commit_group();
                     }
@@ -1086,8 +1100,8 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
                 const int x0 = (int)(cell & 0xffu) * kSegPx + (lane & 7) * 8;
                 const bool lane_on = active && x0 < W;
                 const int xc = min(x0, W - 8);                                 // lanes past the edge recompute the last 8 px, store nothing
-                raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_base + (size_t)y * row_bytes + (size_t)x0 * 3,
-                                  MODE == 1 ? bg_base + (size_t)y * row_bytes + (size_t)x0 * 3 : nullptr, row_bytes,
+                raster_cell<MODE>(plane, (a.debug & 2) ? nullptr : a.lut, W, xc, lane_on, y, two, out_base + (size_t)y * pitch + (size_t)x0 * 3,
+                                  MODE == 1 ? bg_base + (size_t)y * pitch + (size_t)x0 * 3 : nullptr, pitch,
                                   ov, chunk_base + (unsigned)((y * W + x0) >> 3));
             }
             sync_compute();
@@ -1208,6 +1222,14 @@ void fill_cam_block(CamBlock &cams, int n_cams, const double *chassis2cam, const
         const double *K = cams.K[c];
         if (!(cams.k_row2_is_001[c] && K[1] == 0.0 && K[3] == 0.0)) cams.all_pinhole = 0;
     }
+}
+
+// bytes from one frame of `frames` / `background` to the next: n_cams images, or one mosaic of rows x mosaic_cols tiles
+size_t frame_stride_bytes(const cama_clip_desc *d) {
+    const size_t image = (size_t)d->height * d->width * 3;
+    if (d->mosaic_cols <= 0) return (size_t)d->n_cams * image;
+    const int rows = (d->n_cams + d->mosaic_cols - 1) / d->mosaic_cols;
+    return (size_t)rows * d->mosaic_cols * image;
 }
 
 struct ClipPlan {
@@ -1499,6 +1521,20 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.image_base = image_base;
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
     r.cursor = a.cursor; r.records = a.records; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    r.n_cams = d->n_cams;
+    r.frame_stride = frame_stride_bytes(d);
+    {
+        const size_t image = (size_t)d->height * d->width * 3, row = (size_t)d->width * 3;
+        r.pitch = (unsigned)(d->mosaic_cols > 0 ? row * d->mosaic_cols : row);
+        for (int c = 0; c < d->n_cams; ++c) {
+            if (d->mosaic_cols > 0) {
+                const int tile = d->mosaic_tile_of_cam[c];
+                r.cam_offset[c] = (unsigned long long)(tile / d->mosaic_cols) * d->height * r.pitch + (unsigned long long)(tile % d->mosaic_cols) * row;
+            } else {
+                r.cam_offset[c] = (unsigned long long)c * image;
+            }
+        }
+    }
     r.lists = lists; r.list_counts = list_counts;
     r.work_counter = reinterpret_cast<unsigned *>(ws + p.off_counter);
     r.empty_counter = reinterpret_cast<unsigned *>(ws + p.off_counter) + 3;
@@ -1590,6 +1626,15 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_REQUIRE(d->overlay_n_mirrors >= 0 && d->overlay_n_mirrors <= CAMA_MAX_PEERS, "overlay_n_mirrors out of range");
         for (int m = 0; m < d->overlay_n_mirrors; ++m) CAMA_REQUIRE(d->overlay_mirrors[m] && ((uintptr_t)d->overlay_mirrors[m] & 15) == 0, "overlay_mirrors[%d] is NULL or misaligned", m);
     }
+    if (d->mosaic_cols != 0) {
+        CAMA_REQUIRE(d->mosaic_cols > 0, "mosaic_cols is negative");
+        if (p.mode != CAMA_CLIP_BINNED) return fail(CAMA_E_UNSUPPORTED, "the mosaic layout needs BINNED mode");
+        const int tiles = (d->n_cams + d->mosaic_cols - 1) / d->mosaic_cols * d->mosaic_cols;
+        for (int c = 0; c < d->n_cams; ++c) {
+            CAMA_REQUIRE(d->mosaic_tile_of_cam[c] >= 0 && d->mosaic_tile_of_cam[c] < tiles, "mosaic_tile_of_cam[%d] out of range", c);
+            for (int e = 0; e < c; ++e) CAMA_REQUIRE(d->mosaic_tile_of_cam[e] != d->mosaic_tile_of_cam[c], "cameras %d and %d share a mosaic tile", e, c);
+        }
+    }
     CAMA_REQUIRE(d->n_vertices == 0 || d->vertices, "vertices is NULL");
     CAMA_REQUIRE(d->n_instances == 0 || d->instance_bgr, "instance_bgr is NULL");
     CAMA_REQUIRE(d->vertex_layout != CAMA_VERTEX_F64X3 || d->n_vertices == 0 || d->vertex_instance, "vertex_instance is NULL");
@@ -1635,7 +1680,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     cudaStream_t s_sort = ctx->pipe_streams[0], s_raster = ctx->pipe_streams[1];
     // (the side lanes only ever start after an event recorded on the caller's stream, i.e. after everything enqueued there before)
     cudaEvent_t e_join = ctx->pipe_events[2 * p.groups];
-    const size_t image_bytes = (size_t)d->height * d->width * 3;
     ClipPlan q;                                                // every slice has the layout of a full group
     {
         cama_clip_desc full = *d;
@@ -1649,8 +1693,8 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         cama_clip_desc sub = *d;
         sub.n_frames = std::min(p.group_frames, d->n_frames - f0);
         sub.world2chassis = d->world2chassis + (size_t)f0 * 16;
-        if (d->frames) sub.frames = d->frames + (size_t)f0 * d->n_cams * image_bytes;
-        if (d->background) sub.background = d->background + (size_t)f0 * d->n_cams * image_bytes;
+        if (d->frames) sub.frames = d->frames + (size_t)f0 * frame_stride_bytes(d);
+        if (d->background) sub.background = d->background + (size_t)f0 * frame_stride_bytes(d);
         Lanes lanes{s, s_sort, s_raster, ctx->pipe_events[2 * g], ctx->pipe_events[2 * g + 1]};
         rc = render_pass(ctx, &sub, q, ws + (size_t)g * p.group_stride, cams, lanes, nullptr, f0 * d->n_cams, g == 0);
         if (rc != CAMA_OK) return rc;

@@ -263,6 +263,14 @@ typedef struct cama_clip_desc {
      * enqueued on several streams: the geometry CTAs of one clip then fit beside the raster CTAs of another, and the
      * issue-bound geometry runs under the store-bound raster (measured: 104.5 us per clip against 108.2 on config 2). */
     int32_t raster_ctas_per_sm;
+    /* Output layout.  mosaic_cols == 0: plain frames uint8 [n_frames,n_cams,H,W,3].  mosaic_cols > 0 (BINNED mode): `frames`
+     * (and `background`) are the camera mosaic VideoGenerator.concate_image builds before encoding (cama/tools.py:22-25):
+     * uint8 [n_frames, rows*H, mosaic_cols*W, 3] with rows = ceil(n_cams / mosaic_cols) and camera c in tile
+     * mosaic_tile_of_cam[c] (row-major) — the raster writes straight into it, concate_image becomes a no-op and a GPU
+     * encoder gets its frames without a host hop.  Tiles no camera maps to are not written. */
+    int32_t mosaic_cols;
+    int32_t mosaic_tile_of_cam[CAMA_MAX_CAMERAS];
+    int32_t reserved2;
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {

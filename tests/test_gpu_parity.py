@@ -816,3 +816,34 @@ def test_render_maps_on_host_images_both_paths(rt):
         frozen.setflags(write=False)
         assert np.array_equal(runtime.render_points(frozen, vu, offs, bgr), want) and np.array_equal(frozen, background)
     assert n_inst == len(offs) - 1
+
+
+def test_device_mosaic_layout(rt, config2_clip):
+    """Scope row N4: render_device(layout="mosaic") writes straight into the 2x3 camera mosaic of
+    VideoGenerator.concate_image (cama/tools.py:22-25); it must equal concate_image of the plain frames — blank,
+    composited over a background that is itself a mosaic, and through the frame-group pipeline."""
+    import torch
+    from cama_b200.batched import Reproject
+    from cama_b200.tools import concate_image
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    _, w2c = rp.frame_poses("nuscenes")
+    w2c = w2c[:9]
+    plain = rp.render_device("nuscenes", w2c=w2c).cpu().numpy()
+    want = np.stack([concate_image({n: plain[f, c] for c, n in enumerate(rp.camera_names)}) for f in range(len(w2c))])
+    got = rp.render_device("nuscenes", w2c=w2c, layout="mosaic")
+    assert tuple(got.shape) == (9, 2 * H, 3 * W, 3) and np.array_equal(got.cpu().numpy(), want)
+    # in place over a background mosaic
+    rng = np.random.default_rng(3)
+    bg = rng.integers(0, 256, size=(9, 2 * H, 3 * W, 3), dtype=np.uint8)
+    lit = want.any(-1, keepdims=True)
+    bg_dev = to_dev(bg)
+    out = rp.render_device("nuscenes", w2c=w2c, layout="mosaic", background=bg_dev, out=bg_dev)
+    assert np.array_equal(out.cpu().numpy(), np.where(lit, want, bg))
+    # out of place (every cell copied) and the frame-group pipeline (groups of 8 frames)
+    out2 = rp.render_device("nuscenes", w2c=w2c, layout="mosaic", background=to_dev(bg))
+    assert np.array_equal(out2.cpu().numpy(), np.where(lit, want, bg))
+    rp.renderer.pipeline_frames = 8
+    try:
+        assert torch.equal(rp.render_device("nuscenes", w2c=w2c, layout="mosaic"), got)
+    finally:
+        rp.renderer.pipeline_frames = 0
