@@ -16,10 +16,12 @@
 //                                      zero-filled frames.
 //
 // Mailbox of a rank (device memory allocated here with cudaMalloc, so that cudaIpcGetMemHandle can export it):
-//   [2 parities][world sources] slots of  cama_peer_slot_bytes(capacity, record_bytes)  =  256-byte header | records.
-// A slot is rewritten two steps later; the stream order render(s) -> publish(s) -> expand(s) -> render(s+1) on every
-// rank makes that safe (a rank can only publish step s+2 after its expand of step s+1 has seen every peer's step s+1,
-// which those peers published after finishing their expand of step s).
+//   [P parities][world sources] slots of  cama_peer_slot_bytes(capacity, record_bytes)  =  256-byte header | records,
+// laid out by the caller; step s uses parity s % P, so a slot is rewritten P steps later.  With everything of a step on
+// one stream (render(s) -> publish(s) -> expand(s) -> render(s+1)) P = 2 is enough: a rank can only publish step s+2
+// after its expand of step s+1 has seen every peer's step s+1, which those peers published after finishing their expand
+// of step s.  cama_b200/shard.py runs the render of step s+1 beside the fill + expand of step s (it only waits for the
+// expand of step s-1) and uses P = 4 by the same argument two steps further.
 #include <cstdlib>
 #include <cstring>
 

@@ -128,11 +128,14 @@ def render_sharded(reproject, dataset, gather=True, group=None, mode="auto"):
 
 
 # ---------------------------------------------------------------------------------------------- peer exchange
-def slot_layout(world_size, capacity_records, record_bytes, header_bytes=256):
-    """Byte layout of a rank's mailbox: [2 parities][world sources] slots of header | records.
+PARITIES = 4        # slots a source cycles through in every mailbox (see PeerExchange.render_and_assemble)
+
+
+def slot_layout(world_size, capacity_records, record_bytes, header_bytes=256, parities=PARITIES):
+    """Byte layout of a rank's mailbox: [parities][world sources] slots of header | records.
     -> (slot_bytes, total_bytes, offset(parity, source))"""
     slot = -(-(header_bytes + int(capacity_records) * int(record_bytes)) // 256) * 256
-    return slot, 2 * world_size * slot, (lambda parity, source: (parity * world_size + source) * slot)
+    return slot, parities * world_size * slot, (lambda parity, source: (parity * world_size + source) * slot)
 
 
 class PeerExchange:
@@ -161,6 +164,7 @@ class PeerExchange:
         self.step = 0
         self.status = torch.zeros(1, dtype=torch.int32, device=rt.device)
         self.count = torch.zeros(4, dtype=torch.int32, device=rt.device)
+        self._expanded = {}                         # step -> event recorded after its expand (render_and_assemble)
         self.base = [None] * self.world             # mailbox of every rank, as mapped into this process
         self._own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(N.PEER_HANDLE_BYTES)
@@ -211,17 +215,21 @@ class PeerExchange:
         """One step: render this rank's block (frames [frame_lo, frame_lo + len(w2c_dev)) of the clip), exchange, expand.
 
         out            torch uint8 [n_frames_total, C, H, W, 3] on this device: all frames of the clip afterwards
-        render_stream  optional HIGH-PRIORITY torch stream for the render + publish; the zero-fill of `out` then runs
-                       beside it on the current stream (a plain side stream does not overlap: the memset kernel fills
-                       every SM and the render's CTAs queue behind it; with a higher priority the render — which moves
-                       next to no memory — gets its CTAs first and the memset takes the rest of the machine)
+        render_stream  optional torch stream for the render + publish; zero-fill and expand stay on the current stream.
+                       The two streams form a two-stage pipeline over consecutive steps: the render of step s+1 only
+                       waits for the expand of step s-1, so it runs while step s is still being filled and expanded
+                       (inside one step the two do not overlap usefully: the fill saturates the memory system and the
+                       latency-bound render stretches by what it gains).  Four slot parities make that safe: a rank's
+                       render of step s+4 — the next writer of the slots of step s on every peer — waits for its own
+                       expand of step s+2, which has seen every peer's step s+2, which those peers rendered after
+                       their expand of step s.
         Asynchronous; check ``status_code()`` after synchronising.
         """
         import torch
         from . import _native as N
         rt = self.rt
         self.step += 1
-        parity = self.step & 1
+        parity = self.step % PARITIES
         main = torch.cuda.current_stream()
         hdr = N.PEER_HEADER_BYTES
         own_slot = self.slot(self.rank, parity, self.rank)
@@ -233,7 +241,7 @@ class PeerExchange:
         def render_and_publish():
             if int(w2c_dev.shape[0]) > 0:
                 saved, renderer.geometry_ctas_per_sm = renderer.geometry_ctas_per_sm, (3 if render_stream is not None else renderer.geometry_ctas_per_sm)
-                try:                                  # (three geometry CTAs per SM: the zero-fill runs beside them)
+                try:                                  # (three geometry CTAs per SM: the fill / expand of the step before runs beside them)
                     renderer.enqueue_overlay(res, w2c_dev, overlay, mode=mode)
                 finally:
                     renderer.geometry_ctas_per_sm = saved
@@ -242,14 +250,42 @@ class PeerExchange:
             N.check(N.lib().cama_peer_publish(rt.ctx, self.count.data_ptr(), self.step, headers, self.world, rt.stream()))
 
         if render_stream is not None:
-            render_stream.wait_stream(main)          # (the previous step's expand: it still reads the slots of the other parity ... and `count`)
+            before = self._expanded.pop(self.step - 2, None)
+            if before is not None:
+                render_stream.wait_event(before)     # (not the expand of step s-1: that one runs beside this render)
+            else:
+                render_stream.wait_stream(main)      # first steps: everything enqueued so far
             with torch.cuda.stream(render_stream):
                 render_and_publish()
+                published = torch.cuda.Event()
+                published.record(render_stream)
             N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream()))
-            main.wait_stream(render_stream)
+            main.wait_event(published)
         else:
             N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream()))
             render_and_publish()
+        slots = (ctypes.c_void_p * self.world)(*[self.slot(self.rank, parity, r) for r in range(self.world)])
+        pal_dev = scratch = None
+        if self.fmt == N.OVERLAY_PALETTE:
+            pal_dev = self._palette_dev(res)
+            scratch = rt.scratch("palette32", 1024)
+        N.check(N.lib().cama_peer_expand(rt.ctx, slots, self.world, self.rank, self.step, self.capacity, self.fmt, rt.ptr(pal_dev), rt.ptr(scratch),
+                                         rt.ptr(out), int(n_frames_total), renderer.n_cams, renderer.height, renderer.width, 0,
+                                         self.status.data_ptr(), rt.stream()))
+        if render_stream is not None:
+            done = torch.cuda.Event()
+            done.record(main)
+            self._expanded[self.step] = done
+            self._expanded.pop(self.step - 3, None)
+        return out
+
+    def reassemble(self, renderer, res, n_frames_total, out):
+        """Zero-fill + expand of the slots of the LAST published step again (no render, no exchange): what the assembly
+        alone costs — every frame byte of the clip written once, plus the lit chunks (bench.py's roofline figure)."""
+        from . import _native as N
+        rt = self.rt
+        parity = self.step % PARITIES
+        N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(out), out.numel(), rt.stream()))
         slots = (ctypes.c_void_p * self.world)(*[self.slot(self.rank, parity, r) for r in range(self.world)])
         pal_dev = scratch = None
         if self.fmt == N.OVERLAY_PALETTE:

@@ -364,9 +364,10 @@ int cama_overlay_expand(cama_ctx *ctx, const void *records, int64_t n, int forma
  * rebuilds the dense frames at HBM speed.  No host round trip, no NCCL call on the data path.
  *
  * A mailbox is device memory the LIBRARY allocates (the one exception to "the caller owns all buffers": it has to come
- * from cudaMalloc to be exportable through CUDA IPC), laid out by the caller as [2 parities][world] slots of
+ * from cudaMalloc to be exportable through CUDA IPC), laid out by the caller as [P parities][world] slots of
  * cama_peer_slot_bytes(); a slot = CAMA_PEER_HEADER_BYTES header {uint32 count, uint32 step, ...} | records.  Step s uses
- * parity s & 1; steps are numbered from 1 and never reused. */
+ * parity s % P (P = 2 when a step's calls all go to one stream, 4 when the render of the next step is enqueued on a second
+ * stream beside the expand of this one: csrc/peer.cu); steps are numbered from 1 and never reused. */
 int cama_peer_slot_bytes(int64_t capacity_records, int record_bytes, size_t *bytes);
 /* cudaMalloc + zero-fill of `bytes` on the context's device; ipc_handle: CAMA_PEER_HANDLE_BYTES bytes out (host), to be sent
  * to the peer processes.  Synchronises. */

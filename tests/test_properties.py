@@ -80,5 +80,5 @@ def test_frame_blocks_partition_the_clip(n_frames, world):
 def test_mailbox_slots_are_disjoint_and_aligned(world, capacity, record_bytes):
     slot, total, offset = shard.slot_layout(world, capacity, record_bytes)
     assert slot % 256 == 0 and slot >= 256 + capacity * record_bytes
-    offs = sorted(offset(p, s) for p in (0, 1) for s in range(world))
+    offs = sorted(offset(p, s) for p in range(shard.PARITIES) for s in range(world))
     assert offs[0] == 0 and all(b - a == slot for a, b in zip(offs, offs[1:])) and offs[-1] + slot == total

@@ -103,9 +103,9 @@ def test_gather_records_gloo(world):
 
 
 def test_peer_mailbox_layout():
-    """[2 parities][world sources] slots of header | records, 256-byte aligned, disjoint."""
+    """[parities][world sources] slots of header | records, 256-byte aligned, disjoint."""
     for world, cap, rec in ((2, 1000, 12), (8, 2187629, 12), (3, 0, 32), (8, 5, 32)):
         slot, total, offset = shard.slot_layout(world, cap, rec)
-        assert slot % 256 == 0 and slot >= 256 + cap * rec and total == 2 * world * slot
-        starts = sorted(offset(p, s) for p in (0, 1) for s in range(world))
-        assert starts == [k * slot for k in range(2 * world)]
+        assert slot % 256 == 0 and slot >= 256 + cap * rec and total == shard.PARITIES * world * slot
+        starts = sorted(offset(p, s) for p in range(shard.PARITIES) for s in range(world))
+        assert starts == [k * slot for k in range(shard.PARITIES * world)]
