@@ -549,6 +549,7 @@ def run_b200_sharded(args):
     local = torch.empty((hi - lo, C, H, W, 3), dtype=torch.uint8, device=rt.device)
     w2c_block = asm.w2c_dev
     r.render(res, w2c_block, out=local, mode=args.mode, check=True)    # sizing pass of the dense block render
+    center_records = (r.last_stats or {}).get("records_total", 0)      # centre records of this rank's block
 
     def step_assembled():
         if asm.available:
@@ -578,7 +579,9 @@ def run_b200_sharded(args):
     # the assembly alone — zero-fill + expand of the records of the last step: every frame byte of the site written once
     # on this rank (the dominant kernels of the step) — on the launching stream; then one more full step (the frames
     # are compared below)
-    if asm.available:
+    if asm.available and asm.kind == "lists":
+        ms_assembly = timed(lambda: asm.exchange.reraster(r, res, frames_all), max(5, args.steps // 3), 2)
+    elif asm.available:
         ms_assembly = timed(lambda: asm.exchange.reassemble(r, res, F, frames_all), max(5, args.steps // 3), 2)
     else:
         ms_assembly = timed(lambda: N.check(N.lib().cama_frames_clear(rt.ctx, rt.ptr(frames_all), frames_all.numel(), rt.stream())), max(5, args.steps // 3), 2)
@@ -661,9 +664,13 @@ def run_b200_sharded(args):
                                    "all frames assembled on every GPU inside the timed region",
                        "frames": F, "cams": C, "cam_frames_per_step": cam_frames, "frames_per_gpu": hi - lo, "vertices": res.n_vertices,
                        "instances": res.n_instances,
-                       "assembly": ("peer memory: the raster mirrors its lit-chunk records into every peer's mailbox over NVLink while it runs, "
-                                    "cama_peer_publish / cama_peer_expand (no NCCL call and no host round trip in the step)") if asm.available
-                                   else f"NCCL all-gather of the lit-chunk records + cama_overlay_expand (no peer-to-peer path: {asm.exchange.error})",
+                       "assembly": ("peer memory, centre records: every rank's geometry kernel appends the records of its frame block to the per-band lists "
+                                    "of EVERY rank (peer stores over NVLink while it runs), cama_peer_publish_cursors / cama_peer_wait hand the lists "
+                                    "over, every rank rasters all frames (no zero-fill, no expand, no NCCL call, no host round trip in the step)")
+                                   if asm.available and asm.kind == "lists" else
+                                   ("peer memory, lit chunks: the raster mirrors its lit-chunk records into every peer's mailbox over NVLink while it runs, "
+                                    "cama_peer_publish / cama_peer_expand into zero-filled frames (no NCCL call and no host round trip in the step)")
+                                   if asm.available else f"NCCL all-gather of the lit-chunk records + cama_overlay_expand (no peer-to-peer path: {asm.exchange.error})",
                        "l2": f"no flush needed: every step writes {frame_bytes / 1e9:.2f} GB of frames per GPU (> 126 MB L2)",
                        "background": "blank (black) frames, as in the reference CPU timing"},
             "verified": {"assembled_equals_single_gpu_render_on_every_rank": bool(equal[0].item()),
@@ -677,7 +684,9 @@ def run_b200_sharded(args):
                                 "bytes_received_per_gpu": int(frame_bytes * (world - 1) / world),
                                 "nvlink_gbs_in": frame_bytes * (world - 1) / world / (ms_dense * 1e-3) / 1e9,
                                 "note": "dense render + ONE NCCL all_gather_into_tensor of the uint8 frames (north_star's literal collective): NVLink-bound"},
-            "exchange": {"records_per_gpu": records, "bytes_sent_per_gpu": records * 12 * (world - 1), "bytes_received_per_gpu": None},
+            "exchange": ({"kind": "centre records (4 B)", "records_per_gpu": int(center_records), "bytes_sent_per_gpu": int(center_records) * 4 * (world - 1),
+                          "bytes_received_per_gpu": None} if asm.available and asm.kind == "lists" else
+                         {"kind": "lit-chunk records (12 B)", "records_per_gpu": records, "bytes_sent_per_gpu": records * 12 * (world - 1), "bytes_received_per_gpu": None}),
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "e2e": {"value": cam_frames * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(w2c_host[lo:hi].nbytes) * world,
                     "d2h_bytes_per_step": (int(transfer["d2h_bytes"]) + 48) * world, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
@@ -693,12 +702,14 @@ def run_b200_sharded(args):
                                             "(with N ranks x 373 MB of host frames few do); bound_ms_per_step = that traffic at the copy bandwidth"},
                     "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "frames_clear_kernel + peer_expand_kernel (the assembly: every frame byte of the site written once per rank, then the lit chunks)",
+            "roofline": {"bound": "hbm", "kernel": ("binned_raster_kernel over all frames of the site (every frame byte written once per rank)" if asm.available and asm.kind == "lists"
+                                                    else "frames_clear_kernel + peer_expand_kernel (the assembly: every frame byte of the site written once per rank, then the lit chunks)"),
                          "achieved": frame_bytes / (ms_assembly * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": frame_bytes / (ms_assembly * 1e-3) / 1e9 / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "traffic": None, "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": ms_assembly,
-                         "launch_ms_source": "CUDA events on the launching stream around zero-fill + expand of the last step's records (no render, no exchange), "
-                                             "barrier on both sides, max over ranks",
+                         "launch_ms_source": "CUDA events on the launching stream around the assembly of the last step's records alone (raster phase over all "
+                                             "frames, or zero-fill + expand; no geometry, no exchange; includes the ~10 us of prep + classify), barrier on both "
+                                             "sides, max over ranks",
                          "whole_step": {"algorithmic_bytes": int(frame_bytes + vertex_bytes),
                                         "achieved": (frame_bytes + vertex_bytes) / (ms_step * 1e-3) / 1e9,
                                         "frac": (frame_bytes + vertex_bytes) / (ms_step * 1e-3) / 1e9 / peak,

@@ -20,6 +20,7 @@ WARP_VERTICES = 32
 MAX_PEERS = 8
 PEER_HEADER_BYTES = 256
 PEER_HANDLE_BYTES = 64
+PHASE_ALL, PHASE_GEOMETRY, PHASE_RASTER = 0, 1, 2
 CAMERA_TABLE_BYTES = 16 + 256 * 256
 OVERLAY_BGR, OVERLAY_PALETTE = 0, 1
 OVERLAY_RECORD_BYTES = {OVERLAY_BGR: 32, OVERLAY_PALETTE: 12}
@@ -56,7 +57,9 @@ class ClipDesc(Structure):
         ("overlay_format", c_int32), ("pipeline_frames", c_int32), ("instance_palette", c_void_p),
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
         ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("raster_ctas_per_sm", c_int32),
-        ("mosaic_cols", c_int32), ("mosaic_tile_of_cam", c_int32 * 8), ("reserved2", c_int32),
+        ("mosaic_cols", c_int32), ("mosaic_tile_of_cam", c_int32 * 8),
+        ("phases", c_int32), ("list_frame_base", c_int32), ("list_frames", c_int32), ("list_n_mirrors", c_int32),
+        ("list_records", c_void_p), ("list_cursor", c_void_p), ("list_record_mirrors", c_void_p * 8),
     ]
 
 
@@ -73,7 +76,7 @@ class ClipStats(Structure):
     _fields_ = [
         ("records_total", c_int64), ("record_capacity_needed", c_int64), ("record_capacity", c_int64),
         ("overflow", c_int32), ("mode", c_int32), ("band_rows", c_int32), ("n_bands", c_int32),
-        ("overlay_records", c_int64),
+        ("overlay_records", c_int64), ("lists_per_image", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -117,6 +120,8 @@ SIGNATURES = {
     "cama_peer_open": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_void_p)]),
     "cama_peer_close": (c_int, [c_void_p, c_void_p]),
     "cama_peer_publish": (c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_void_p), c_int, c_void_p]),
+    "cama_peer_publish_cursors": (c_int, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p), c_int, c_uint32, POINTER(c_void_p), c_int, c_void_p]),
+    "cama_peer_wait": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_uint32, c_int, c_void_p, c_void_p]),
     "cama_frames_clear": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cama_peer_expand": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_uint32, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

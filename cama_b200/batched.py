@@ -124,7 +124,7 @@ class ClipRenderer:
     def resident(self, instances, device_vertices=None):
         return _Resident(self.rt, instances, device_vertices)
 
-    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None, mosaic=None):
+    def _desc(self, res, w2c_dev, n_frames, frames, background, mode, capacity, debug, overlay=None, mosaic=None, lists=None):
         d = N.ClipDesc()
         d.struct_bytes = ctypes.sizeof(N.ClipDesc)
         d.mode = _MODES[mode] if isinstance(mode, str) else int(mode)
@@ -134,7 +134,7 @@ class ClipRenderer:
         d.n_vertices = res.n_vertices
         d.vertices = res.vertices.data_ptr() if res.n_vertices else None
         d.vertex_instance = res.ordinal.data_ptr() if res.ordinal is not None and res.n_vertices else None
-        d.world2chassis = w2c_dev.data_ptr() if n_frames else None
+        d.world2chassis = w2c_dev.data_ptr() if n_frames and w2c_dev is not None else None
         d.chassis2cam = N.dptr(self.chassis2cam)
         d.intrinsics = N.dptr(self.intrinsics)
         d.crop_box = (ctypes.c_double * 6)(*self.crop_box)
@@ -150,6 +150,14 @@ class ClipRenderer:
         d.warp_bounds = res.warp_bounds.data_ptr() if getattr(res, "warp_bounds", None) is not None else None
         d.camera_table = self.camera_table().data_ptr()
         d.geometry_ctas_per_sm = int(self.geometry_ctas_per_sm)
+        if lists is not None:                        # record lists outside the workspace / one half of the pipeline (shard.ListExchange)
+            d.phases = int(lists["phases"])
+            d.list_records, d.list_cursor = lists["records_ptr"], lists["cursor_ptr"]
+            d.list_frame_base, d.list_frames = int(lists.get("frame_base", 0)), int(lists["frames"])
+            mirrors = list(lists.get("mirrors", ()))
+            d.list_n_mirrors = len(mirrors)
+            for m, ptr in enumerate(mirrors):
+                d.list_record_mirrors[m] = ptr
         if mosaic is not None:
             cols, tiles = mosaic
             d.mosaic_cols = int(cols)
@@ -325,6 +333,20 @@ class ClipRenderer:
         N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
         ws = rt.scratch("clip" if lane == 0 else f"clip{lane}", need.value)
         N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
+
+    def enqueue_phase(self, res, w2c_dev, n_frames, lists, capacity, out=None, mode="binned"):
+        """Asynchronous half pipeline on external record lists (cama_clip_desc.phases): the geometry of this rank's frames
+        into lists the peers mirror, or the raster of all frames from complete lists.  ``lists``: dict(phases,
+        records_ptr, cursor_ptr, frames[, frame_base, mirrors]); ``capacity`` = records per list of those arrays."""
+        rt = self.rt
+        if n_frames == 0:
+            return
+        desc = self._desc(res, w2c_dev, n_frames, out, None, mode, capacity, None, lists=lists)
+        need = ctypes.c_size_t()
+        N.check(N.lib().cama_clip_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+        ws = rt.scratch("clip_phase%d" % int(lists["phases"]), need.value)
+        N.check(N.lib().cama_clip_render(rt.ctx, ctypes.byref(desc), rt.ptr(ws), ws.numel(), rt.stream()))
+        return desc, ws
 
     def expand_overlay(self, records, n, fmt, palette, n_frames, out=None, zero_first=True):
         """cama_overlay_expand: overlay records (device) -> dense frames torch uint8 [n_frames,C,H,W,3] on the device.

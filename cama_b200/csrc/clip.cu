@@ -82,6 +82,9 @@ struct ClipArgs {
     unsigned list_cap;                 // records a list holds
     unsigned *cursor;                  // [F*C*n_groups] records appended (attempted) to each list so far (cleared by prep)
     unsigned *records;                 // [F*C*n_groups][list_cap] payloads
+    int list_frame_base;               // frame f of this call is frame list_frame_base + f of the lists (frame-sharded clips)
+    int n_mirrors;                     // list arrays on peer GPUs that receive every record too
+    unsigned *mirror_records[CAMA_MAX_PEERS];
 };
 
 // ------------------------------------------------------------------------------------------------ camera table
@@ -155,14 +158,16 @@ __global__ void __launch_bounds__(256) camera_table_kernel(const __grid_constant
 __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double *__restrict__ w2c64,
                             const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
-                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette) {
+                            unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette,
+                            unsigned *__restrict__ zero2, long long zero2_words) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                    // (the previous clip's raster still reads the counters cleared here)
     pdl_trigger();
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
+    for (long long k = i; k < zero2_words; k += (long long)gridDim.x * blockDim.x) zero2[k] = 0u;      // (external list cursors of this call's frames)
     if (i < stats_words) stats[i] = 0u;
     if (i == 0 && overlay_count) *overlay_count = 0u;
-    if (i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
+    if (w2c && i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
     // lut[ordinal+1] = B | G << 8 | R << 16 | palette entry << 24 (the raster never looks at the top byte of a colour)
     if (i <= n_inst) lut[i] = i == 0 ? 0u
                                       : (unsigned)inst_bgr[3 * (i - 1)] | ((unsigned)inst_bgr[3 * (i - 1) + 1] << 8) |
@@ -315,7 +320,11 @@ __device__ __forceinline__ void stage_flush(const ClipArgs &a, GeoStage &st) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned pos = __shfl_sync(kFull, first[k], __ffs(peers[k]) - 1) + (unsigned)__popc(peers[k] & lt);
-            if (live[k] && pos < a.list_cap) a.records[(size_t)r[k].x * a.list_cap + pos] = r[k].y;
+            if (live[k] && pos < a.list_cap) {
+                const size_t at = (size_t)r[k].x * a.list_cap + pos;
+                a.records[at] = r[k].y;
+                for (int m = 0; m < a.n_mirrors; ++m) a.mirror_records[m][at] = r[k].y;      // (peer stores over NVLink: frame-sharded clips)
+            }
         }
     }
     __syncwarp();
@@ -344,7 +353,7 @@ __device__ __forceinline__ void emit_centre(const ClipArgs &a, GeoStage &st, int
         const int rg = a.group_rows;
         const int g0 = (int)__umulhi((unsigned)vi, a.group_magic);  // vi / rg
         const int r = vi - g0 * rg;                                  // row inside the band group (stored + 2: rows -2, -1 belong to the halo)
-        const unsigned list = (unsigned)((f * a.n_cams + c) * a.n_groups + g0);
+        const unsigned list = (unsigned)(((a.list_frame_base + f) * a.n_cams + c) * a.n_groups + g0);
         const unsigned key = (unsigned)(ord + 1) << 16;
         warp_append(a, st, vis, list, key | (unsigned)(((r + 2) << a.x_bits) | ui));
         // the two rows next to a group edge also matter to the neighbouring group (dilation radius 2); band edges
@@ -1347,10 +1356,12 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         p.cap = cap;
         p.raster_smem = (size_t)(band_rows + 5) * W * 2 + kRasterStageSmem + (size_t)kZeroRows * W * 3;
         if (d->overlay_records) p.raster_smem += sizeof(OvStage) * kRasterWarps;
-        p.off_cursor = take(sizeof(unsigned) * ((size_t)p.n_lists + 1));    // (directly after the counter block: cleared with it)
-        p.zero_bytes = off - p.off_zero;
+        if (!d->list_records) {                                              // (external lists: frame-sharded clips)
+            p.off_cursor = take(sizeof(unsigned) * ((size_t)p.n_lists + 1));    // (directly after the counter block: cleared with it)
+            p.zero_bytes = off - p.off_zero;
+        }
         p.off_lists = take(sizeof(unsigned) * 4 * (size_t)nb);             // work lists of the raster, one per weight class
-        p.off_records = take(sizeof(unsigned) * (size_t)p.n_lists * (size_t)cap);
+        if (!d->list_records) p.off_records = take(sizeof(unsigned) * (size_t)p.n_lists * (size_t)cap);
     }
     p.total = std::max<size_t>(off, 256);
     p.groups = 1;
@@ -1358,7 +1369,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     p.group_stride = 0;
     // Frame groups: the geometry of group g+1 runs while group g is sorted and rastered (three stream lanes, see
     // cama_clip_render).  Not with the per-instance debug outputs (their consumers want one pass), not for small clips.
-    if (allow_groups && mode == CAMA_CLIP_BINNED && !d->crop_counts && !d->visible_counts && !d->vu_dense) {
+    if (allow_groups && mode == CAMA_CLIP_BINNED && !d->crop_counts && !d->visible_counts && !d->vu_dense && d->phases == CAMA_PHASE_ALL && !d->list_records) {
         int want = d->pipeline_frames > 0 ? (d->pipeline_frames + 7) / 8 * 8 : d->pipeline_frames < 0 ? 0 : pipe_group_frames();
         if (want > 0 && d->n_frames > want) {
             cama_clip_desc sub = *d;
@@ -1423,12 +1434,19 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
         const long long zero_words = (long long)(p.zero_bytes / 4);
         const long long n = std::max<long long>(std::max(d->n_frames * 12, d->n_instances + 1), std::min<long long>(zero_words, 1 << 20));
         // (PDL only in BINNED mode: PLANE mode has memsets between its kernels)
-        CAMA_CUDA_TRY(launch_k(pdl, prep_kernel, (unsigned)((n + 255) / 256), 256, 0, s,
+        // external record lists (frame-sharded clips): the cursors of THIS call's frames are cleared, unless the call only rasters
+        unsigned *zero2 = nullptr;
+        long long zero2_words = 0;
+        if (binned && d->list_records && d->phases != CAMA_PHASE_RASTER) {
+            zero2 = d->list_cursor + (size_t)d->list_frame_base * d->n_cams * p.n_groups;
+            zero2_words = (long long)d->n_frames * d->n_cams * p.n_groups;
+        }
+        CAMA_CUDA_TRY(launch_k(pdl, prep_kernel, (unsigned)((std::max(n, std::min<long long>(zero2_words, 1 << 20)) + 255) / 256), 256, 0, s,
                                d->world2chassis, d->n_frames, reinterpret_cast<double *>(ws + p.off_w2c64),
                                d->instance_bgr, d->n_instances, lut,
                                reinterpret_cast<unsigned *>(ws + p.off_zero), zero_words,
                                reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette));
+                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette, zero2, zero2_words));
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
@@ -1475,10 +1493,18 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     a.group_rows = p.band_rows * p.group_bands; a.n_groups = p.n_groups;
     a.group_magic = (unsigned)(((1ull << 32) + a.group_rows - 1) / a.group_rows);
     a.list_cap = (unsigned)p.cap;
-    a.cursor = reinterpret_cast<unsigned *>(ws + p.off_cursor);
-    a.records = reinterpret_cast<unsigned *>(ws + p.off_records);
+    if (d->list_records) {                       // lists outside the workspace, shared with the peers; frame f of this call = list frame base + f
+        a.records = static_cast<unsigned *>(d->list_records);
+        a.cursor = d->list_cursor;
+        a.list_frame_base = d->list_frame_base;
+        a.n_mirrors = d->list_n_mirrors;
+        for (int m = 0; m < d->list_n_mirrors; ++m) a.mirror_records[m] = static_cast<unsigned *>(d->list_record_mirrors[m]);
+    } else {
+        a.cursor = reinterpret_cast<unsigned *>(ws + p.off_cursor);
+        a.records = reinterpret_cast<unsigned *>(ws + p.off_records);
+    }
     CAMA_CUDA_TRY(mark(1));
-    if (units > 0) {
+    if (units > 0 && d->phases != CAMA_PHASE_RASTER) {
         NvtxRange nvtx_phase("geometry");
         // big clips: cull (tile, frame chunk) units first and run the geometry over the live ones only
         if (site) {
@@ -1494,6 +1520,14 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
         CAMA_LAUNCHED(ctx);
     }
     CAMA_CUDA_TRY(mark(2));
+    if (d->phases == CAMA_PHASE_GEOMETRY) {      // the lists are handed to the peers; classify + raster run in a later call
+        CAMA_CUDA_TRY(mark(3));
+        CAMA_CUDA_TRY(mark(4));
+        return CAMA_OK;
+    }
+    // (a raster-only call reads lists whose frame 0 is this call's frame 0 + list_frame_base)
+    const unsigned *cursor = a.cursor + (size_t)a.list_frame_base * d->n_cams * p.n_groups;
+    const unsigned *records = a.records + (size_t)a.list_frame_base * d->n_cams * p.n_groups * a.list_cap;
     const bool lanes_split = lanes.geo_done != nullptr;
     if (lanes_split) {
         CAMA_CUDA_TRY(cudaEventRecord(lanes.geo_done, s));
@@ -1504,7 +1538,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     unsigned *list_counts = reinterpret_cast<unsigned *>(ws + p.off_counter) + 4;
     {
         NvtxRange nvtx_phase("classify");
-        CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, band_classify_kernel, (unsigned)((std::max(n_buckets, n_lists) + 255) / 256), 256, 0, s, a.cursor, n_lists, n_buckets,
+        CAMA_CUDA_TRY(launch_k(pdl && !lanes_split, band_classify_kernel, (unsigned)((std::max(n_buckets, n_lists) + 255) / 256), 256, 0, s, cursor, n_lists, n_buckets,
                                p.n_bands, p.group_bands, p.n_groups, a.list_cap, stats, lists, list_counts));
         CAMA_LAUNCHED(ctx);
     }
@@ -1520,7 +1554,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     r.n_instances = d->n_instances; r.group_bands = p.group_bands; r.n_groups = p.n_groups; r.list_cap = (unsigned)p.cap;
     r.x_bits = p.x_bits; r.n_strips = p.n_strips; r.image_base = image_base;
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
-    r.cursor = a.cursor; r.records = a.records; r.lut = lut; r.bg = d->background; r.frames = d->frames;
+    r.cursor = cursor; r.records = records; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     r.n_cams = d->n_cams;
     r.frame_stride = frame_stride_bytes(d);
     {
@@ -1612,8 +1646,19 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     if (!workspace || workspace_bytes < p.total) return fail(CAMA_E_WORKSPACE, "clip workspace: need %zu bytes, got %zu", p.total, workspace_bytes);
     CAMA_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (d->n_frames == 0) return CAMA_OK;
-    CAMA_REQUIRE(d->world2chassis && d->chassis2cam && d->intrinsics, "NULL buffer in desc");
-    CAMA_REQUIRE(d->frames || d->overlay_records, "neither frames nor overlay_records given");
+    CAMA_REQUIRE(d->phases == CAMA_PHASE_ALL || d->phases == CAMA_PHASE_GEOMETRY || d->phases == CAMA_PHASE_RASTER, "bad phases");
+    if (d->phases != CAMA_PHASE_ALL || d->list_records) {
+        if (p.mode != CAMA_CLIP_BINNED) return fail(CAMA_E_UNSUPPORTED, "split phases / external record lists need BINNED mode");
+        CAMA_REQUIRE(d->list_records && d->list_cursor, "split phases need external record lists (list_records, list_cursor)");
+        CAMA_REQUIRE(d->list_frame_base >= 0 && (d->list_frames == 0 ? d->list_frame_base == 0 : d->list_frame_base + d->n_frames <= d->list_frames),
+                     "this call's frames do not fit the external lists");
+        CAMA_REQUIRE(d->list_n_mirrors >= 0 && d->list_n_mirrors <= CAMA_MAX_PEERS, "list_n_mirrors out of range");
+        for (int m = 0; m < d->list_n_mirrors; ++m) CAMA_REQUIRE(d->list_record_mirrors[m], "list_record_mirrors[%d] is NULL", m);
+        CAMA_REQUIRE(!d->crop_counts && !d->visible_counts && !d->vu_dense, "the per-instance debug outputs need the whole pipeline in one call");
+    }
+    CAMA_REQUIRE(d->chassis2cam && d->intrinsics, "NULL buffer in desc");
+    CAMA_REQUIRE(d->world2chassis || d->phases == CAMA_PHASE_RASTER, "world2chassis is NULL");
+    CAMA_REQUIRE(d->frames || d->overlay_records || d->phases == CAMA_PHASE_GEOMETRY, "neither frames nor overlay_records given");
     if (d->overlay_records) {
         if (p.mode != CAMA_CLIP_BINNED) return fail(CAMA_E_UNSUPPORTED, "the sparse overlay output needs BINNED mode");
         CAMA_REQUIRE(!d->background, "the sparse overlay output takes no background (the host composites)");
@@ -1715,6 +1760,7 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
         out->mode = p.mode;
         out->band_rows = p.band_rows;
         out->n_bands = p.n_bands;
+        out->lists_per_image = p.n_groups;
         return CAMA_OK;
     }
     DeviceGuard guard(ctx->device);
@@ -1749,6 +1795,7 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
     out->mode = p.mode;
     out->band_rows = p.band_rows;
     out->n_bands = p.n_bands;
+    out->lists_per_image = p.n_groups;
     out->overlay_records = sparse ? n_overlay : 0;
     if (overflow)
         return fail(CAMA_E_CAPACITY, "record list overflow: the fullest list needs %llu records, capacity %lld", max_per_frame, p.cap);

@@ -22,6 +22,7 @@
 // after its expand of step s+1 has seen every peer's step s+1, which those peers published after finishing their expand
 // of step s.  cama_b200/shard.py runs the render of step s+1 beside the fill + expand of step s (it only waits for the
 // expand of step s-1) and uses P = 4 by the same argument two steps further.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -137,6 +138,42 @@ __global__ void __launch_bounds__(256) peer_expand_kernel(PeerPtrs slots, int wo
     }
 }
 
+// ---- exchange of the centre-record lists (cama_b200/shard.py::ListExchange) ----------------------------------------
+// The geometry kernel of a rank has mirrored the records of its frames into every peer's list array; what the peers still
+// need are the list lengths.  One kernel copies the rank's cursor range into the same range of every peer's cursor
+// array; the step number follows in peer_publish_step_kernel (release, system scope), after that kernel in stream order.
+__global__ void __launch_bounds__(256) peer_cursor_copy_kernel(const unsigned *__restrict__ own, long long first, long long count, PeerPtrs peer_cursors, int n_peers) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < count; i += (long long)gridDim.x * 256) {
+        const unsigned v = own[first + i];
+        for (int p = 0; p < n_peers; ++p) static_cast<unsigned *>(peer_cursors.p[p])[first + i] = v;
+    }
+}
+
+__global__ void peer_publish_step_kernel(unsigned step, PeerPtrs headers, int n) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    SlotHeader *h = static_cast<SlotHeader *>(headers.p[i]);
+    __threadfence_system();
+    st_release_sys(&h->step, step);
+}
+
+// One CTA: waits until the `world` headers (in this rank's own memory) carry `step`; the kernels after it in the stream
+// then see everything the peers wrote before they published.
+__global__ void peer_wait_kernel(PeerPtrs headers, int world, unsigned step, unsigned long long timeout_ns, int *status) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const SlotHeader *h = static_cast<const SlotHeader *>(headers.p[r]);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(&h->step) != step) {
+        if (global_ns() - t0 > timeout_ns) {
+            atomicMax(status, 1);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
 // Zero-fill with many short-lived CTAs (64 KiB each) and streaming stores.  cudaMemsetAsync is as fast alone, but its
 // CTAs stay resident until the fill is done, so the render of the same step — enqueued on a higher-priority stream
 // exactly so that it can run beside the fill — only got its CTAs when the fill had finished; with short CTAs the block
@@ -232,6 +269,46 @@ int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t ste
         hp.p[i] = slot_headers[i];
     }
     peer_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(overlay_count, step, hp, n);
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+int cama_peer_publish_cursors(cama_ctx *ctx, const uint32_t *own_cursor, int64_t first, int64_t count, void *const *peer_cursors, int n_peers,
+                              uint32_t step, void *const *headers, int n_headers, void *stream) {
+    CAMA_REQUIRE(ctx && own_cursor && headers, "NULL argument");
+    CAMA_REQUIRE(first >= 0 && count >= 0 && n_peers >= 0 && n_peers <= CAMA_MAX_PEERS && n_headers > 0 && n_headers <= CAMA_MAX_PEERS, "bad argument");
+    CAMA_REQUIRE(n_peers == 0 || peer_cursors, "peer_cursors is NULL");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerPtrs pc{}, hp{};
+    for (int i = 0; i < n_peers; ++i) {
+        CAMA_REQUIRE(peer_cursors[i], "peer_cursors[%d] is NULL", i);
+        pc.p[i] = peer_cursors[i];
+    }
+    for (int i = 0; i < n_headers; ++i) {
+        CAMA_REQUIRE(headers[i], "headers[%d] is NULL", i);
+        hp.p[i] = headers[i];
+    }
+    if (count > 0 && n_peers > 0) {
+        peer_cursor_copy_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 1024), 256, 0, s>>>(own_cursor, first, count, pc, n_peers);
+        CAMA_LAUNCHED(ctx);
+    }
+    peer_publish_step_kernel<<<1, 32, 0, s>>>(step, hp, n_headers);
+    CAMA_LAUNCHED(ctx);
+    return CAMA_OK;
+}
+
+int cama_peer_wait(cama_ctx *ctx, void *const *headers, int world, uint32_t step, int timeout_ms, int32_t *status, void *stream) {
+    CAMA_REQUIRE(ctx && headers && status, "NULL argument");
+    CAMA_REQUIRE(world > 0 && world <= CAMA_MAX_PEERS, "1..%d ranks", CAMA_MAX_PEERS);
+    DeviceGuard guard(ctx->device);
+    PeerPtrs hp{};
+    for (int i = 0; i < world; ++i) {
+        CAMA_REQUIRE(headers[i], "headers[%d] is NULL", i);
+        hp.p[i] = headers[i];
+    }
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hp, world, step, timeout_ns, status);
     CAMA_LAUNCHED(ctx);
     return CAMA_OK;
 }

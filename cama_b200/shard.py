@@ -128,6 +128,10 @@ def render_sharded(reproject, dataset, gather=True, group=None, mode="auto"):
 
 
 # ---------------------------------------------------------------------------------------------- peer exchange
+def _MODES_BINNED(mode):
+    return mode in ("auto", "binned")
+
+
 PARITIES = 4        # slots a source cycles through in every mailbox (see PeerExchange.render_and_assemble)
 
 
@@ -307,6 +311,126 @@ class PeerExchange:
         return int(self.status.item())
 
 
+class ListExchange:
+    """A frame-sharded clip assembled on every rank by exchanging the CENTRE RECORDS and rastering everything everywhere.
+
+    Every rank ends a step with every frame of the clip in its HBM; those bytes have to be written by somebody on that
+    GPU, and the raster is the kernel that writes them at ~0.75 of the HBM peak anyway.  So only the geometry is sharded:
+    a rank runs ``cama_clip_render(phases=GEOMETRY)`` on its frame block, the kernel appends every centre record to the
+    band's list in the rank's own list array AND, by peer stores over NVLink, at the same place of every peer's array
+    (4 bytes per visible point: a third of the bytes of the lit-chunk records of PeerExchange); ``cama_peer_publish_cursors``
+    delivers the list lengths and the step number; after ``cama_peer_wait`` every rank runs ``phases=RASTER`` over ALL
+    frames.  No zero-fill, no expand, no NCCL, no host round trip.  Two parities of list arrays (one stream per rank:
+    a rank reaches the geometry of step s+2 — the next writer of step s's arrays on its peers — only after it has seen
+    their step s+1, which they published after rastering step s).
+    """
+
+    def __init__(self, rt, renderer, res, n_frames_total, capacity, lists_per_image, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        self.rt, self.group = rt, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > N.MAX_PEERS:
+            raise ValueError(f"at most {N.MAX_PEERS} ranks")
+        self.capacity = int(capacity)
+        self.n_frames = int(n_frames_total)
+        self.lists_per_frame = renderer.n_cams * int(lists_per_image)
+        self.n_lists = self.n_frames * self.lists_per_frame
+        hdr = N.PEER_HEADER_BYTES
+        self.cursor_off = self.world * hdr
+        self.records_off = -(-(self.cursor_off + self.n_lists * 4) // 256) * 256
+        self.parity_bytes = -(-(self.records_off + self.n_lists * self.capacity * 4) // 256) * 256
+        self.total_bytes = 2 * self.parity_bytes
+        self.step = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=rt.device)
+        self.base = [None] * self.world
+        self._own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(N.PEER_HANDLE_BYTES)
+        error = None
+        try:
+            N.check(N.lib().cama_peer_alloc(rt.ctx, self.total_bytes, ctypes.byref(self._own), handle))
+        except N.CamaError as exc:
+            error = str(exc)
+        mine = {"handle": bytes(handle.raw), "device": int(rt.device.index), "error": error}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        if all(e["error"] is None for e in everyone):
+            for r, e in enumerate(everyone):
+                if r == self.rank:
+                    self.base[r] = self._own.value
+                    continue
+                ptr = ctypes.c_void_p()
+                if N.lib().cama_peer_open(rt.ctx, e["device"], e["handle"], ctypes.byref(ptr)) != N.CAMA_OK:
+                    error = N.lib().cama_last_error().decode("utf-8", "replace")
+                    break
+                self.base[r] = ptr.value
+        else:
+            error = error or "a peer could not allocate its list arrays"
+        verdicts = [None] * self.world
+        dist.all_gather_object(verdicts, error, group=group)
+        self.error = next((v for v in verdicts if v), None)
+        self.available = self.error is None
+        if not self.available:
+            self.close()
+
+    close = PeerExchange.close
+
+    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, out, mode="binned"):
+        """One step (asynchronous): geometry of this rank's frames [frame_lo, frame_lo + len(w2c_dev)) into everybody's
+        lists, hand-off, raster of all frames into ``out`` (torch uint8 [n_frames_total, C, H, W, 3])."""
+        from . import _native as N
+        rt = self.rt
+        self.step += 1
+        at = (self.step & 1) * self.parity_bytes
+        hdr = N.PEER_HEADER_BYTES
+        n_local = int(w2c_dev.shape[0])
+        own = self.base[self.rank] + at
+        peers = [r for r in range(self.world) if r != self.rank]
+        if n_local:
+            renderer.enqueue_phase(res, w2c_dev, n_local,
+                                   {"phases": N.PHASE_GEOMETRY, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
+                                    "frame_base": frame_lo, "frames": self.n_frames,
+                                    "mirrors": [self.base[r] + at + self.records_off for r in peers]}, self.capacity, mode=mode)
+        peer_cursors = (ctypes.c_void_p * max(len(peers), 1))(*[self.base[r] + at + self.cursor_off for r in peers])
+        headers = (ctypes.c_void_p * self.world)(*[self.base[r] + at + self.rank * hdr for r in range(self.world)])
+        N.check(N.lib().cama_peer_publish_cursors(rt.ctx, own + self.cursor_off, frame_lo * self.lists_per_frame, n_local * self.lists_per_frame,
+                                                  peer_cursors, len(peers), self.step, headers, self.world, rt.stream()))
+        arrived = (ctypes.c_void_p * self.world)(*[own + r * hdr for r in range(self.world)])
+        N.check(N.lib().cama_peer_wait(rt.ctx, arrived, self.world, self.step, 0, self.status.data_ptr(), rt.stream()))
+        self._last_raster = renderer.enqueue_phase(res, None, self.n_frames,
+                                                   {"phases": N.PHASE_RASTER, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
+                                                    "frame_base": 0, "frames": self.n_frames}, self.capacity, out=out, mode=mode)
+        return out
+
+    def reraster(self, renderer, res, out, mode="binned"):
+        """The raster phase of the last step again (complete lists, no geometry, no exchange): what writing every frame of
+        the clip on this rank costs — bench.py's roofline figure."""
+        from . import _native as N
+        own = self.base[self.rank] + (self.step & 1) * self.parity_bytes
+        renderer.enqueue_phase(res, None, self.n_frames,
+                               {"phases": N.PHASE_RASTER, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
+                                "frame_base": 0, "frames": self.n_frames}, self.capacity, out=out, mode=mode)
+        return out
+
+    def status_code(self):
+        """0 ok, 1 a peer's step timed out, 2 a record list overflowed its capacity in the last step (synchronises)."""
+        from . import _native as N
+        code = int(self.status.item())
+        last = getattr(self, "_last_raster", None)
+        if code == 0 and last is not None:
+            desc, ws = last
+            stats = N.ClipStats()
+            rc = N.lib().cama_clip_stats_read(self.rt.ctx, ctypes.byref(desc), self.rt.ptr(ws), self.rt.stream(), ctypes.byref(stats))
+            if rc == N.CAMA_E_CAPACITY:
+                code = 2
+            else:
+                N.check(rc)
+            self.last_stats = {f: getattr(stats, f) for f, _ in N.ClipStats._fields_}
+        return code
+
+
 class SiteAssembler:
     """A frame-sharded clip assembled on every rank, step after step (BASELINE.json configs[3]).
 
@@ -314,7 +438,9 @@ class SiteAssembler:
     25 % headroom), builds the PeerExchange.  ``step()`` enqueues render + exchange + expand of this rank's frame
     block and returns the tensor that holds ALL frames of the clip afterwards (the same tensor every step)."""
 
-    def __init__(self, reproject, dataset, group=None, mode="auto", overlap_clear=True):
+    def __init__(self, reproject, dataset, group=None, mode="auto", overlap_clear=True, exchange="lists"):
+        """exchange="lists": centre records exchanged, every rank rasters every frame (ListExchange, the default);
+        "chunks": lit-chunk records exchanged, zero-fill + expand on every rank (PeerExchange)."""
         import torch
         import torch.distributed as dist
         self.rp, self.dataset, self.mode = reproject, dataset, mode
@@ -326,13 +452,21 @@ class SiteAssembler:
         self.n_frames = len(self.idx)
         self.lo, self.hi = frame_block(self.n_frames, self.rank, self.world)
         self.w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c[self.lo:self.hi], dtype=np.float32).reshape(-1, 16)).to(rt.device)
-        _, n, fmt = r.render_overlay(self.res, self.w2c_dev, mode=mode)          # settles the centre-record pool, counts the lit chunks
-        most = torch.tensor([int(n)], dtype=torch.int64, device=rt.device)
+        _, n, fmt = r.render_overlay(self.res, self.w2c_dev, mode=mode)          # settles the centre-record lists, counts the lit chunks
+        stats = r.last_stats or {}
+        most = torch.tensor([int(n), int(stats.get("record_capacity", 0)), int(stats.get("record_capacity_needed", 0))], dtype=torch.int64, device=rt.device)
         dist.all_reduce(most, op=dist.ReduceOp.MAX, group=group)
-        self.exchange = PeerExchange(rt, int(int(most.item()) * 1.25) + 4096, fmt, group=group)
-        self.available = self.exchange.available
+        self.kind = exchange
         self.frames = None
-        self.render_stream = torch.cuda.Stream(device=rt.device, priority=-1) if overlap_clear else None
+        self.render_stream = None
+        if exchange == "lists" and _MODES_BINNED(mode) and stats.get("lists_per_image", 0) > 0:
+            capacity = max(int(most[1].item()), int(int(most[2].item()) * 1.1) + 256)       # every rank: the same list capacity
+            self.exchange = ListExchange(rt, r, self.res, self.n_frames, capacity, stats["lists_per_image"], group=group)
+        else:
+            self.kind = "chunks"
+            self.exchange = PeerExchange(rt, int(int(most[0].item()) * 1.25) + 4096, fmt, group=group)
+            self.render_stream = torch.cuda.Stream(device=rt.device, priority=-1) if overlap_clear else None
+        self.available = self.exchange.available
 
     def step(self, out=None):
         import torch
@@ -341,4 +475,6 @@ class SiteAssembler:
             if self.frames is None:
                 self.frames = torch.empty((self.n_frames, r.n_cams, r.height, r.width, 3), dtype=torch.uint8, device=self.rp.rt.device)
             out = self.frames
+        if self.kind == "lists":
+            return self.exchange.render_and_assemble(r, self.res, self.w2c_dev, self.lo, out)
         return self.exchange.render_and_assemble(r, self.res, self.w2c_dev, self.lo, self.n_frames, out, mode=self.mode, render_stream=self.render_stream)

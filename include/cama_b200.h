@@ -206,6 +206,7 @@ typedef struct cama_overlay_record_palette {
     uint8_t index[8];
 } cama_overlay_record_palette;
 enum { CAMA_OVERLAY_BGR = 0, CAMA_OVERLAY_PALETTE = 1 };
+enum { CAMA_PHASE_ALL = 0, CAMA_PHASE_GEOMETRY = 1, CAMA_PHASE_RASTER = 2 };
 
 typedef struct cama_clip_desc {
     uint32_t struct_bytes;          /* sizeof(cama_clip_desc), ABI guard */
@@ -270,7 +271,23 @@ typedef struct cama_clip_desc {
      * encoder gets its frames without a host hop.  Tiles no camera maps to are not written. */
     int32_t mosaic_cols;
     int32_t mosaic_tile_of_cam[CAMA_MAX_CAMERAS];
-    int32_t reserved2;
+    /* Frame-sharded clips, exchange of the CENTRE RECORDS (BINNED mode; cama_peer_* below, cama_b200/shard.py::ListExchange).
+     * The record lists may live outside the workspace — in memory the peers can write — and a call may run only one half
+     * of the pipeline:
+     *   phases = CAMA_PHASE_GEOMETRY  prep + geometry of this call's n_frames frames, which are frames list_frame_base ..
+     *            of the lists; every record is also stored at the same place of list_record_mirrors[0 .. list_n_mirrors)
+     *            (the peers' list arrays, over NVLink); only the cursors of this call's frames are cleared and advanced;
+     *   phases = CAMA_PHASE_RASTER    work lists + raster of n_frames frames (normally all list_frames) from lists that are
+     *            complete (cursors of the other ranks' frames delivered by cama_peer_publish_cursors / cama_peer_wait).
+     * list_records: device uint32 [list_frames * n_cams * n_bands][record_capacity]; list_cursor: device uint32
+     * [list_frames * n_cams * n_bands] (n_bands: cama_clip_stats.n_bands of this shape). */
+    int32_t phases;                 /* 0 = the whole pipeline */
+    int32_t list_frame_base;
+    int32_t list_frames;            /* 0 = n_frames */
+    int32_t list_n_mirrors;
+    void *list_records;             /* NULL = inside the workspace */
+    uint32_t *list_cursor;
+    void *list_record_mirrors[CAMA_MAX_PEERS];
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -282,6 +299,8 @@ typedef struct cama_clip_stats {
     int32_t band_rows;              /* BINNED: output rows per band */
     int32_t n_bands;
     int64_t overlay_records;        /* lit chunks produced (sparse output), 0 otherwise */
+    int32_t lists_per_image;        /* BINNED: record lists per (frame, camera) image (= n_bands unless bands share lists) */
+    int32_t reserved;
 } cama_clip_stats;
 
 /* Which cameras can see a point of the crop box at all?  Cuts the crop box's x-y rectangle into cells of about a metre
@@ -391,6 +410,19 @@ int cama_frames_clear(cama_ctx *ctx, uint8_t *frames, size_t bytes, void *stream
 int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, int own_rank, uint32_t step, int64_t capacity_records, int format,
                      const uint8_t *palette_bgr, void *palette_scratch, uint8_t *frames, int64_t n_frames, int n_cams,
                      int height, int width, int timeout_ms, int32_t *status, void *stream);
+
+/* The same hand-off for the exchange of the CENTRE RECORDS (cama_clip_desc.phases / list_*): every rank's geometry has
+ * mirrored the records of its frames into the peers' list arrays; cama_peer_publish_cursors copies the rank's cursor range
+ * [first, first + count) (own_cursor: this rank's array) into the same range of the n_peers peer arrays and then writes
+ * `step`, with release semantics at system scope, into the n_headers headers (own and peers'); cama_peer_wait (one warp)
+ * waits on `stream` until the `world` headers in this rank's own memory carry `step` (timeout_ms <= 0: 2000; status 1 on a
+ * time-out), so that the raster-phase call enqueued after it sees complete lists.  Every rank then rasters EVERY frame from
+ * the lists: the dense frames are written once, by the HBM-bound kernel that writes them anyway — no zero-fill, no expand. */
+int cama_peer_publish_cursors(cama_ctx *ctx, const uint32_t *own_cursor, int64_t first, int64_t count,
+                              void *const *peer_cursors, int n_peers, uint32_t step, void *const *headers, int n_headers,
+                              void *stream);
+int cama_peer_wait(cama_ctx *ctx, void *const *headers, int world, uint32_t step, int timeout_ms, int32_t *status,
+                   void *stream);
 
 /* ---- LiDAR aggregation (BASELINE.json configs[4]) -------------------------------- */
 

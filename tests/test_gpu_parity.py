@@ -847,3 +847,39 @@ def test_device_mosaic_layout(rt, config2_clip):
         assert torch.equal(rp.render_device("nuscenes", w2c=w2c, layout="mosaic"), got)
     finally:
         rp.renderer.pipeline_frames = 0
+
+
+def test_split_phases_with_external_lists(rt, config2_clip):
+    """The two halves of the pipeline on record lists outside the workspace (cama_clip_desc.phases / list_*), as the
+    list exchange of a frame-sharded clip runs them: geometry of frame blocks [0,15), [15,29), [29,40) — each block's
+    records also mirrored into a second list array — then ONE raster call over all 40 frames, from the primary arrays and
+    from the mirror: both equal the ordinary render."""
+    import torch
+    from cama_b200 import _native as N
+    from cama_b200.batched import Reproject
+    rp = Reproject(synth.CAMA_CONFIGS, config2_clip, device=0)
+    r, res = rp.renderer, rp.resident("nuscenes")
+    _, w2c = rp.frame_poses("nuscenes")
+    w2c_dev = to_dev(w2c)
+    want = r.render(res, w2c_dev, mode="binned")
+    stats = r.last_stats
+    F, cap, per_image = 40, int(stats["record_capacity"]), int(stats["lists_per_image"])
+    n_lists = F * r.n_cams * per_image
+    arrays = []
+    for _ in range(2):                                     # primary, mirror
+        arrays.append((torch.full((n_lists, cap), 0x7fffffff, dtype=torch.int32, device="cuda"), torch.full((n_lists,), 12345, dtype=torch.int32, device="cuda")))
+    (rec, cur), (rec_m, cur_m) = arrays
+    for lo, hi in ((0, 15), (15, 29), (29, 40)):
+        r.enqueue_phase(res, w2c_dev[lo:hi], hi - lo, {"phases": N.PHASE_GEOMETRY, "records_ptr": rec.data_ptr(), "cursor_ptr": cur.data_ptr(),
+                                                        "frame_base": lo, "frames": F, "mirrors": [rec_m.data_ptr()]}, cap)
+    cur_m.copy_(cur)                                       # (what cama_peer_publish_cursors does for a peer)
+    for records, cursor in ((rec, cur), (rec_m, cur_m)):
+        out = torch.empty_like(want)
+        r.enqueue_phase(res, None, F, {"phases": N.PHASE_RASTER, "records_ptr": records.data_ptr(), "cursor_ptr": cursor.data_ptr(), "frame_base": 0, "frames": F},
+                        cap, out=out)
+        assert torch.equal(out, want)
+    assert int(cur.sum().item()) == int(stats["records_total"])
+    # a raster call over a sub-range of the lists' frames
+    part = torch.empty_like(want[10:25])
+    r.enqueue_phase(res, None, 15, {"phases": N.PHASE_RASTER, "records_ptr": rec.data_ptr(), "cursor_ptr": cur.data_ptr(), "frame_base": 10, "frames": F}, cap, out=part)
+    assert torch.equal(part, want[10:25])

@@ -43,22 +43,33 @@ def main():
         ok = ok and idx_local == idx[lo:hi] and bool((block == whole[lo:hi]).all())
         report = {"world": world, "frames": 37, "dense_nccl_allgather": bool((gathered == whole).all()), "sparse_nccl_allgather": bool((gathered_s == whole).all())}
         # peer-memory assembly: five steps in a row into the same output, every one checked; then a poisoned output buffer
+        peer_ok = True
+        for kind in ("lists", "chunks"):
+            asm = shard.SiteAssembler(rp, "nuscenes", exchange=kind)
+            report[f"peer_{kind}_available"] = bool(asm.available) and asm.kind == kind
+            report[f"peer_{kind}_error"] = asm.exchange.error
+            kind_ok = asm.available and asm.kind == kind
+            if asm.available:
+                for step in range(5):
+                    out = asm.step()
+                    if step == 3:
+                        torch.cuda.synchronize()
+                        out.fill_(0x5a)                               # the next step must overwrite every byte
+                        out = asm.step()
+                    torch.cuda.synchronize()
+                    kind_ok = kind_ok and asm.exchange.status_code() == 0 and bool((out == whole).all())
+                dist.barrier()
+                asm.exchange.close()
+            report[f"peer_{kind}_assembly"] = bool(kind_ok)
+            peer_ok = peer_ok and kind_ok
         asm = shard.SiteAssembler(rp, "nuscenes")
         report["peer_available"] = bool(asm.available)
         report["peer_error"] = asm.exchange.error
-        peer_ok = True
         if asm.available:
-            for step in range(5):
-                out = asm.step()
-                if step == 3:
-                    torch.cuda.synchronize()
-                    out.fill_(0x5a)                               # the next step must overwrite every byte
-                    out = asm.step()
-                torch.cuda.synchronize()
-                peer_ok = peer_ok and asm.exchange.status_code() == 0 and bool((out == whole).all())
             idx_p, gathered_p = shard.render_sharded(rp, "nuscenes", gather="peer")    # the public entry
             peer_ok = peer_ok and idx_p == idx and bool((gathered_p == whole).all())
             dist.barrier()
+            asm.exchange.close()
         report["peer_assembly"] = peer_ok
         ok = ok and peer_ok
         # LiDAR aggregation (configs[4]): sweeps sharded across the ranks, voxel counts summed with one all-reduce

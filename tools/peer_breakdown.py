@@ -19,7 +19,7 @@ spec = synth.config3_spec(); spec.write_cama = False
 clip = synth.write_clip(spec, root)
 rp = Reproject(synth.CAMA_CONFIGS, clip, device=local)
 rt, r = rp.rt, rp.renderer
-asm = shard.SiteAssembler(rp, "nuscenes")
+asm = shard.SiteAssembler(rp, "nuscenes", exchange="chunks")
 px = asm.exchange
 F, C = asm.n_frames, r.n_cams
 out = torch.empty((F, C, 540, 960, 3), dtype=torch.uint8, device=rt.device)
@@ -69,8 +69,27 @@ rs, asm.render_stream = asm.render_stream, None
 res["full_step_serial_clear"] = timed(lambda: asm.step(out=out))
 asm.render_stream = rs
 res["status"] = px.status_code()
+dist.barrier()
+# ---- the other exchange: centre records into everybody's per-band lists, every rank rasters every frame
+asm2 = shard.SiteAssembler(rp, "nuscenes", exchange="lists")
+res["lists_available"] = bool(asm2.available and asm2.kind == "lists")
+if res["lists_available"]:
+    lx = asm2.exchange
+    res["lists_capacity"], res["lists_bytes_per_rank"] = lx.capacity, lx.total_bytes
+    res["lists_full_step"] = timed(lambda: asm2.step(out=out))
+    res["lists_raster_all_frames"] = timed(lambda: lx.reraster(r, asm2.res, out))
+    own = lx.base[rank] + (lx.step & 1) * lx.parity_bytes
+    geo = {"phases": N.PHASE_GEOMETRY, "records_ptr": own + lx.records_off, "cursor_ptr": own + lx.cursor_off, "frame_base": asm2.lo, "frames": lx.n_frames}
+    res["lists_geometry_local_only"] = timed(lambda: r.enqueue_phase(asm2.res, asm2.w2c_dev, asm2.hi - asm2.lo, geo, lx.capacity))
+    dist.barrier()
+    at = (lx.step & 1) * lx.parity_bytes
+    geo_m = dict(geo, mirrors=[lx.base[q] + at + lx.records_off for q in range(world) if q != rank])
+    res["lists_geometry_mirrored"] = timed(lambda: r.enqueue_phase(asm2.res, asm2.w2c_dev, asm2.hi - asm2.lo, geo_m, lx.capacity))
+    res["lists_status"] = lx.status_code()
 if rank == 0:
     print(json.dumps(res), flush=True)
 dist.barrier()
 px.close()
+if asm2.available:
+    asm2.exchange.close()
 dist.destroy_process_group()
