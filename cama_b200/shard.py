@@ -377,11 +377,21 @@ class ListExchange:
 
     close = PeerExchange.close
 
-    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, out, mode="binned"):
+    def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, out, mode="binned", marks=None):
         """One step (asynchronous): geometry of this rank's frames [frame_lo, frame_lo + len(w2c_dev)) into everybody's
-        lists, hand-off, raster of all frames into ``out`` (torch uint8 [n_frames_total, C, H, W, 3])."""
+        lists, hand-off, raster of all frames into ``out`` (torch uint8 [n_frames_total, C, H, W, 3]).
+        ``marks``: optional list that receives five timing events (start, geometry, published, arrived, rastered)."""
+        import torch
         from . import _native as N
         rt = self.rt
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream())
+                marks.append(e)
+
+        mark()
         self.step += 1
         at = (self.step & 1) * self.parity_bytes
         hdr = N.PEER_HEADER_BYTES
@@ -393,15 +403,19 @@ class ListExchange:
                                    {"phases": N.PHASE_GEOMETRY, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
                                     "frame_base": frame_lo, "frames": self.n_frames,
                                     "mirrors": [self.base[r] + at + self.records_off for r in peers]}, self.capacity, mode=mode)
+        mark()
         peer_cursors = (ctypes.c_void_p * max(len(peers), 1))(*[self.base[r] + at + self.cursor_off for r in peers])
         headers = (ctypes.c_void_p * self.world)(*[self.base[r] + at + self.rank * hdr for r in range(self.world)])
         N.check(N.lib().cama_peer_publish_cursors(rt.ctx, own + self.cursor_off, frame_lo * self.lists_per_frame, n_local * self.lists_per_frame,
                                                   peer_cursors, len(peers), self.step, headers, self.world, rt.stream()))
+        mark()
         arrived = (ctypes.c_void_p * self.world)(*[own + r * hdr for r in range(self.world)])
         N.check(N.lib().cama_peer_wait(rt.ctx, arrived, self.world, self.step, 0, self.status.data_ptr(), rt.stream()))
+        mark()
         self._last_raster = renderer.enqueue_phase(res, None, self.n_frames,
                                                    {"phases": N.PHASE_RASTER, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
                                                     "frame_base": 0, "frames": self.n_frames}, self.capacity, out=out, mode=mode)
+        mark()
         return out
 
     def reraster(self, renderer, res, out, mode="binned"):
