@@ -121,6 +121,8 @@ SIGNATURES = {
     "cama_peer_close": (c_int, [c_void_p, c_void_p]),
     "cama_peer_publish": (c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_void_p), c_int, c_void_p]),
     "cama_peer_publish_cursors": (c_int, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_void_p), c_int, c_uint32, POINTER(c_void_p), c_int, c_void_p]),
+    "cama_peer_publish_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_int, c_uint32,
+                                        POINTER(c_void_p), c_int, c_void_p]),
     "cama_peer_wait": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_uint32, c_int, c_void_p, c_void_p]),
     "cama_frames_clear": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cama_peer_expand": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_uint32, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,

@@ -316,11 +316,11 @@ class ListExchange:
 
     Every rank ends a step with every frame of the clip in its HBM; those bytes have to be written by somebody on that
     GPU, and the raster is the kernel that writes them at ~0.75 of the HBM peak anyway.  So only the geometry is sharded:
-    a rank runs ``cama_clip_render(phases=GEOMETRY)`` on its frame block, the kernel appends every centre record to the
-    band's list in the rank's own list array AND, by peer stores over NVLink, at the same place of every peer's array
-    (4 bytes per visible point: a third of the bytes of the lit-chunk records of PeerExchange); ``cama_peer_publish_cursors``
-    delivers the list lengths and the step number; after ``cama_peer_wait`` every rank runs ``phases=RASTER`` over ALL
-    frames.  No zero-fill, no expand, no NCCL, no host round trip.  Two parities of list arrays (one stream per rank:
+    a rank runs ``cama_clip_render(phases=GEOMETRY)`` on its frame block (centre records into the per-band lists of its
+    own list array); ``cama_peer_publish_lists`` copies the filled part of those lists to the same place of every peer's
+    array with wide peer stores over NVLink (4 bytes per visible point: a third of the bytes of the lit-chunk records of
+    PeerExchange), then the list lengths and the step number; after ``cama_peer_wait`` every rank runs ``phases=RASTER``
+    over ALL frames.  No zero-fill, no expand, no NCCL, no host round trip.  Two parities of list arrays (one stream per rank:
     a rank reaches the geometry of step s+2 — the next writer of step s's arrays on its peers — only after it has seen
     their step s+1, which they published after rastering step s).
     """
@@ -334,7 +334,7 @@ class ListExchange:
         self.rank = dist.get_rank(group)
         if self.world > N.MAX_PEERS:
             raise ValueError(f"at most {N.MAX_PEERS} ranks")
-        self.capacity = int(capacity)
+        self.capacity = -(-int(capacity) // 4) * 4        # (16-byte lists: cama_peer_publish_lists copies them with wide stores)
         self.n_frames = int(n_frames_total)
         self.lists_per_frame = renderer.n_cams * int(lists_per_image)
         self.n_lists = self.n_frames * self.lists_per_frame
@@ -401,13 +401,14 @@ class ListExchange:
         if n_local:
             renderer.enqueue_phase(res, w2c_dev, n_local,
                                    {"phases": N.PHASE_GEOMETRY, "records_ptr": own + self.records_off, "cursor_ptr": own + self.cursor_off,
-                                    "frame_base": frame_lo, "frames": self.n_frames,
-                                    "mirrors": [self.base[r] + at + self.records_off for r in peers]}, self.capacity, mode=mode)
+                                    "frame_base": frame_lo, "frames": self.n_frames}, self.capacity, mode=mode)
         mark()
+        peer_records = (ctypes.c_void_p * max(len(peers), 1))(*[self.base[r] + at + self.records_off for r in peers])
         peer_cursors = (ctypes.c_void_p * max(len(peers), 1))(*[self.base[r] + at + self.cursor_off for r in peers])
         headers = (ctypes.c_void_p * self.world)(*[self.base[r] + at + self.rank * hdr for r in range(self.world)])
-        N.check(N.lib().cama_peer_publish_cursors(rt.ctx, own + self.cursor_off, frame_lo * self.lists_per_frame, n_local * self.lists_per_frame,
-                                                  peer_cursors, len(peers), self.step, headers, self.world, rt.stream()))
+        N.check(N.lib().cama_peer_publish_lists(rt.ctx, own + self.records_off, own + self.cursor_off, self.capacity,
+                                                frame_lo * self.lists_per_frame, n_local * self.lists_per_frame,
+                                                peer_records, peer_cursors, len(peers), self.step, headers, self.world, rt.stream()))
         mark()
         arrived = (ctypes.c_void_p * self.world)(*[own + r * hdr for r in range(self.world)])
         N.check(N.lib().cama_peer_wait(rt.ctx, arrived, self.world, self.step, 0, self.status.data_ptr(), rt.stream()))

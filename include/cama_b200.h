@@ -423,6 +423,13 @@ int cama_peer_publish_cursors(cama_ctx *ctx, const uint32_t *own_cursor, int64_t
                               void *stream);
 int cama_peer_wait(cama_ctx *ctx, void *const *headers, int world, uint32_t step, int timeout_ms, int32_t *status,
                    void *stream);
+/* cama_peer_publish_cursors preceded by the records themselves: the filled part of each of the rank's lists [first, first +
+ * count) is copied to the same place of every peer's list array with wide coalesced peer stores (a geometry call that ran
+ * WITHOUT list_record_mirrors; mirroring record by record from the geometry kernel is 8x slower over NVLink at 8 GPUs).
+ * capacity: records per list, a multiple of 4; arrays 16-byte aligned. */
+int cama_peer_publish_lists(cama_ctx *ctx, const void *own_records, const uint32_t *own_cursor, int64_t capacity, int64_t first,
+                            int64_t count, void *const *peer_records, void *const *peer_cursors, int n_peers, uint32_t step,
+                            void *const *headers, int n_headers, void *stream);
 
 /* ---- LiDAR aggregation (BASELINE.json configs[4]) -------------------------------- */
 

@@ -82,9 +82,6 @@ if res["lists_available"]:
     geo = {"phases": N.PHASE_GEOMETRY, "records_ptr": own + lx.records_off, "cursor_ptr": own + lx.cursor_off, "frame_base": asm2.lo, "frames": lx.n_frames}
     res["lists_geometry_local_only"] = timed(lambda: r.enqueue_phase(asm2.res, asm2.w2c_dev, asm2.hi - asm2.lo, geo, lx.capacity))
     dist.barrier()
-    at = (lx.step & 1) * lx.parity_bytes
-    geo_m = dict(geo, mirrors=[lx.base[q] + at + lx.records_off for q in range(world) if q != rank])
-    res["lists_geometry_mirrored"] = timed(lambda: r.enqueue_phase(asm2.res, asm2.w2c_dev, asm2.hi - asm2.lo, geo_m, lx.capacity))
     # phase times INSIDE full steps (events on the stream): geometry, publish, wait for the peers, raster
     import time
     dist.barrier(); torch.cuda.synchronize()
@@ -95,7 +92,7 @@ if res["lists_available"]:
         all_marks.append(marks)
     host_ms = (time.perf_counter() - t0) / 12 * 1e3
     torch.cuda.synchronize()
-    names = ("geometry", "publish", "wait", "raster")
+    names = ("geometry", "push+publish", "wait", "raster")
     res["lists_in_step_ms"] = {n: round(sum(m[i].elapsed_time(m[i + 1]) for m in all_marks[2:]) / len(all_marks[2:]), 4) for i, n in enumerate(names)}
     res["lists_in_step_ms"]["step_to_step"] = round(sum(a[0].elapsed_time(b[0]) for a, b in zip(all_marks[2:-1], all_marks[3:])) / (len(all_marks) - 3), 4)
     res["lists_host_enqueue_ms_per_step"] = round(host_ms, 4)
