@@ -60,7 +60,9 @@ def parse_args():
     ap.add_argument("--geometry-ctas", type=int, default=3,
                     help="resident geometry CTAs per SM while clips overlap on several streams (cama_clip_desc.geometry_ctas_per_sm; 4 takes every "
                          "register of an SM, 3 lets raster CTAs of another clip in); the single-stream loops use the library default")
-    ap.add_argument("--raster-ctas", type=int, default=0, help="cama_clip_desc.raster_ctas_per_sm for the overlapping clips (0 = library default)")
+    ap.add_argument("--raster-ctas", type=int, default=3,
+                    help="cama_clip_desc.raster_ctas_per_sm for the overlapping clips (0 = library default of 4: fastest for one clip alone; with 3 + 3 "
+                         "CTAs per SM geometry and raster CTAs of different clips co-reside)")
     ap.add_argument("--ramp-seconds", type=float, default=0.4, help="untimed clock-ramp loop before the warm-up (0 under ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded cpu_baseline sample")
     return ap.parse_args()

@@ -58,8 +58,8 @@ class ClipDesc(Structure):
         ("overlay_mirrors", c_void_p * 8), ("overlay_n_mirrors", c_int32), ("reserved0", c_int32), ("overlay_image_base", c_int64),
         ("camera_table", c_void_p), ("geometry_ctas_per_sm", c_int32), ("raster_ctas_per_sm", c_int32),
         ("mosaic_cols", c_int32), ("mosaic_tile_of_cam", c_int32 * 8),
-        ("phases", c_int32), ("list_frame_base", c_int32), ("list_frames", c_int32), ("list_n_mirrors", c_int32),
-        ("list_records", c_void_p), ("list_cursor", c_void_p), ("list_record_mirrors", c_void_p * 8),
+        ("phases", c_int32), ("list_frame_base", c_int32), ("list_frames", c_int32), ("reserved2", c_int32),
+        ("list_records", c_void_p), ("list_cursor", c_void_p),
     ]
 
 

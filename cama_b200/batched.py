@@ -154,10 +154,6 @@ class ClipRenderer:
             d.phases = int(lists["phases"])
             d.list_records, d.list_cursor = lists["records_ptr"], lists["cursor_ptr"]
             d.list_frame_base, d.list_frames = int(lists.get("frame_base", 0)), int(lists["frames"])
-            mirrors = list(lists.get("mirrors", ()))
-            d.list_n_mirrors = len(mirrors)
-            for m, ptr in enumerate(mirrors):
-                d.list_record_mirrors[m] = ptr
         if mosaic is not None:
             cols, tiles = mosaic
             d.mosaic_cols = int(cols)
@@ -337,7 +333,7 @@ class ClipRenderer:
     def enqueue_phase(self, res, w2c_dev, n_frames, lists, capacity, out=None, mode="binned"):
         """Asynchronous half pipeline on external record lists (cama_clip_desc.phases): the geometry of this rank's frames
         into lists the peers mirror, or the raster of all frames from complete lists.  ``lists``: dict(phases,
-        records_ptr, cursor_ptr, frames[, frame_base, mirrors]); ``capacity`` = records per list of those arrays."""
+        records_ptr, cursor_ptr, frames[, frame_base]); ``capacity`` = records per list of those arrays."""
         rt = self.rt
         if n_frames == 0:
             return

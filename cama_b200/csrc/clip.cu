@@ -83,8 +83,6 @@ struct ClipArgs {
     unsigned *cursor;                  // [F*C*n_groups] records appended (attempted) to each list so far (cleared by prep)
     unsigned *records;                 // [F*C*n_groups][list_cap] payloads
     int list_frame_base;               // frame f of this call is frame list_frame_base + f of the lists (frame-sharded clips)
-    int n_mirrors;                     // list arrays on peer GPUs that receive every record too
-    unsigned *mirror_records[CAMA_MAX_PEERS];
 };
 
 // ------------------------------------------------------------------------------------------------ camera table
@@ -320,11 +318,7 @@ __device__ __forceinline__ void stage_flush(const ClipArgs &a, GeoStage &st) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned pos = __shfl_sync(kFull, first[k], __ffs(peers[k]) - 1) + (unsigned)__popc(peers[k] & lt);
-            if (live[k] && pos < a.list_cap) {
-                const size_t at = (size_t)r[k].x * a.list_cap + pos;
-                a.records[at] = r[k].y;
-                for (int m = 0; m < a.n_mirrors; ++m) a.mirror_records[m][at] = r[k].y;      // (peer stores over NVLink: frame-sharded clips)
-            }
+            if (live[k] && pos < a.list_cap) a.records[(size_t)r[k].x * a.list_cap + pos] = r[k].y;
         }
     }
     __syncwarp();
@@ -707,6 +701,7 @@ struct RasterArgs {
     // VideoGenerator.concate_image (cama/tools.py:22-25): frame_stride = rows*H*cols*W*3, pitch = cols*W*3.
     int n_cams;
     unsigned pitch;
+    unsigned long long image_bytes;        // H*W*3
     unsigned long long frame_stride;
     unsigned long long cam_offset[CAMA_MAX_CAMERAS];
 };
@@ -920,7 +915,10 @@ __global__ void __launch_bounds__(kRasterBlock, CAMA_RASTER_MINB) binned_raster_
     const unsigned row_bytes = (unsigned)W * 3u, pitch = a.pitch;               // bytes of a row / distance between rows (equal for plain frames)
     const bool contiguous = pitch == row_bytes;
     const unsigned zero_bytes = (unsigned)kZeroRows * row_bytes;
-    auto image_offset = [&](int image) -> size_t { return (size_t)(image / a.n_cams) * a.frame_stride + a.cam_offset[image % a.n_cams]; };
+    // (plain frames: image i starts at i * H * W * 3; the division and the per-camera table are only needed for the mosaic)
+    auto image_offset = [&](int image) -> size_t {
+        return contiguous ? (size_t)image * a.image_bytes : (size_t)(image / a.n_cams) * a.frame_stride + a.cam_offset[image % a.n_cams];
+    };
     unsigned short *plane = reinterpret_cast<unsigned short *>(smem);
     unsigned *hits = reinterpret_cast<unsigned *>(smem + plane_bytes);
     unsigned char *zeros = smem + plane_bytes + kHitBytes;
@@ -1497,8 +1495,6 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
         a.records = static_cast<unsigned *>(d->list_records);
         a.cursor = d->list_cursor;
         a.list_frame_base = d->list_frame_base;
-        a.n_mirrors = d->list_n_mirrors;
-        for (int m = 0; m < d->list_n_mirrors; ++m) a.mirror_records[m] = static_cast<unsigned *>(d->list_record_mirrors[m]);
     } else {
         a.cursor = reinterpret_cast<unsigned *>(ws + p.off_cursor);
         a.records = reinterpret_cast<unsigned *>(ws + p.off_records);
@@ -1556,6 +1552,7 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
     if (const char *env = getenv("CAMA_RASTER_DEBUG")) r.debug = atoi(env);
     r.cursor = cursor; r.records = records; r.lut = lut; r.bg = d->background; r.frames = d->frames;
     r.n_cams = d->n_cams;
+    r.image_bytes = (unsigned long long)d->height * d->width * 3;
     r.frame_stride = frame_stride_bytes(d);
     {
         const size_t image = (size_t)d->height * d->width * 3, row = (size_t)d->width * 3;
@@ -1652,8 +1649,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         CAMA_REQUIRE(d->list_records && d->list_cursor, "split phases need external record lists (list_records, list_cursor)");
         CAMA_REQUIRE(d->list_frame_base >= 0 && (d->list_frames == 0 ? d->list_frame_base == 0 : d->list_frame_base + d->n_frames <= d->list_frames),
                      "this call's frames do not fit the external lists");
-        CAMA_REQUIRE(d->list_n_mirrors >= 0 && d->list_n_mirrors <= CAMA_MAX_PEERS, "list_n_mirrors out of range");
-        for (int m = 0; m < d->list_n_mirrors; ++m) CAMA_REQUIRE(d->list_record_mirrors[m], "list_record_mirrors[%d] is NULL", m);
         CAMA_REQUIRE(!d->crop_counts && !d->visible_counts && !d->vu_dense, "the per-instance debug outputs need the whole pipeline in one call");
     }
     CAMA_REQUIRE(d->chassis2cam && d->intrinsics, "NULL buffer in desc");

@@ -275,8 +275,8 @@ typedef struct cama_clip_desc {
      * The record lists may live outside the workspace — in memory the peers can write — and a call may run only one half
      * of the pipeline:
      *   phases = CAMA_PHASE_GEOMETRY  prep + geometry of this call's n_frames frames, which are frames list_frame_base ..
-     *            of the lists; every record is also stored at the same place of list_record_mirrors[0 .. list_n_mirrors)
-     *            (the peers' list arrays, over NVLink); only the cursors of this call's frames are cleared and advanced;
+     *            of the lists; only the cursors of this call's frames are cleared and advanced (cama_peer_publish_lists
+     *            then copies the filled lists to the peers);
      *   phases = CAMA_PHASE_RASTER    work lists + raster of n_frames frames (normally all list_frames) from lists that are
      *            complete (cursors of the other ranks' frames delivered by cama_peer_publish_cursors / cama_peer_wait).
      * list_records: device uint32 [list_frames * n_cams * n_bands][record_capacity]; list_cursor: device uint32
@@ -284,10 +284,9 @@ typedef struct cama_clip_desc {
     int32_t phases;                 /* 0 = the whole pipeline */
     int32_t list_frame_base;
     int32_t list_frames;            /* 0 = n_frames */
-    int32_t list_n_mirrors;
+    int32_t reserved2;
     void *list_records;             /* NULL = inside the workspace */
     uint32_t *list_cursor;
-    void *list_record_mirrors[CAMA_MAX_PEERS];
 } cama_clip_desc;
 
 typedef struct cama_clip_stats {
@@ -425,7 +424,7 @@ int cama_peer_wait(cama_ctx *ctx, void *const *headers, int world, uint32_t step
                    void *stream);
 /* cama_peer_publish_cursors preceded by the records themselves: the filled part of each of the rank's lists [first, first +
  * count) is copied to the same place of every peer's list array with wide coalesced peer stores (a geometry call that ran
- * WITHOUT list_record_mirrors; mirroring record by record from the geometry kernel is 8x slower over NVLink at 8 GPUs).
+ * (mirroring record by record from the geometry kernel was measured: 8x slower over NVLink at 8 GPUs).
  * capacity: records per list, a multiple of 4; arrays 16-byte aligned. */
 int cama_peer_publish_lists(cama_ctx *ctx, const void *own_records, const uint32_t *own_cursor, int64_t capacity, int64_t first,
                             int64_t count, void *const *peer_records, void *const *peer_cursors, int n_peers, uint32_t step,

@@ -851,9 +851,9 @@ def test_device_mosaic_layout(rt, config2_clip):
 
 def test_split_phases_with_external_lists(rt, config2_clip):
     """The two halves of the pipeline on record lists outside the workspace (cama_clip_desc.phases / list_*), as the
-    list exchange of a frame-sharded clip runs them: geometry of frame blocks [0,15), [15,29), [29,40) — each block's
-    records also mirrored into a second list array — then ONE raster call over all 40 frames, from the primary arrays and
-    from the mirror: both equal the ordinary render."""
+    list exchange of a frame-sharded clip runs them: geometry of frame blocks [0,15), [15,29), [29,40), then ONE raster
+    call over all 40 frames — from the arrays the geometry wrote and from a copy of their filled parts (what
+    cama_peer_publish_lists makes on a peer): both equal the ordinary render."""
     import torch
     from cama_b200 import _native as N
     from cama_b200.batched import Reproject
@@ -871,8 +871,10 @@ def test_split_phases_with_external_lists(rt, config2_clip):
     (rec, cur), (rec_m, cur_m) = arrays
     for lo, hi in ((0, 15), (15, 29), (29, 40)):
         r.enqueue_phase(res, w2c_dev[lo:hi], hi - lo, {"phases": N.PHASE_GEOMETRY, "records_ptr": rec.data_ptr(), "cursor_ptr": cur.data_ptr(),
-                                                        "frame_base": lo, "frames": F, "mirrors": [rec_m.data_ptr()]}, cap)
-    cur_m.copy_(cur)                                       # (what cama_peer_publish_cursors does for a peer)
+                                                        "frame_base": lo, "frames": F}, cap)
+    cur_m.copy_(cur)                                       # (what cama_peer_publish_lists does for a peer: lengths + the filled part of every list)
+    filled = torch.arange(cap, device="cuda")[None, :] < cur[:, None]
+    rec_m[filled] = rec[filled]
     for records, cursor in ((rec, cur), (rec_m, cur_m)):
         out = torch.empty_like(want)
         r.enqueue_phase(res, None, F, {"phases": N.PHASE_RASTER, "records_ptr": records.data_ptr(), "cursor_ptr": cursor.data_ptr(), "frame_base": 0, "frames": F},
