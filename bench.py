@@ -56,6 +56,7 @@ def parse_args():
                     help="default: config2 on one GPU, config3 (the site, sharded by frame) on several")
     ap.add_argument("--mode", default="auto", choices=["auto", "binned", "plane"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the config-3 (site, 320 frames) block of the single-GPU line")
     ap.add_argument("--lanes", type=int, default=3, help="CUDA streams the K steps are dealt over (independent clips overlap); 1 = one stream")
     ap.add_argument("--geometry-ctas", type=int, default=3,
                     help="resident geometry CTAs per SM while clips overlap on several streams (cama_clip_desc.geometry_ctas_per_sm; 4 takes every "
@@ -251,6 +252,53 @@ def run_reference(args):
             runner.close()
 
 
+def config3_block(args, root, device):
+    """The site of BASELINE.json configs[2] on one GPU: ms per step (one stream; the library pipelines its frame groups over
+    its own lanes), per-phase times from CUDA events, raster and whole-step roofline figures."""
+    import torch
+    from cama_b200 import synth
+    from cama_b200 import _native as N
+    from cama_b200.batched import Reproject
+    clip, dataset = make_clip("config3", root, 0)
+    rp = Reproject(synth.CAMA_CONFIGS, clip, device=device)
+    rt, res = rp.rt, rp.resident(dataset)
+    idx, w2c = rp.frame_poses(dataset)
+    F, C = len(idx), rp.renderer.n_cams
+    w2c_dev = torch.from_numpy(w2c).to(rt.device)
+    frames = torch.empty((F, C, H, W, 3), dtype=torch.uint8, device=rt.device)
+    rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=True)
+    stats = dict(rp.renderer.last_stats)
+    steps = max(5, args.steps // 3)
+    step = lambda: rp.renderer.render(res, w2c_dev, out=frames, mode=args.mode, check=False)
+    for _ in range(3):
+        step()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    rt.profile_enable(steps)                       # (phase events: the frame groups then run in one pass on one stream)
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    phases = rt.profile_read().mean(axis=0)
+    rt.profile_enable(0)
+    frame_bytes, vertex_bytes = F * C * H * W * 3, F * 12 * res.n_vertices
+    raster_ms = float(phases[3])
+    return {"workload": workload_name("config3"), "frames": F, "cams": C, "vertices": res.n_vertices, "instances": res.n_instances,
+            "value": F * C / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "records_total": int(stats["records_total"]), "record_capacity": int(stats["record_capacity"]),
+            "roofline": {"bound": "hbm", "kernel": "binned_raster_kernel", "achieved": frame_bytes / (raster_ms * 1e-3) / 1e9, "unit": "GB/s",
+                         "algorithmic_bytes_per_launch": int(frame_bytes), "launch_ms": raster_ms,
+                         "launch_ms_source": "CUDA events on the launching stream around the raster phase, mean over a second run of the same steps",
+                         "whole_step": {"algorithmic_bytes": int(frame_bytes + vertex_bytes), "achieved": (frame_bytes + vertex_bytes) / (ms * 1e-3) / 1e9},
+                         "phase_ms": {name: float(phases[i]) for i, name in enumerate(N.PHASE_NAMES)}}}
+
+
 def host_memory_probe(threads):
     """STREAM-like fill / copy bandwidth of this process's host threads (cama_host_bandwidth_probe), GB/s."""
     import ctypes
@@ -418,6 +466,12 @@ def run_b200(args):
     dropin_t, dropin_done, _ = dropin_loop(cm_dropin, dataset, H, W, max_frames=min(F, 20))
     dropin_s = sum(dropin_t.values())
 
+    # ---- BASELINE.json configs[2] on this GPU: the site (320 frames x 6 cameras, ~767 k vertices), whose 5.9 GB of algorithmic
+    # traffic per step is the size BASELINE.md asks the roofline fraction for (config 2 moves 0.42 GB: a latency-sized problem)
+    site = None
+    if not args.no_config3 and args.workload == "config2":
+        site = config3_block(args, tmp.name, local_rank)
+
     clocks = sampler.stop()
 
     if rank == 0:
@@ -490,6 +544,11 @@ def run_b200(args):
                          "phase_ms": {name: float(np.mean(phases[:, i])) for i, name in enumerate(N.PHASE_NAMES)}},
             "records": {k: int(stats[k]) for k in ("records_total", "record_capacity_needed", "record_capacity")},
         }
+        if site is not None:
+            site["roofline"]["peak"] = peak
+            site["roofline"]["frac"] = site["roofline"]["achieved"] / peak
+            site["roofline"]["whole_step"]["frac"] = site["roofline"]["whole_step"]["achieved"] / peak
+            line["config3"] = site
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
