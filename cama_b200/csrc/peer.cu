@@ -359,7 +359,7 @@ int cama_peer_wait(cama_ctx *ctx, void *const *headers, int world, uint32_t step
         CAMA_REQUIRE(headers[i], "headers[%d] is NULL", i);
         hp.p[i] = headers[i];
     }
-    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 10000) * 1000000ull;
     peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hp, world, step, timeout_ns, status);
     CAMA_LAUNCHED(ctx);
     return CAMA_OK;
@@ -404,7 +404,7 @@ int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, int own_rank,
         CAMA_REQUIRE(slots[r] && ((uintptr_t)slots[r] & 255) == 0, "slots[%d] must be a 256-byte aligned device pointer", r);
         sp.p[r] = slots[r];
     }
-    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 10000) * 1000000ull;
     // a few CTAs per SM: the record loop is grid-stride, and every CTA first waits for the peers' step numbers
     const unsigned grid = (unsigned)ctx->sm_count * 8u;
     if (format == CAMA_OVERLAY_PALETTE) {

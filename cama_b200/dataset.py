@@ -168,8 +168,17 @@ class ClipManager:
             size = {(cm.width, cm.height) for cm in self.cm_list}
             if len(size) == 1:
                 width, height = next(iter(size))
+                from .reproject import InstanceList
                 results = get_runtime(self._device).project_points_cameras(dev["points"], dev["offsets"], dev["n_inst"], cams, width, height)
-                return {cm.camera_name: unpack_instances(vu, offs, dev["classes"]) for cm, (vu, offs) in zip(self.cm_list, results)}
+                out = {}
+                for cm, (vu, offs, d_vu, d_offs) in zip(self.cm_list, results):
+                    maps_2d = InstanceList(unpack_instances(vu, offs, dev["classes"]))
+                    # (render_maps on this very list finds its points on the device already)
+                    maps_2d.device_points = None if d_vu is None else {"points": d_vu, "offsets": d_offs, "host_offsets": offs, "classes": dev["classes"],
+                                                                       "n_inst": dev["n_inst"], "n_kept": len(maps_2d), "host_flat": vu,
+                                                                       "host_sum": float(vu.sum()) if vu.size else 0.0}
+                    out[cm.camera_name] = maps_2d
+                return out
         return {cm.camera_name: cm.transform_project_to_image(maps_3d) for cm in self.cm_list}
 
     def render_vectors(self, maps_2d_dict, image_idx):

@@ -83,6 +83,10 @@ class InstanceList(list):
     pack and upload them again.  Behaves like the plain list in every other respect."""
     __slots__ = ("device_points",)
 
+    def __init__(self, *args):
+        super().__init__(*args)
+        self.device_points = None
+
 
 def densify_polyline(points, resolution):
     """Dense float32 points of one polyline (reference :49-63 / :79-93), vectorised.
@@ -315,6 +319,10 @@ class CameraManager(BaseManager):
         """Stamp every point as a radius-2 filled disc, instance after instance, in place."""
         if len(maps_2d) == 0:
             return image
+        dev = MapManager.device_points_if_untouched(maps_2d)
+        if dev is not None and "host_offsets" in dev:      # the list project_all_camera returned, untouched: its points are on the device
+            bgr = np.array([render_bgr_of_class(c) for c in dev["classes"]], dtype=np.uint8).reshape(-1, 3)
+            return get_runtime(self._device).render_points(image, None, dev["host_offsets"], bgr, device_points=(dev["points"], dev["offsets"]))
         flat, offsets, classes = pack_instances(maps_2d)
         bgr = np.array([render_bgr_of_class(c) for c in classes], dtype=np.uint8).reshape(-1, 3)
         return get_runtime(self._device).render_points(image, flat, offsets, bgr)

@@ -196,7 +196,7 @@ class Runtime:
         torch = _torch()
         n, n_cams = int(d_pts.shape[0]), len(cameras)
         if n == 0:
-            return [(np.zeros((0, 2)), np.zeros(n_inst + 1, np.int64)) for _ in cameras]
+            return [(np.zeros((0, 2)), np.zeros(n_inst + 1, np.int64), None, None) for _ in cameras]
         d_vu = torch.empty((n_cams, n, 2), dtype=torch.float64, device=self.device)
         d_offs = torch.empty((n_cams, n_inst + 1), dtype=torch.int64, device=self.device)
         need = ctypes.c_size_t()
@@ -211,7 +211,8 @@ class Runtime:
         offs = d_offs.cpu().numpy()                                  # (synchronises)
         most = int(offs[:, -1].max())
         vu = d_vu[:, :most].cpu().numpy() if most else np.zeros((n_cams, 0, 2))
-        return [(vu[c, :int(offs[c, -1])], offs[c]) for c in range(n_cams)]
+        # (the device copies ride along: render_maps on the list this becomes does not upload the points again)
+        return [(vu[c, :int(offs[c, -1])], offs[c], d_vu[c, :int(offs[c, -1])], d_offs[c]) for c in range(n_cams)]
 
     def project_points(self, flat, offsets, K, width, height, T=None):
         """cama_project_points -> ((k,2) f64 (v,u), new offsets)."""
@@ -231,22 +232,29 @@ class Runtime:
         out_off = d_out_off.cpu().numpy()
         return d_out[:int(out_off[-1])].cpu().numpy(), out_off
 
-    def render_points(self, image, vu_flat, offsets, inst_bgr):
+    def render_points(self, image, vu_flat, offsets, inst_bgr, device_points=None):
         """render_maps on a host image (uint8 HxWx3 numpy): stamps in place and returns it.
+        ``device_points``: (device (k,2) float64 (v,u), device int64 offsets) when the points are on the device already.
 
         The image itself never crosses PCIe when its width is a multiple of 8 (and it is writeable and contiguous):
         cama_render_points_overlay returns the lit 8-pixel chunks (~160 KB for a 540x960 frame of config 2) and
         cama_overlay_apply_host draws them into ``image``.  Otherwise: upload, cama_render_points, download."""
         torch = _torch()
         assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3, "image must be uint8 [H,W,3]"
-        vu = np.ascontiguousarray(vu_flat, dtype=np.float64)
-        n, n_inst = vu.shape[0], len(offsets) - 1
+        n_inst = len(offsets) - 1
+        if device_points is not None:
+            d_vu, d_off = device_points
+            n = int(d_vu.shape[0])
+        else:
+            vu = np.ascontiguousarray(vu_flat, dtype=np.float64)
+            n = vu.shape[0]
         if n == 0:
             return image
         height, width = image.shape[:2]
-        d_vu = self.to_device(vu)
-        d_off = self.to_device(offsets, np.int64)
-        d_bgr = self.to_device(inst_bgr, np.uint8)
+        if device_points is None:
+            d_vu = self.to_device(vu)
+            d_off = self.to_device(offsets, np.int64)
+        d_bgr = self._cached_bgr(inst_bgr)
         need = ctypes.c_size_t()
         N.check(N.lib().cama_render_workspace_bytes(height, width, ctypes.byref(need)))
         ws = self.scratch("render", need.value)
@@ -271,6 +279,15 @@ class Runtime:
             image[...] = result            # the reference draws in place (cv2.circle mutates its argument)
             return image
         return result
+
+    def _cached_bgr(self, inst_bgr):
+        """instance colours on the device; the same array (by content) is uploaded once"""
+        arr = np.ascontiguousarray(inst_bgr, dtype=np.uint8)
+        key = arr.tobytes()
+        hit = self._scratch.get("bgr_cache")
+        if hit is None or hit[0] != key:
+            hit = self._scratch["bgr_cache"] = (key, self.to_device(arr, np.uint8))
+        return hit[1]
 
     def _pinned_records(self, n_records):
         torch = _torch()

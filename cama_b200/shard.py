@@ -211,6 +211,12 @@ class PeerExchange:
             N.lib().cama_peer_free(self.rt.ctx, self._own)
             self._own = ctypes.c_void_p()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                            # (interpreter shutdown: the driver frees the memory anyway)
+            pass
+
     def slot(self, owner, parity, source):
         """device pointer (in this process) of the slot of `source`'s records in `owner`'s mailbox"""
         return self.base[owner] + self.offset(parity, source)
@@ -376,6 +382,7 @@ class ListExchange:
             self.close()
 
     close = PeerExchange.close
+    __del__ = PeerExchange.__del__
 
     def render_and_assemble(self, renderer, res, w2c_dev, frame_lo, out, mode="binned", marks=None):
         """One step (asynchronous): geometry of this rank's frames [frame_lo, frame_lo + len(w2c_dev)) into everybody's
@@ -472,17 +479,18 @@ class SiteAssembler:
         self.lo, self.hi = frame_block(self.n_frames, self.rank, self.world)
         self.w2c_dev = torch.from_numpy(np.ascontiguousarray(w2c[self.lo:self.hi], dtype=np.float32).reshape(-1, 16)).to(rt.device)
         _, n, fmt = r.render_overlay(self.res, self.w2c_dev, mode=mode)          # settles the centre-record lists, counts the lit chunks
-        stats = r.last_stats or {}
-        most = torch.tensor([int(n), int(stats.get("record_capacity", 0)), int(stats.get("record_capacity_needed", 0))], dtype=torch.int64, device=rt.device)
-        dist.all_reduce(most, op=dist.ReduceOp.MAX, group=group)
+        stats = (r.last_stats or {}) if self.hi > self.lo else {}          # (a rank with an empty block has rendered nothing)
+        most = torch.tensor([int(n), int(stats.get("record_capacity", 0)), int(stats.get("record_capacity_needed", 0)), int(stats.get("lists_per_image", 0))],
+                            dtype=torch.int64, device=rt.device)
+        dist.all_reduce(most, op=dist.ReduceOp.MAX, group=group)           # every rank decides from the same numbers
         if exchange == "auto":
             exchange = "lists" if self.world <= 4 else "chunks"
         self.kind = exchange
         self.frames = None
         self.render_stream = None
-        if exchange == "lists" and _MODES_BINNED(mode) and stats.get("lists_per_image", 0) > 0:
+        if exchange == "lists" and _MODES_BINNED(mode) and int(most[3].item()) > 0:
             capacity = max(int(most[1].item()), int(int(most[2].item()) * 1.1) + 256)       # every rank: the same list capacity
-            self.exchange = ListExchange(rt, r, self.res, self.n_frames, capacity, stats["lists_per_image"], group=group)
+            self.exchange = ListExchange(rt, r, self.res, self.n_frames, capacity, int(most[3].item()), group=group)
         else:
             self.kind = "chunks"
             self.exchange = PeerExchange(rt, int(int(most[0].item()) * 1.25) + 4096, fmt, group=group)

@@ -400,7 +400,7 @@ int cama_peer_close(cama_ctx *ctx, void *dev_ptr);
 int cama_peer_publish(cama_ctx *ctx, const uint32_t *overlay_count, uint32_t step, void *const *slot_headers, int n, void *stream);
 /* slots: host array of `world` device pointers, the slots of this rank's own mailbox that hold the records of rank
  * 0..world-1 for `step`.  Slot after slot, starting with own_rank's: waits on the device until the slot carries `step`
- * (at most timeout_ms in all, <= 0: 2000), then writes the 8 pixels of each of its records into frames uint8
+ * (at most timeout_ms in all, <= 0: 10000), then writes the 8 pixels of each of its records into frames uint8
  * [n_frames,n_cams,H,W,3] (device, zero-filled by the caller, e.g. with cama_frames_clear).
  * status: device int32 [1], caller zero-fills once; set to 1 when a peer's step did not arrive in time (its records are
  * missing), 2 when a slot held more records than capacity_records (frames incomplete).  palette_*: as
@@ -414,7 +414,7 @@ int cama_peer_expand(cama_ctx *ctx, void *const *slots, int world, int own_rank,
  * mirrored the records of its frames into the peers' list arrays; cama_peer_publish_cursors copies the rank's cursor range
  * [first, first + count) (own_cursor: this rank's array) into the same range of the n_peers peer arrays and then writes
  * `step`, with release semantics at system scope, into the n_headers headers (own and peers'); cama_peer_wait (one warp)
- * waits on `stream` until the `world` headers in this rank's own memory carry `step` (timeout_ms <= 0: 2000; status 1 on a
+ * waits on `stream` until the `world` headers in this rank's own memory carry `step` (timeout_ms <= 0: 10000; status 1 on a
  * time-out), so that the raster-phase call enqueued after it sees complete lists.  Every rank then rasters EVERY frame from
  * the lists: the dense frames are written once, by the HBM-bound kernel that writes them anyway — no zero-fill, no expand. */
 int cama_peer_publish_cursors(cama_ctx *ctx, const uint32_t *own_cursor, int64_t first, int64_t count,
