@@ -517,10 +517,11 @@ def run_b200(args):
                             "into the host frames [F,C,540,960,3]",
                     "transfer": "sparse", "overlay_records": int(transfer["records"]), "checksum": checksum,
                     "host_memory": {"fill_gbs": host_fill_gbs, "copy_gbs": host_copy_gbs, "threads": int(rp.host_threads),
-                                    "line_traffic_bytes_per_step": int(transfer["records"]) * 2 * 128,
+                                    "line_traffic_bytes_per_step": [int(transfer["records"]) * 2 * 48, int(transfer["records"]) * 2 * 128],
                                     "note": "fill/copy: STREAM-like figures of the worker pool that blanks and draws the lit chunks; line_traffic = "
-                                            "records x 2 (blank + draw) x 128 B, what the call would move to and from DRAM if no lit line stayed in the "
-                                            "last-level cache between blank and draw (an upper estimate: ~80 MB of distinct lines per clip do)"},
+                                            "records x 2 (blank + draw) x (read-for-ownership + write-back) of the 64-byte lines touched, between 24/64 of a "
+                                            "line per chunk (adjacent chunks share lines) and a line per chunk — what the call moves to and from DRAM if no "
+                                            "lit line stays in the last-level cache between blank and draw (with one clip's ~80 MB of lit lines most do)"},
                     "host_draw_threads": int(rp.host_threads), "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
                     "dense": {"value": world * cam_frames * dense_steps / dense_s, "unit": UNIT, "ms_per_step": 1e3 * dense_s / dense_steps,
                               "d2h_bytes_per_step": int(frame_bytes), "d2h_gbs": frame_bytes * dense_steps / dense_s / 1e9,
@@ -756,11 +757,13 @@ def run_b200_sharded(args):
                             "cama_overlay_apply_host into the rank's host frames; the site's frames end up in host memory once, split over the ranks",
                     "checksum_all_ranks": int(sums[0].item()), "host_draw_threads_per_rank": int(rp.host_threads),
                     "host_memory": {"fill_gbs_all_ranks": float(host_bw[0].item()), "copy_gbs_all_ranks": float(host_bw[1].item()),
-                                    "line_traffic_bytes_per_step": int(sums[1].item()) * 2 * 128,
-                                    "bound_ms_per_step": int(sums[1].item()) * 2 * 128 / max(float(host_bw[1].item()), 1e-9) / 1e6,
+                                    "line_traffic_bytes_per_step": [int(sums[1].item()) * 2 * 48, int(sums[1].item()) * 2 * 128],
+                                    "ms_per_step_at_copy_bandwidth": [int(sums[1].item()) * 2 * b / max(float(host_bw[1].item()), 1e-9) / 1e6 for b in (48, 128)],
                                     "note": "fill/copy: STREAM-like figures of all ranks' worker pools running at once (they share the box's memory system); "
-                                            "line_traffic = records x 2 (blank + draw) x 128 B = DRAM traffic if no lit line stays in the last-level cache "
-                                            "(with N ranks x 373 MB of host frames few do); bound_ms_per_step = that traffic at the copy bandwidth"},
+                                            "line_traffic = records x 2 (blank + draw) x (read-for-ownership + write-back) of the 64-byte lines touched, between "
+                                            "24/64 of a line per chunk (adjacent chunks share lines) and a line per chunk; with N ranks x 373 MB of host frames "
+                                            "the lit lines do not stay in the last-level cache, so the step is bound by this traffic at the bandwidth these "
+                                            "threads reach (ms_per_step_at_copy_bandwidth: the two ends)"},
                     "host_cores": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": ("binned_raster_kernel over all frames of the site (every frame byte written once per rank)" if asm.available and asm.kind == "lists"
