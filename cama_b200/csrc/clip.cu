@@ -157,13 +157,13 @@ __global__ void prep_kernel(const float *__restrict__ w2c, int n_frames, double 
                             const uint8_t *__restrict__ inst_bgr, int n_inst, unsigned *__restrict__ lut,
                             unsigned *__restrict__ zero, long long zero_words, unsigned *__restrict__ stats, int stats_words,
                             unsigned *__restrict__ overlay_count, const uint8_t *__restrict__ inst_palette,
-                            unsigned *__restrict__ zero2, long long zero2_words) {
+                            unsigned *__restrict__ zero2, long long zero2_words, unsigned groups_used) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();                                    // (the previous clip's raster still reads the counters cleared here)
     pdl_trigger();
     for (long long k = i; k < zero_words; k += (long long)gridDim.x * blockDim.x) zero[k] = 0u;
     for (long long k = i; k < zero2_words; k += (long long)gridDim.x * blockDim.x) zero2[k] = 0u;      // (external list cursors of this call's frames)
-    if (i < stats_words) stats[i] = 0u;
+    if (i < stats_words) stats[i] = i == stats_words - 1 ? groups_used : 0u;       // (ClipStatsDev: counters cleared, groups_used set)
     if (i == 0 && overlay_count) *overlay_count = 0u;
     if (w2c && i < n_frames * 12) w2c64[i] = (double)w2c[(i / 12) * 16 + (i % 12)];
     // lut[ordinal+1] = B | G << 8 | R << 16 | palette entry << 24 (the raster never looks at the top byte of a colour)
@@ -583,8 +583,9 @@ struct ClipStatsDev {
     unsigned long long records_total;      // appended to all lists (attempted)
     unsigned long long list_max;           // the fullest list (attempted)
     unsigned overflow;
-    unsigned pad;
+    unsigned groups_used;                  // written by prep: statistics blocks (frame groups) the render that owns this block used
 };
+static_assert(sizeof(ClipStatsDev) == 24, "prep_kernel writes groups_used as the last 32-bit word");
 
 // One thread per raster work item = (frame, camera, band).  The items are sorted into four work lists by the weight
 // of their band group's record list: >= kHeavyBand / >= kMediumBand (per band of the group) / >= 1 records (claimed dynamically by the raster CTAs, in
@@ -1324,9 +1325,9 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     p.mode = mode;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p.off_stats = take(sizeof(ClipStatsDev));                             // first, in every layout: cama_clip_stats_read finds block 0 at the workspace's start
     p.off_w2c64 = take(sizeof(double) * 12 * (size_t)std::max(d->n_frames, 1));
     p.off_lut = take(sizeof(unsigned) * ((size_t)d->n_instances + 1));
-    p.off_stats = take(sizeof(ClipStatsDev));
     p.geo_units = ((d->n_vertices + kGeoThreads - 1) / kGeoThreads) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
     p.off_worklist = take(sizeof(unsigned long long) * (size_t)std::max<long long>(p.geo_units, 1));
     p.off_zero = off;                                                      // cleared by prep every call: counters | hist (BINNED)
@@ -1394,7 +1395,7 @@ struct Lanes {
 // Enqueues one pass over the frames of `d` with the workspace slice `ws` laid out by `p`.  image_base: index of the
 // pass's first (frame, camera) image inside the clip (sparse output); first: this pass clears the clip-wide counters.
 int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsigned char *ws, const CamBlock &cams, const Lanes &lanes,
-                cudaEvent_t *prof, int image_base, bool first) {
+                cudaEvent_t *prof, int image_base, bool first, int groups_used) {
     cudaStream_t s = lanes.geo;
     auto mark = [&](int i) { return prof ? cudaEventRecord(prof[i], s) : cudaSuccess; };
     CAMA_CUDA_TRY(mark(0));
@@ -1444,7 +1445,8 @@ int render_pass(cama_ctx *ctx, const cama_clip_desc *d, const ClipPlan &p, unsig
                                d->instance_bgr, d->n_instances, lut,
                                reinterpret_cast<unsigned *>(ws + p.off_zero), zero_words,
                                reinterpret_cast<unsigned *>(stats), (int)(sizeof(ClipStatsDev) / 4),
-                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette, zero2, zero2_words));
+                               d->overlay_records && first ? d->overlay_count : (unsigned *)nullptr, d->instance_palette, zero2, zero2_words,
+                               (unsigned)groups_used));
         CAMA_LAUNCHED(ctx);
     }
     const long long n_tiles = (d->n_vertices + kGeoThreads - 1) / kGeoThreads;
@@ -1691,7 +1693,6 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
     CamBlock cams;
     fill_cam_block(cams, d->n_cams, d->chassis2cam, d->intrinsics, d->crop_box, d->width, d->height);
 
-    ctx->last_render_grouped = p.groups > 1 && !prof;
     if (p.groups <= 1 || prof) {                       // one pass, one stream (phase events would serialise the lanes anyway)
         ClipPlan whole = p;
         if (p.groups > 1) {
@@ -1699,7 +1700,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
             if (rc != CAMA_OK) return rc;
         }
         Lanes lanes{s, s, s, nullptr, nullptr};
-        return render_pass(ctx, d, whole, ws, cams, lanes, prof, 0, true);
+        return render_pass(ctx, d, whole, ws, cams, lanes, prof, 0, true, 1);
     }
 
     // Frame-group pipeline.  Lane 0 = the caller's stream: prep + geometry of every group, back to back; lane 1:
@@ -1736,7 +1737,7 @@ int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *d, void *workspace, si
         if (d->frames) sub.frames = d->frames + (size_t)f0 * frame_stride_bytes(d);
         if (d->background) sub.background = d->background + (size_t)f0 * frame_stride_bytes(d);
         Lanes lanes{s, s_sort, s_raster, ctx->pipe_events[2 * g], ctx->pipe_events[2 * g + 1]};
-        rc = render_pass(ctx, &sub, q, ws + (size_t)g * p.group_stride, cams, lanes, nullptr, f0 * d->n_cams, g == 0);
+        rc = render_pass(ctx, &sub, q, ws + (size_t)g * p.group_stride, cams, lanes, nullptr, f0 * d->n_cams, g == 0, p.groups);
         if (rc != CAMA_OK) return rc;
     }
     CAMA_CUDA_TRY(cudaEventRecord(e_join, s_raster));          // (the raster lane's last kernel waited for everything on the sort lane)
@@ -1759,23 +1760,19 @@ int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *d, const void *wor
         return CAMA_OK;
     }
     DeviceGuard guard(ctx->device);
-    const bool grouped = p.groups > 1 && ctx->last_render_grouped;      // (phase-profiled renders are un-grouped)
-    const int n_blocks = grouped ? p.groups : 1;
-    ClipPlan q = p;
-    if (p.groups > 1) {
-        cama_clip_desc sub = *d;
-        if (grouped) sub.n_frames = p.group_frames;
-        rc = make_plan(&sub, q, false);
-        if (rc != CAMA_OK) return rc;
-    }
+    // The statistics block of a pass sits at the start of its workspace slice and names the number of slices (frame
+    // groups) the render used: 1 for a one-pass render (also a phase-profiled one), p.groups for the pipeline.  So the
+    // layout of the render that last used this workspace is read from the workspace itself, not remembered in the context.
+    const int n_blocks = std::max(p.groups, 1);
     std::vector<ClipStatsDev> h((size_t)n_blocks);
     unsigned n_overlay = 0;
     const bool sparse = d->overlay_records && d->overlay_count;
     for (int g = 0; g < n_blocks; ++g)
-        CAMA_CUDA_TRY(cudaMemcpyAsync(&h[g], static_cast<const unsigned char *>(workspace) + (size_t)g * p.group_stride + q.off_stats, sizeof(ClipStatsDev),
+        CAMA_CUDA_TRY(cudaMemcpyAsync(&h[g], static_cast<const unsigned char *>(workspace) + (size_t)g * p.group_stride + p.off_stats, sizeof(ClipStatsDev),
                                       cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     if (sparse) CAMA_CUDA_TRY(cudaMemcpyAsync(&n_overlay, d->overlay_count, sizeof(n_overlay), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CAMA_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));      // one round trip for all counters
+    h.resize((size_t)std::min<unsigned>(std::max(h[0].groups_used, 1u), (unsigned)n_blocks));
     unsigned long long total = 0, max_per_frame = 0;
     unsigned overflow = 0;
     for (const ClipStatsDev &b : h) {

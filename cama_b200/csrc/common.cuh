@@ -78,5 +78,4 @@ struct cama_ctx {
     cudaStream_t pipe_streams[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> pipe_events;
     std::vector<cudaEvent_t> fetch_events;     // cama_overlay_fetch_apply: one per record slice
-    bool last_render_grouped = false;      // workspace layout of the most recent cama_clip_render (read by cama_clip_stats_read)
 };

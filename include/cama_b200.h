@@ -18,9 +18,11 @@
  *   - every device call takes the cudaStream_t to enqueue on as a void* (0 = legacy
  *     default stream) and returns after enqueueing; no call synchronises unless its
  *     comment says so.  Calls on different streams are independent as long as they use different
- *     workspaces; the context itself carries a launch counter, the phase-profiling events
- *     (cama_ctx_profile_*: enable/read from one thread at a time) and the helper streams of the
- *     frame-group pipeline, which every cama_clip_render call orders behind its own stream.
+ *     workspaces (everything a later call needs to know about an earlier one — e.g. the layout
+ *     cama_clip_stats_read has to read — is in the workspace); the context itself carries a launch
+ *     counter, the phase-profiling events (cama_ctx_profile_*: enable/read from one thread at a time)
+ *     and the helper streams of the frame-group pipeline, which every cama_clip_render call orders
+ *     behind its own stream.
  *   - images are uint8 [H,W,3] BGR, row-major, as in the reference (cv2 convention).
  *   - point arrays are row-major [n,3] (x,y,z) or [n,2] (v,u) = (row,col), like the
  *     reference's "points" arrays; ragged instance lists are flat arrays plus

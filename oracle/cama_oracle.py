@@ -5,7 +5,8 @@ A NumPy/SciPy/OpenCV restatement of the algorithm in the reference
 container).  Every function cites the reference lines it restates.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
 reference`` legs of ``bench.py`` may import this module; the product package
-``cama_b200`` never does (tests/test_layout.py enforces that).
+``cama_b200`` never does (tests/test_native_abi.py::test_product_never_imports_the_oracle
+enforces that).
 
 Parity pinning: the reference itself has no tests or golden vectors
 (SURVEY.md section 4), so this oracle is pinned against OUTPUTS OF THE
