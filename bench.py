@@ -9,10 +9,12 @@ transformed, cropped, projected, masked and stamped into the uint8 [F,C,540,960,
 (40 frames x 6 cameras, 200 polylines, 0.1 m densify => ~96 k vertices).  At N>1 the workload is
 BASELINE.json configs[3]: the config-3 site (320 frames x 6 cameras, ~767 k vertices) SHARDED BY FRAME over
 the N GPUs (strong scaling), and a step ends with every frame of the site assembled in the HBM of every
-rank — the assembly is inside the timed region.  The ranks exchange the lit 8-pixel chunks through peer
-memory while the raster runs (cama_b200/shard.py::PeerExchange, csrc/peer.cu) instead of all-gathering
-the dense frames; the literal NCCL all-gather of the uint8 frames is timed beside it (`dense_allgather`),
-as are the compute-only figure and one GPU rendering the same site alone.
+rank — the assembly is inside the timed region.  The ranks exchange records through peer memory
+(cama_b200/shard.py, csrc/peer.cu: up to 4 GPUs the centre records, after which every rank rasters every
+frame; beyond, the lit 8-pixel chunks, mirrored by the raster while it runs and expanded into zero-filled
+frames) instead of all-gathering the dense frames; the literal NCCL all-gather of the uint8 frames is timed
+beside it (`dense_allgather`), as are the compute-only figure and one GPU rendering the same site alone,
+and every rank checks its assembled frames byte for byte against its own single-GPU render (`verified`).
 
 One JSON line on rank 0:
   value        cam-frames/s, inputs (vertices, poses) resident in HBM, frames left in HBM; the K steps are dealt
@@ -21,7 +23,9 @@ One JSON line on rank 0:
                the poses, render, lit-chunk records back over PCIe and drawn into the host frames
                (e2e.dense: every frame byte copied back instead)
   roofline     the raster kernel (writes every frame byte once) against the measured HBM peak
-  cpu_baseline the NumPy/OpenCV oracle (= the reference's loop) on this box's host cores
+  config3      the site of BASELINE.json configs[2] on this GPU: ms per site, raster and whole-step roofline
+  dropin       the per-frame calls unmodified main.py makes (yield_frame, project_all_camera, render_maps)
+  cpu_baseline the NumPy/OpenCV oracle (= the reference's loop) on this box's host cores (+ with_images)
 `--impl reference` times that CPU path alone and prints the same line shape.
 """
 from __future__ import annotations

@@ -37,7 +37,7 @@ class CamaError(RuntimeError):
 
 
 class CapacityError(CamaError):
-    """The record pool of a clip render overflowed; rerun with stats.record_capacity_needed."""
+    """A record list of a clip render overflowed; rerun with stats.record_capacity_needed."""
 
 
 class ClipDesc(Structure):

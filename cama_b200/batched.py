@@ -192,7 +192,7 @@ class ClipRenderer:
         w2c_dev     torch float32 [F,16] (or [F,4,4]) on this device
         out         optional torch uint8 [F,C,H,W,3] to write into
         background  optional torch uint8 [F,C,H,W,3] composited under the overlay (may be ``out``)
-        check       read the record counters back (synchronises) and rerun with a larger pool if a
+        check       read the record counters back (synchronises) and rerun with longer record lists if one
                     frame overflowed; with ``check=False`` the call is fully asynchronous
         debug       also return per-instance crop / visibility counts (and dense (v,u) if want_vu)
         """
@@ -307,7 +307,7 @@ class ClipRenderer:
                 retry = True
             if not retry:
                 return records, int(stats.overlay_records), fmt
-        raise N.CamaError(N.CAMA_E_CAPACITY, "record pools kept overflowing")
+        raise N.CamaError(N.CAMA_E_CAPACITY, "record lists kept overflowing")
 
 
     def enqueue_overlay(self, res, w2c_dev, overlay, mode="auto", capacity=None, lane=0):
@@ -315,7 +315,7 @@ class ClipRenderer:
         returns at once (no counter is read back; the caller checks the count against its capacity later).
 
         overlay   dict(records_ptr, count_ptr, capacity, fmt[, mirrors, image_base]) — see ``cama_clip_desc``
-        capacity  centre records per frame of the internal pool (default: what earlier checked renders of this
+        capacity  centre records per (frame, camera, band) list (default: what earlier checked renders of this
                   resident / frame count settled on)
         """
         n_frames = int(w2c_dev.shape[0])

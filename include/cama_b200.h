@@ -321,7 +321,7 @@ int cama_clip_workspace_bytes(const cama_clip_desc *desc, size_t *bytes);
 int cama_clip_render(cama_ctx *ctx, const cama_clip_desc *desc, void *workspace, size_t workspace_bytes,
                      void *stream);
 /* Synchronises `stream` and reads back the counters of the last cama_clip_render that used this
- * workspace.  Returns CAMA_E_CAPACITY when the record pool overflowed. */
+ * workspace.  Returns CAMA_E_CAPACITY when a record list overflowed. */
 int cama_clip_stats_read(cama_ctx *ctx, const cama_clip_desc *desc, const void *workspace, void *stream,
                          cama_clip_stats *stats);
 
