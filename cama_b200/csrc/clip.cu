@@ -257,11 +257,10 @@ __device__ __forceinline__ bool candidate_pixel(bool cand, double qx, double qy,
     return vis;
 }
 
-// Records are staged in shared memory, per warp, and flushed to the global pool >= 128 at a time, so
-// the only global atomic whose result is waited for is one reservation per flush; the per-bucket
-// counts are fire-and-forget reductions, and no block-level barrier is involved.  (A version that
-// reserved a pool slot and a bucket rank with returning atomics per warp spent a quarter of its
-// time waiting for them; one that staged per CTA spent a third of it in the per-frame barrier.)
+// Records {list, payload} are staged in shared memory, per warp, and flushed to their band lists >= 128 at a time
+// (stage_flush): the returning atomics that reserve the places are issued per flush round, not per append, and no
+// block-level barrier is involved.  (A version that reserved with returning atomics per warp and append spent a
+// quarter of its time waiting for them; one that staged per CTA spent a third of it in the per-frame barrier.)
 #ifndef CAMA_PIPE_FRAMES_DEFAULT
 #define CAMA_PIPE_FRAMES_DEFAULT 160
 #endif
@@ -281,12 +280,12 @@ struct GeoStage {                          // one per warp
     unsigned pad[3];
 };
 
-__device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, bool pred, unsigned bucket, unsigned payload) {
+__device__ __forceinline__ void warp_append(const ClipArgs &a, GeoStage &st, bool pred, unsigned list, unsigned payload) {
     const unsigned mask = __ballot_sync(kFull, pred);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
     const unsigned slot = st.count + __popc(mask & ((1u << lane) - 1u));                  // the warp owns its stage: no atomic
-    if (pred) st.rec[slot] = make_uint2(bucket, payload);
+    if (pred) st.rec[slot] = make_uint2(list, payload);
     __syncwarp();
     if (lane == 0) st.count += (unsigned)__popc(mask);
     __syncwarp();
@@ -687,7 +686,7 @@ struct RasterArgs {
     const unsigned *lut;
     const uint8_t *bg;
     uint8_t *frames;
-    const unsigned *lists;                 // [4][n_items]: buckets with >= 2048 / >= 256 / >= 1 records (claimed dynamically, in this order) | empty buckets (dealt round-robin)
+    const unsigned *lists;                 // [4][n_items]: bands whose list holds >= 2048 / >= 256 / >= 1 records (claimed dynamically, in this order) | bands with an empty list (dealt round-robin)
     const unsigned *list_counts;           // [4]
     unsigned *work_counter;                // claims of active buckets beyond the first three of every CTA
     unsigned *empty_counter;               // claims of the dynamically dealt empty buckets
@@ -1250,7 +1249,7 @@ struct ClipPlan {
     long long n_lists;
     size_t raster_smem;
     // workspace offsets
-    size_t off_zero, zero_bytes;     // region memset to 0 each call: counters | hist
+    size_t off_zero, zero_bytes;     // region cleared by prep each call: counters | list cursors (BINNED, lists inside the workspace)
     size_t off_counter, off_cursor, off_stats, off_w2c64, off_lut, off_records, off_plane, off_worklist, off_lists;
     long long geo_units;
     size_t total;
@@ -1330,7 +1329,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
     p.off_lut = take(sizeof(unsigned) * ((size_t)d->n_instances + 1));
     p.geo_units = ((d->n_vertices + kGeoThreads - 1) / kGeoThreads) * ((d->n_frames + kGeoFrames - 1) / kGeoFrames);
     p.off_worklist = take(sizeof(unsigned long long) * (size_t)std::max<long long>(p.geo_units, 1));
-    p.off_zero = off;                                                      // cleared by prep every call: counters | hist (BINNED)
+    p.off_zero = off;                                                      // cleared by prep every call: counters | list cursors (BINNED)
     p.off_counter = take(256);
     p.zero_bytes = off - p.off_zero;
     if (mode == CAMA_CLIP_PLANE) {
@@ -1342,7 +1341,7 @@ int make_plan(const cama_clip_desc *d, ClipPlan &p, bool allow_groups = true) {
         p.n_strips = (W + kSegPx - 1) / kSegPx;
 
         const long long nb = (long long)d->n_frames * d->n_cams * p.n_bands;
-        CAMA_REQUIRE(nb < INT_MAX, "too many buckets");
+        CAMA_REQUIRE(nb < INT_MAX, "too many (frame, camera, band) work items");
         p.n_buckets = (int)nb;
         // band groups: a record stores its row inside the group (+ 2 halo rows either side) in 16 - x_bits bits
         static const int max_group_bands = getenv("CAMA_GROUP_BANDS") ? std::max(1, atoi(getenv("CAMA_GROUP_BANDS"))) : kDefaultGroupBands;   // tuning knob
