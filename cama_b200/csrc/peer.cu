@@ -155,18 +155,14 @@ __global__ void __launch_bounds__(256) peer_cursor_copy_kernel(const unsigned *_
 // 8 GPUs and took 0.8 ms; this copy moves the same 55 MB in ~0.1 ms.)  capacity % 4 == 0, arrays 16-byte aligned.
 __global__ void __launch_bounds__(256) peer_list_push_kernel(const unsigned *__restrict__ own_records, const unsigned *__restrict__ own_cursor, long long first,
                                                             long long count, unsigned capacity, PeerPtrs peer_records, int n_peers) {
-    // one WARP per (list, peer): blockIdx.y = peer, so the stores to different peers leave from different CTAs at the
-    // same time (a list holds a few hundred records: a CTA per list left three quarters of its threads idle; one warp
-    // storing a list to all peers in turn serialised the links); 512 contiguous bytes per warp store.  The list is read
-    // once per peer, from L2.
+    // one WARP per list (a list holds a few hundred records: a CTA per list left three quarters of its threads idle and
+    // the lists of a CTA in a queue); 512 contiguous bytes per warp store and peer
     const int lane = threadIdx.x & 31;
     const long long warps = (long long)gridDim.x * 8;
-    unsigned *dst_base = static_cast<unsigned *>(peer_records.p[blockIdx.y]);
     for (long long l = first + (long long)blockIdx.x * 8 + (threadIdx.x >> 5); l < first + count; l += warps) {
         const unsigned n = min(own_cursor[l], capacity);
         const unsigned n4 = (n + 3u) >> 2;                                   // (capacity % 4 == 0: the padding stays inside the list)
         const uint4 *src = reinterpret_cast<const uint4 *>(own_records + (size_t)l * capacity);
-        uint4 *dst = reinterpret_cast<uint4 *>(dst_base + (size_t)l * capacity);
         for (unsigned i0 = 0; i0 < n4; i0 += 128u) {                          // four 16-byte loads in flight per lane
             uint4 v[4];
 #pragma unroll
@@ -177,7 +173,8 @@ __global__ void __launch_bounds__(256) peer_list_push_kernel(const unsigned *__r
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned i = i0 + 32u * k + lane;
-                if (i < n4) dst[i] = v[k];
+                if (i < n4)
+                    for (int p = 0; p < n_peers; ++p) reinterpret_cast<uint4 *>(static_cast<unsigned *>(peer_records.p[p]) + (size_t)l * capacity)[i] = v[k];
             }
         }
     }
@@ -321,8 +318,7 @@ int cama_peer_publish_lists(cama_ctx *ctx, const void *own_records, const uint32
             CAMA_REQUIRE(peer_records[i] && ((uintptr_t)peer_records[i] & 15) == 0, "peer_records[%d] is NULL or misaligned", i);
             pr.p[i] = peer_records[i];
         }
-        const dim3 grid((unsigned)std::min<long long>((count + 7) / 8, (long long)ctx->sm_count * 8), (unsigned)n_peers, 1);
-        peer_list_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        peer_list_push_kernel<<<(unsigned)std::min<long long>((count + 7) / 8, (long long)ctx->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
             static_cast<const unsigned *>(own_records), own_cursor, first, count, (unsigned)capacity, pr, n_peers);
         CAMA_LAUNCHED(ctx);
     }
