@@ -109,3 +109,80 @@ def test_peer_mailbox_layout():
         assert slot % 256 == 0 and slot >= 256 + cap * rec and total == shard.PARITIES * world * slot
         starts = sorted(offset(p, s) for p in range(shard.PARITIES) for s in range(world))
         assert starts == [k * slot for k in range(shard.PARITIES * world)]
+
+
+# ---------------------------------------------------------------------------------------------- SiteAssembler: one decision on all ranks
+class _StubRuntime:
+    device = torch.device("cpu")
+
+
+class _StubRenderer:
+    n_cams, height, width = 6, 540, 960
+
+    def __init__(self, rank):
+        self.rank, self.last_stats = rank, None
+
+    def render_overlay(self, res, w2c_dev, mode="auto"):
+        n_frames = int(w2c_dev.shape[0])
+        if n_frames == 0:                                    # (a rank with an empty block renders nothing and has no statistics)
+            return None, 0, 1
+        self.last_stats = {"record_capacity": 8192, "record_capacity_needed": 5000 + 1000 * self.rank, "lists_per_image": 34}
+        return None, 1000 * (self.rank + 1), 1
+
+
+class _StubReproject:
+    def __init__(self, rank, n_frames):
+        self.renderer, self.rt, self.n = _StubRenderer(rank), _StubRuntime(), n_frames
+
+    def resident(self, dataset):
+        return object()
+
+    def frame_poses(self, dataset):
+        return list(range(1, self.n + 1)), np.zeros((self.n, 16), np.float32)
+
+
+def _assembler_worker(rank, world, port, n_frames, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        made = {}
+
+        class _StubExchange:                                 # stands in for ListExchange / PeerExchange (both need CUDA IPC)
+            available, error = True, None
+
+            def __init__(self, *args, **kwargs):
+                made["args"] = args
+
+        saved = shard.ListExchange, shard.PeerExchange
+        shard.ListExchange = shard.PeerExchange = _StubExchange
+        try:
+            asm = shard.SiteAssembler(_StubReproject(rank, n_frames), "nuscenes", exchange="lists")
+        finally:
+            shard.ListExchange, shard.PeerExchange = saved
+        # args of ListExchange: (rt, renderer, res, n_frames_total, capacity, lists_per_image)
+        results[rank] = (asm.kind, asm.lo, asm.hi, made["args"][3], made["args"][4], made["args"][5])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(3, 2), (2, 5)])
+def test_site_assembler_decides_collectively(world, n_frames):
+    """Every rank must build the same exchange with the same list capacity — also a rank whose frame block is empty
+    (3 ranks, 2 frames) and therefore has no statistics of its own: a rank deciding alone would wait for peers that took
+    the other path."""
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        results = manager.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_assembler_worker, args=(r, world, port, n_frames, results)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=120)
+        assert all(p.exitcode == 0 for p in procs)
+        got = [results[r] for r in range(world)]
+    assert {g[0] for g in got} == {"lists"}
+    assert [(g[1], g[2]) for g in got] == [shard.frame_block(n_frames, r, world) for r in range(world)]
+    ranks_with_frames = [r for r in range(world) if shard.frame_block(n_frames, r, world)[1] > shard.frame_block(n_frames, r, world)[0]]
+    needed = 5000 + 1000 * max(ranks_with_frames)
+    assert len({g[3:] for g in got}) == 1 and got[0][3] == n_frames and got[0][4] == max(8192, int(needed * 1.1) + 256) and got[0][5] == 34
